@@ -1,0 +1,465 @@
+// plbert_b200 — bf16 GEMM on the 5th-generation tensor cores (tcgen05.mma, accumulators in TMEM),
+// operands staged by TMA into a 128-byte-swizzled shared-memory ring.
+//
+// One persistent, warp-specialised kernel template serves the three GEMM shapes of an nn.Linear
+// (HF modeling_albert.py:180-182,198-200,239-241,276; R/model.py:15-16):
+//
+//   FWD   (A K-major,  B K-major ):  C[M,N]  = A[M,K] W[N,K]^T
+//   DGRAD (A K-major,  B MN-major):  C[M,N]  = A[M,K] W[K,N]
+//   WGRAD (A MN-major, B MN-major):  C[M,N] += A[K,M]^T B[K,N]   (fp32 atomics, split-K)
+//
+// CTA = 6 warps: warp 0 TMA producer, warp 1 TMEM owner + single-thread MMA issuer, warps 2..5
+// epilogue (one accumulator row per thread, tcgen05.ld 32x32b).  Tile 128 x 256 x 64, fp32
+// accumulators double-buffered in TMEM (2 x 256 columns) so the epilogue of unit i overlaps the
+// main loop of unit i+1.  Epilogue output goes registers -> swizzled smem -> TMA store; a residual /
+// pre-activation operand comes in by TMA into the same staging buffer and is updated in place.
+#include "common.cuh"
+
+#include <mutex>
+#include <unordered_map>
+
+namespace plb {
+
+namespace {
+
+constexpr int BM = 128;
+constexpr int BN = 256;
+constexpr int BK = 64;
+constexpr int UMMA_K = 16;
+constexpr int A_TILE_BYTES = BM * BK * 2;       // 16 KB
+constexpr int B_TILE_BYTES = BN * BK * 2;       // 32 KB
+constexpr int STAGE_BYTES = A_TILE_BYTES + B_TILE_BYTES;
+constexpr int EPI_COLS = 64;                    // columns per epilogue chunk (128 B of bf16)
+constexpr int EPI_BUF_BYTES = BM * EPI_COLS * 2;  // 16 KB
+constexpr int MN_BOX_BYTES = 64 * 64 * 2;       // one MN-major TMA box: 64 K-rows x 64 elements
+constexpr int NUM_THREADS = 192;
+constexpr int EPI_THREADS = 128;
+constexpr int TMEM_COLS = 512;
+
+enum Epi : int { kNone = 0, kResidual = 1, kGelu = 2, kGeluBwd = 3, kAtomicF32 = 4 };
+
+struct GemmParams {
+  int M, N, K;
+  int m_tiles, n_tiles, splits;
+  int k_iters;        // ceil(K / BK)
+  int k_per_split;    // k iterations per split
+  int num_units;      // m_tiles * n_tiles * splits
+  const float* bias;  // [N] or null
+  float* c_f32;       // WGRAD output
+  int ldc;
+};
+
+template <int kStages, int kBufs>
+struct SmemLayout {
+  static constexpr int kStageOff = 0;
+  static constexpr int kEpiOff = kStages * STAGE_BYTES;
+  static constexpr int kBarOff = kEpiOff + kBufs * EPI_BUF_BYTES;
+  // full[kStages], empty[kStages], tmem_full[2], tmem_empty[2], epi_in[kBufs], tmem ptr
+  static constexpr int kNumBars = 2 * kStages + 4 + kBufs;
+  static constexpr int kBytes = kBarOff + kNumBars * 8 + 16;
+  static constexpr int kAlloc = kBytes + 1024;  // slack for manual 1024 B alignment
+};
+
+__device__ __forceinline__ void unit_coords(const GemmParams& p, int u, int& m_blk, int& n_blk, int& k_begin,
+                                            int& k_end) {
+  const int tiles = p.m_tiles * p.n_tiles;
+  const int tile = u % tiles;
+  const int split = u / tiles;
+  n_blk = tile % p.n_tiles;
+  m_blk = tile / p.n_tiles;
+  k_begin = split * p.k_per_split;
+  k_end = min(k_begin + p.k_per_split, p.k_iters);
+}
+
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory"); }
+
+template <bool kAMn, bool kBMn, int kEpi, int kStages, int kBufs>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
+            const __grid_constant__ CUtensorMap tm_c, const __grid_constant__ CUtensorMap tm_aux_in,
+            const __grid_constant__ CUtensorMap tm_aux_out, const GemmParams p) {
+  using L = SmemLayout<kStages, kBufs>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::kBarOff);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + kStages;
+  uint64_t* tmem_full = bars + 2 * kStages;
+  uint64_t* tmem_empty = bars + 2 * kStages + 2;
+  uint64_t* epi_in = bars + 2 * kStages + 4;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + L::kNumBars);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tm_a);
+    tma_prefetch_desc(&tm_b);
+    if (kEpi != kAtomicF32) tma_prefetch_desc(&tm_c);
+    for (int i = 0; i < kStages; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full[i], 1);
+      mbar_init(&tmem_empty[i], 4);  // one arrive per epilogue warp
+    }
+    for (int i = 0; i < kBufs; ++i) mbar_init(&epi_in[i], 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_ptr_smem, TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp == 0) {
+    // =========================== TMA producer ===========================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int u = blockIdx.x; u < p.num_units; u += gridDim.x) {
+        int m_blk, n_blk, k_begin, k_end;
+        unit_coords(p, u, m_blk, n_blk, k_begin, k_end);
+        const int m0 = m_blk * BM, n0 = n_blk * BN;
+        for (int kb = k_begin; kb < k_end; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * STAGE_BYTES;
+          uint8_t* sb = sa + A_TILE_BYTES;
+          mbar_arrive_expect_tx(&full_bar[stage], STAGE_BYTES);
+          if (!kAMn) {
+            tma_load_2d(sa, &tm_a, &full_bar[stage], kb * BK, m0);
+          } else {
+#pragma unroll
+            for (int j = 0; j < BM / 64; ++j)
+              tma_load_2d(sa + j * MN_BOX_BYTES, &tm_a, &full_bar[stage], m0 + j * 64, kb * BK);
+          }
+          if (!kBMn) {
+            tma_load_2d(sb, &tm_b, &full_bar[stage], kb * BK, n0);
+          } else {
+#pragma unroll
+            for (int j = 0; j < BN / 64; ++j)
+              tma_load_2d(sb + j * MN_BOX_BYTES, &tm_b, &full_bar[stage], n0 + j * 64, kb * BK);
+          }
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // =========================== MMA issuer ===========================
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, kAMn ? 1 : 0, kBMn ? 1 : 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int u = blockIdx.x; u < p.num_units; u += gridDim.x) {
+        int m_blk, n_blk, k_begin, k_end;
+        unit_coords(p, u, m_blk, n_blk, k_begin, k_end);
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + acc * BN;
+        for (int kb = k_begin; kb < k_end; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
+          const uint32_t sb = sa + A_TILE_BYTES;
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            const uint64_t da = kAMn ? umma_smem_desc(sa + k * (UMMA_K * 128), MN_BOX_BYTES, 1024)
+                                     : umma_smem_desc(sa + k * (UMMA_K * 2), 16, 1024);
+            const uint64_t db = kBMn ? umma_smem_desc(sb + k * (UMMA_K * 128), MN_BOX_BYTES, 1024)
+                                     : umma_smem_desc(sb + k * (UMMA_K * 2), 16, 1024);
+            umma_bf16(tmem_d, da, db, idesc, (kb > k_begin || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs have read it
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tmem_full[acc]);  // accumulator complete
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+    __syncwarp();
+  } else {
+    // =========================== epilogue (warps 2..5) ===========================
+    const int quad = warp & 3;             // TMEM lane quadrant this warp may read
+    const int row = quad * 32 + lane;      // accumulator row owned by this thread
+    const bool leader = (threadIdx.x == 64);
+    uint8_t* epi_smem = smem + L::kEpiOff;
+    constexpr bool kHasAuxIn = (kEpi == kResidual || kEpi == kGeluBwd);
+    constexpr bool kDual = (kEpi == kGelu);
+    constexpr int kSlots = kDual ? kBufs / 2 : kBufs;
+    static_assert(kEpi == kAtomicF32 || kSlots >= 2, "need at least two staging slots");
+
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    uint32_t seq = 0;  // running chunk sequence number (staging slot = seq % kSlots)
+
+    // look-ahead iterator for the aux-in prefetch (leader only)
+    int la_u = blockIdx.x, la_c = 0;
+    uint32_t la_seq = 0;
+    auto la_issue = [&]() {
+      // issue the aux load for the next not-yet-issued chunk, if any
+      while (la_u < p.num_units) {
+        int m_blk, n_blk, k_begin, k_end;
+        unit_coords(p, la_u, m_blk, n_blk, k_begin, k_end);
+        const int n0 = n_blk * BN + la_c * EPI_COLS;
+        if (la_c < BN / EPI_COLS && n0 < p.N) {
+          const int slot = la_seq % kSlots;
+          mbar_arrive_expect_tx(&epi_in[slot], EPI_BUF_BYTES);
+          tma_load_2d(epi_smem + slot * EPI_BUF_BYTES, &tm_aux_in, &epi_in[slot], n0, m_blk * BM);
+          ++la_seq;
+          ++la_c;
+          return;
+        }
+        la_u += gridDim.x;
+        la_c = 0;
+      }
+    };
+    if (kHasAuxIn && leader) {
+      for (int i = 0; i < kSlots - 1; ++i) la_issue();
+    }
+
+    for (int u = blockIdx.x; u < p.num_units; u += gridDim.x) {
+      int m_blk, n_blk, k_begin, k_end;
+      unit_coords(p, u, m_blk, n_blk, k_begin, k_end);
+      const int m0 = m_blk * BM, n0 = n_blk * BN;
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BN;
+
+      if (kEpi == kAtomicF32) {
+        const int m = m0 + row;
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; ++c) {
+          if (n0 + c * 32 >= p.N) break;
+          uint32_t v[32];
+          tmem_ld_32x32(taddr + c * 32, v);
+          tmem_ld_wait();
+          if (m < p.M) {
+            float* dst = p.c_f32 + static_cast<size_t>(m) * p.ldc + n0 + c * 32;
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) {
+              const int n = n0 + c * 32 + i;
+              if (n + 3 < p.N && ((reinterpret_cast<uintptr_t>(dst + i) & 15) == 0)) {
+                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + i),
+                             "f"(__uint_as_float(v[i])), "f"(__uint_as_float(v[i + 1])),
+                             "f"(__uint_as_float(v[i + 2])), "f"(__uint_as_float(v[i + 3]))
+                             : "memory");
+              } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                  if (n + j < p.N) atomicAdd(dst + i + j, __uint_as_float(v[i + j]));
+              }
+            }
+          }
+        }
+      } else {
+#pragma unroll 1
+        for (int c = 0; c < BN / EPI_COLS; ++c) {
+          const int nc = n0 + c * EPI_COLS;
+          if (nc >= p.N) break;
+          const int slot = seq % kSlots;
+          uint8_t* buf = epi_smem + (kDual ? 2 * slot : slot) * EPI_BUF_BYTES;
+          uint8_t* my_row = buf + row * 128;
+
+          uint32_t v0[32], v1[32];
+          tmem_ld_32x32(taddr + c * EPI_COLS, v0);
+          tmem_ld_32x32(taddr + c * EPI_COLS + 32, v1);
+          if (kHasAuxIn) mbar_wait(&epi_in[slot], (seq / kSlots) & 1);
+          tmem_ld_wait();
+
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {  // eight 16-byte pieces of this thread's 128-byte row
+            float f[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(j < 4 ? v0[j * 8 + i] : v1[(j - 4) * 8 + i]);
+            if (p.bias != nullptr) {
+              const int n = nc + j * 8;
+              if (n + 7 < p.N) {
+                const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + n));
+                const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + n + 4));
+                f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
+                f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
+              } else {
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+                  if (n + i < p.N) f[i] += __ldg(p.bias + n + i);
+              }
+            }
+            uint4* piece = reinterpret_cast<uint4*>(my_row + ((j ^ (row & 7)) << 4));
+            if (kHasAuxIn) {
+              const uint4 a = *piece;
+              const uint32_t aw[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const float lo = bf16_lo(aw[i]), hi = bf16_hi(aw[i]);
+                if (kEpi == kResidual) {
+                  f[2 * i] += lo;
+                  f[2 * i + 1] += hi;
+                } else {  // kGeluBwd: acc * gelu'(u)
+                  f[2 * i] *= gelu_new_grad(lo);
+                  f[2 * i + 1] *= gelu_new_grad(hi);
+                }
+              }
+            }
+            if (kDual) {
+              // pre-activation u goes to the second buffer of the pair, gelu(u) to the first
+              uint4 pu;
+              pu.x = pack_bf16x2(f[0], f[1]); pu.y = pack_bf16x2(f[2], f[3]);
+              pu.z = pack_bf16x2(f[4], f[5]); pu.w = pack_bf16x2(f[6], f[7]);
+              *reinterpret_cast<uint4*>(my_row + EPI_BUF_BYTES + ((j ^ (row & 7)) << 4)) = pu;
+              // gelu is evaluated on the bf16-rounded u so that forward and backward see the same value
+              const uint32_t uw[4] = {pu.x, pu.y, pu.z, pu.w};
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                f[2 * i] = gelu_new_fwd(bf16_lo(uw[i]));
+                f[2 * i + 1] = gelu_new_fwd(bf16_hi(uw[i]));
+              }
+            }
+            uint4 o;
+            o.x = pack_bf16x2(f[0], f[1]); o.y = pack_bf16x2(f[2], f[3]);
+            o.z = pack_bf16x2(f[4], f[5]); o.w = pack_bf16x2(f[6], f[7]);
+            *piece = o;
+          }
+          fence_proxy_async_smem();
+          if (leader && !kHasAuxIn) {
+            // by this barrier the slot chunk seq+1 will write must have been read out by its last store
+            bulk_wait_read<(kSlots >= 2 ? kSlots - 2 : 0)>();
+          }
+          epi_bar_sync();
+          if (leader) {
+            tma_store_2d(&tm_c, buf, nc, m0);
+            if (kDual) tma_store_2d(&tm_aux_out, buf + EPI_BUF_BYTES, nc, m0);
+            bulk_commit();
+            if (kHasAuxIn) {
+              bulk_wait_read<1>();  // store seq-1 has left its slot -> prefetch chunk seq+kSlots-1 into it
+              la_issue();
+            }
+          }
+          ++seq;
+        }
+      }
+      // accumulator drained -> hand the TMEM buffer back to the MMA warp
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+    if (leader && kEpi != kAtomicF32) bulk_wait<0>();  // all stores globally visible before exit
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+template <bool kAMn, bool kBMn, int kEpi, int kStages, int kBufs>
+int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const CUtensorMap& tin,
+           const CUtensorMap& tout, const GemmParams& p, cudaStream_t stream) {
+  using L = SmemLayout<kStages, kBufs>;
+  auto kern = gemm_kernel<kAMn, kBMn, kEpi, kStages, kBufs>;
+  static bool configured = false;  // benign race: the attribute call is idempotent
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kAlloc);
+    PLB_REQUIRE(e == cudaSuccess, PLB_ERR_CUDA, "gemm: cudaFuncSetAttribute(smem=%d): %s", L::kAlloc,
+                cudaGetErrorString(e));
+    configured = true;
+  }
+  const int grid = p.num_units < sm_count() ? p.num_units : sm_count();
+  kern<<<grid, NUM_THREADS, L::kAlloc, stream>>>(ta, tb, tc, tin, tout, p);
+  return check_launch("plb_gemm_bf16");
+}
+
+}  // namespace
+
+}  // namespace plb
+
+using namespace plb;
+
+extern "C" int plb_gemm_bf16(int op, int epilogue, int M, int N, int K, const void* A, int lda, const void* B,
+                             int ldb, void* C, int ldc, const float* bias, const void* aux_in, int ld_aux_in,
+                             void* aux_out, int ld_aux_out, plb_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  PLB_REQUIRE(M > 0 && N > 0 && K > 0, PLB_ERR_ARG, "gemm: bad shape M=%d N=%d K=%d", M, N, K);
+  PLB_REQUIRE(A && B && C, PLB_ERR_ARG, "gemm: null operand");
+  PLB_REQUIRE(op >= PLB_GEMM_FWD && op <= PLB_GEMM_WGRAD, PLB_ERR_ARG, "gemm: bad op %d", op);
+  PLB_REQUIRE((lda % 8) == 0 && (ldb % 8) == 0, PLB_ERR_ARG, "gemm: lda/ldb must be multiples of 8 (got %d, %d)",
+              lda, ldb);
+  PLB_REQUIRE(((uintptr_t)A % 16) == 0 && ((uintptr_t)B % 16) == 0, PLB_ERR_ARG, "gemm: A/B must be 16-byte aligned");
+
+  GemmParams p{};
+  p.M = M; p.N = N; p.K = K;
+  p.m_tiles = (M + BM - 1) / BM;
+  p.n_tiles = (N + BN - 1) / BN;
+  p.k_iters = (K + BK - 1) / BK;
+  p.bias = bias;
+  p.splits = 1;
+
+  CUtensorMap ta, tb, tc, tin, tout;
+  bool ok;
+  if (op == PLB_GEMM_FWD) {
+    ok = tensor_map_bf16(&ta, A, M, K, lda, BM, 64) && tensor_map_bf16(&tb, B, N, K, ldb, BN, 64);
+  } else if (op == PLB_GEMM_DGRAD) {
+    ok = tensor_map_bf16(&ta, A, M, K, lda, BM, 64) && tensor_map_bf16(&tb, B, K, N, ldb, 64, 64);
+  } else {
+    ok = tensor_map_bf16(&ta, A, K, M, lda, 64, 64) && tensor_map_bf16(&tb, B, K, N, ldb, 64, 64);
+  }
+  if (!ok) return PLB_ERR_CUDA;
+
+  if (op == PLB_GEMM_WGRAD) {
+    PLB_REQUIRE(epilogue == PLB_EPI_NONE && bias == nullptr, PLB_ERR_ARG, "gemm: WGRAD takes no epilogue/bias");
+    PLB_REQUIRE(ldc >= N, PLB_ERR_ARG, "gemm: ldc < N");
+    // split K so that every SM gets about two units; each unit keeps at least 8 k-iterations
+    const int tiles = p.m_tiles * p.n_tiles;
+    int splits = (2 * sm_count() + tiles - 1) / tiles;
+    const int max_splits = p.k_iters / 8 > 0 ? p.k_iters / 8 : 1;
+    if (splits > max_splits) splits = max_splits;
+    if (splits < 1) splits = 1;
+    p.k_per_split = (p.k_iters + splits - 1) / splits;
+    p.splits = (p.k_iters + p.k_per_split - 1) / p.k_per_split;
+    p.num_units = tiles * p.splits;
+    p.c_f32 = static_cast<float*>(C);
+    p.ldc = ldc;
+    return launch<true, true, kAtomicF32, 4, 2>(ta, tb, ta, ta, ta, p, stream);
+  }
+
+  PLB_REQUIRE((ldc % 8) == 0 && ((uintptr_t)C % 16) == 0, PLB_ERR_ARG, "gemm: C must be 16-byte aligned, ldc %% 8 == 0");
+  p.k_per_split = p.k_iters;
+  p.num_units = p.m_tiles * p.n_tiles;
+  if (!tensor_map_bf16(&tc, C, M, N, ldc, BM, EPI_COLS)) return PLB_ERR_CUDA;
+  tin = tout = tc;
+  if (epilogue == PLB_EPI_RESIDUAL || epilogue == PLB_EPI_GELU_BWD) {
+    PLB_REQUIRE(aux_in && (ld_aux_in % 8) == 0 && ((uintptr_t)aux_in % 16) == 0, PLB_ERR_ARG,
+                "gemm: epilogue %d needs an aligned aux_in", epilogue);
+    if (!tensor_map_bf16(&tin, aux_in, M, N, ld_aux_in, BM, EPI_COLS)) return PLB_ERR_CUDA;
+  }
+  if (epilogue == PLB_EPI_GELU) {
+    PLB_REQUIRE(aux_out && (ld_aux_out % 8) == 0 && ((uintptr_t)aux_out % 16) == 0, PLB_ERR_ARG,
+                "gemm: GELU epilogue needs an aligned aux_out");
+    if (!tensor_map_bf16(&tout, aux_out, M, N, ld_aux_out, BM, EPI_COLS)) return PLB_ERR_CUDA;
+  }
+
+  if (op == PLB_GEMM_FWD) {
+    switch (epilogue) {
+      case PLB_EPI_NONE:     return launch<false, false, kNone, 4, 2>(ta, tb, tc, tin, tout, p, stream);
+      case PLB_EPI_RESIDUAL: return launch<false, false, kResidual, 3, 4>(ta, tb, tc, tin, tout, p, stream);
+      case PLB_EPI_GELU:     return launch<false, false, kGelu, 3, 4>(ta, tb, tc, tin, tout, p, stream);
+      default: break;
+    }
+  } else {
+    switch (epilogue) {
+      case PLB_EPI_NONE:     return launch<false, true, kNone, 4, 2>(ta, tb, tc, tin, tout, p, stream);
+      case PLB_EPI_RESIDUAL: return launch<false, true, kResidual, 3, 4>(ta, tb, tc, tin, tout, p, stream);
+      case PLB_EPI_GELU_BWD: return launch<false, true, kGeluBwd, 3, 4>(ta, tb, tc, tin, tout, p, stream);
+      default: break;
+    }
+  }
+  set_error("gemm: op %d does not support epilogue %d", op, epilogue);
+  return PLB_ERR_UNSUPPORTED;
+}
