@@ -90,6 +90,77 @@ int plb_gemm_bf16_check(int op, int epilogue, int M, int N, int K,
                         void* aux_out, int ld_aux_out,
                         plb_stream_t stream);
 
+/* ---- a3: embeddings -------------------------------------------------------------------------------
+ * HF/:71-110 AlbertEmbeddings.forward:  e = LayerNorm(word[ids[t]] + type[0] + pos_table[pos[t]])
+ * ids/pos: int32 [T] (pos restarts at 0 per sequence, HF/:85-86).  Tables are fp32 [*, E]; `type0` points at
+ * row 0 of token_type_embeddings.  out: bf16 [T, E]; stats: fp32 [T, 2] = (mean, rstd) saved for backward.
+ * Backward: `de` = gradient of the LN output (bf16 [T, E]); accumulates (+=, fp32 atomics) into dword [V, E]
+ * (row pad_id skipped: padding_idx, HF/:56), dpos, dtype0 [E], dln_w, dln_b. */
+int plb_embed_ln_fwd(const int32_t* ids, const int32_t* pos, int T, int E,
+                     const float* word, const float* posemb, const float* type0,
+                     const float* ln_w, const float* ln_b, float eps,
+                     void* out, float* stats, plb_stream_t stream);
+int plb_embed_ln_bwd(const void* de, const int32_t* ids, const int32_t* pos, int T, int E,
+                     const float* word, const float* posemb, const float* type0,
+                     const float* ln_w, const float* stats, int pad_id,
+                     float* dword, float* dpos, float* dtype0, float* dln_w, float* dln_b,
+                     plb_stream_t stream);
+
+/* ---- a5/a6: LayerNorm over bf16 rows ----------------------------------------------------------------
+ * HF/:202 attention.LayerNorm and HF/:235 full_layer_layer_norm (the residual add is fused into the producing
+ * GEMM's epilogue, so `z` is already x + sublayer(x)).  y = (z - mean) * rstd * w + b, biased variance,
+ * eps inside the sqrt.  stats: fp32 [T, 2] = (mean, rstd).
+ * Backward: dz = rstd * (g - mean(g) - xhat * mean(g * xhat)), g = dy * w; dw_accum += sum dy * xhat;
+ * db_accum += sum dy; if colsum_accum != NULL, colsum_accum += sum_rows dz (the bias gradient of the Linear
+ * that produced z). */
+int plb_ln_fwd(const void* z, int T, int H, const float* w, const float* b, float eps,
+               void* y, float* stats, plb_stream_t stream);
+int plb_ln_bwd(const void* dy, const void* z, const float* stats, const float* w, int T, int H,
+               void* dz, float* dw_accum, float* db_accum, float* colsum_accum, plb_stream_t stream);
+
+/* ---- a5: fused attention with key padding -----------------------------------------------------------
+ * HF/:184-197 (+ HF/integrations/sdpa_attention.py:92, HF/masking_utils.py:495-520).  qkv: bf16 [T, 3*heads*64]
+ * = q | k | v as written by the fused QKV GEMM.  Sequence b owns rows [seq_start[b], seq_start[b] + q_len[b]);
+ * its first kv_len[b] rows are valid keys, the rest (padded layout) are masked exactly like the reference's
+ * -inf key mask.  No [B,H,L,L] tensor exists.  ctx: bf16 [T, heads*64].  lse2: fp32 [heads, total_rows], the
+ * row log-sum-exp in the log2 domain (saved for backward).  Backward writes dqkv (bf16, same layout as qkv;
+ * rows of masked keys get exact zeros) and uses `delta` (fp32 [heads, total_rows]) as scratch. head_dim must be 64. */
+int plb_attn_fwd(const void* qkv, int ld_qkv, const int32_t* seq_start, const int32_t* q_len,
+                 const int32_t* kv_len, int B, int heads, int head_dim, int max_q_len, int total_rows,
+                 void* ctx, int ld_ctx, float* lse2, plb_stream_t stream);
+int plb_attn_bwd(const void* qkv, int ld_qkv, const int32_t* seq_start, const int32_t* q_len,
+                 const int32_t* kv_len, int B, int heads, int head_dim, int max_q_len, int total_rows,
+                 const void* ctx, const void* dctx, int ld_ctx, const float* lse2, float* delta,
+                 void* dqkv, int ld_dqkv, plb_stream_t stream);
+
+/* ---- a8: masked-row loss ----------------------------------------------------------------------------
+ * R/train.py:107-131 calculate_phoneme_loss.  The host flattens masked_indices into rows[M] (= b*L + i, in the
+ * reference's order) and weights[M] = 1 / (count * n_b); only those rows go through the heads.
+ *   plb_gather_rows       dst[i, :] = src[rows[i], :]                    (bf16, bit-exact)
+ *   plb_scatter_add_rows  dst[rows[i], :] += src[i, :]                   (bf16, atomics: duplicates add)
+ *   plb_masked_ce         row_loss[i] = w_i * (logsumexp(z_i) - z_i[y_i]); loss_out (+)= sum_i row_loss[i]
+ *                         (fixed-order sum); logits are OVERWRITTEN with dz = w_i * (softmax(z_i) - onehot(y_i)),
+ *                         columns [V, ld) zeroed.  M == 0 gives loss 0 (R/train.py:129).
+ *   plb_colsum            out_accum[n] += sum_t x[t, n]                  (bias gradients)             */
+int plb_gather_rows(const void* src, int ld_src, const int32_t* rows, int M, int H,
+                    void* dst, int ld_dst, plb_stream_t stream);
+int plb_scatter_add_rows(const void* src, int ld_src, const int32_t* rows, int M, int H,
+                         void* dst, int ld_dst, plb_stream_t stream);
+int plb_masked_ce(void* logits, int ld, int M, int V, const int32_t* labels, const float* weights,
+                  float* row_loss, float* loss_out, int accumulate, plb_stream_t stream);
+int plb_colsum(const void* x, int ld, int T, int N, float* out_accum, plb_stream_t stream);
+
+/* ---- a10: fused AdamW --------------------------------------------------------------------------------
+ * torch.optim.AdamW as built at R/train.py:272 (rule: torch/optim/adam.py:417-419,457,476,531-547) over flat
+ * fp32 arenas of n elements (n % 4 == 0).  `step` is the 1-based step count of these parameters; gradients are
+ * multiplied by grad_scale first (1/world_size after a SUM all-reduce).  If bf16_shadow != NULL the updated
+ * parameters are also written as bf16 (the copy the GEMMs read); if zero_grad != 0 the gradient arena is
+ * zeroed for the next step's in-place accumulation. */
+int plb_adamw_step(float* params, float* grads, float* exp_avg, float* exp_avg_sq, void* bf16_shadow,
+                   long n, int step, float lr, float beta1, float beta2, float eps, float weight_decay,
+                   float grad_scale, int zero_grad, plb_stream_t stream);
+int plb_cast_bf16(const float* src, void* dst, long n, plb_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

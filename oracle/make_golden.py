@@ -185,6 +185,48 @@ def main():
     np.savez_compressed(os.path.join(OUT, "phoneme_only_step.npz"), **out)
     print("case B: loss %.6f lengths %s masked rows %s" % (out["loss"], lengths, [len(m) for m in midx]))
 
+    # ---------------- case C: a configuration the CUDA path supports (head_dim 64), fp32 storage ---------
+    # Pins the CUDA kernels DIRECTLY to reference outputs (tests/test_step_gpu.py), not only through the oracle.
+    np.random.seed(23)
+    random.seed(23)
+    rng = np.random.default_rng(23)
+    gp = dict(hidden_size=128, num_attention_heads=2, intermediate_size=256, max_position_embeddings=64,
+              num_hidden_layers=3, embedding_size=32)
+    recs = synthetic_records(6, rng, 3, 14, symbols, Vt)
+    ds = ref_data.MaskedPhonemeDataset(recs, use_token_ids=True, **{**dataset_params, "max_seq_length": 56,
+                                                                    "word_pred_prob": 0.3})
+    token_ids, labels, masked, lengths, midx = ref_data.Collater()([ds[i] for i in range(len(ds))])
+    midx = [list(m) for m in midx]
+    midx[2] = []
+    torch.manual_seed(2)
+    net = ref_model.MultiTaskModel(AlbertModel(AlbertConfig(vocab_size=Vp, **gp)), num_phonemes=Vp, num_tokens=Vt,
+                                   hidden_size=gp["hidden_size"])
+    with torch.no_grad():
+        for n, p in net.named_parameters():
+            if n.endswith("bias") or "LayerNorm" in n or "layer_norm" in n:
+                p.add_(0.05 * torch.randn_like(p))
+    out = {f"param/{k}": v.astype(np.float32) for k, v in state_to_np(net.state_dict()).items()}  # exact: fp32 init
+    net = net.double().train()
+    out["token_ids"], out["labels"], out["masked"] = token_ids.numpy(), labels.numpy(), masked.numpy()
+    out["lengths"] = np.asarray(lengths, dtype=np.int64)
+    out["midx_flat"], out["midx_offs"] = ragged(midx)
+    out["config"] = np.asarray([Vp, gp["embedding_size"], gp["hidden_size"], gp["num_attention_heads"],
+                                gp["intermediate_size"], gp["num_hidden_layers"], gp["max_position_embeddings"], Vt],
+                               dtype=np.int64)
+    attn = (~ref_train.length_to_mask(torch.Tensor(lengths))).int()
+    p_pred, t_pred = net(masked, attention_mask=attn)
+    loss_p = ref_train.calculate_phoneme_loss(p_pred, labels, lengths, midx, criterion)
+    loss_t = ref_train.calculate_phoneme_loss(t_pred, token_ids, lengths, midx, criterion)
+    (loss_p + loss_t).backward()
+    out["loss_phoneme"], out["loss_token"] = np.float64(loss_p.item()), np.float64(loss_t.item())
+    out["last_hidden"] = net.encoder(masked, attention_mask=attn).last_hidden_state.detach().numpy().astype(np.float32)
+    for n, p in net.named_parameters():
+        if p.grad is not None:
+            out[f"grad/{n}"] = p.grad.detach().numpy().astype(np.float32)
+    np.savez_compressed(os.path.join(OUT, "cuda_config_step.npz"), **out)
+    print("case C: loss_p %.6f loss_t %.6f lengths %s masked rows %s" %
+          (out["loss_phoneme"], out["loss_token"], lengths, [len(m) for m in midx]))
+
     # all-empty batch: R/train.py:129 returns tensor(0.)
     empty = ref_train.calculate_phoneme_loss(torch.zeros(2, 3, Vp), torch.zeros(2, 3).long(), [3, 2], [[], []], criterion)
     assert float(empty) == 0.0

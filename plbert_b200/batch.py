@@ -1,0 +1,214 @@
+"""Host side of the hot path's input contract.
+
+The reference's collate (R/dataloader.py:200-223 ``Collater``, :276-297 ``PhonemeOnlyCollater``) yields
+``(phoneme_labels[B,L] int64, masked_phonemes[B,L] int64, input_lengths: list[int], masked_indices: list[list[int]])``
+(the 5-tuple form prepends ``token_ids[B,L]``).  This module turns that tuple into the flat integer arrays the
+kernels consume — bit-exactly, on the host, once per batch — and stages them through pinned memory.  It also
+provides a synthetic generator with the reference pipeline's statistics for benchmarks (the reference dataset
+code cannot travel to the GPU box).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+PAD_ID = 0          # R/char_indexer.py:5,15 — symbols[0] == "P"
+MASK_ID = 185       # 'M'
+SEPARATOR_ID = 186  # ' '
+NUM_SYMBOLS = 188   # len(symbols), probe in SURVEY.md §0
+
+
+def flatten_masked_indices(input_lengths: Sequence[int], masked_indices: Sequence[Sequence[int]],
+                           seq_stride: int) -> Tuple[np.ndarray, np.ndarray]:
+    """Row selection of R/train.py:123-129 as flat arrays: ``rows[k] = b * seq_stride + i`` in the reference's
+    iteration order and ``weights[k] = 1 / (count * n_b)`` where ``count`` is the number of samples with at least
+    one masked index.  int32 / float32, bit-exact index arithmetic."""
+    count = sum(1 for m in masked_indices if len(m) > 0)
+    rows: List[np.ndarray] = []
+    weights: List[np.ndarray] = []
+    for b, (length, idx) in enumerate(zip(input_lengths, masked_indices)):
+        n_b = len(idx)
+        if n_b == 0:
+            continue
+        a = np.asarray(idx, dtype=np.int64)
+        a = np.where(a < 0, a + int(length), a)
+        if a.min() < 0 or a.max() >= int(length):
+            raise IndexError(f"masked index out of range for sample {b} (length {length})")
+        rows.append(a + b * seq_stride)
+        weights.append(np.full(n_b, 1.0 / (count * n_b), dtype=np.float64))
+    if not rows:
+        return np.zeros(0, dtype=np.int32), np.zeros(0, dtype=np.float32)
+    return np.concatenate(rows).astype(np.int32), np.concatenate(weights).astype(np.float32)
+
+
+@dataclass
+class DeviceBatch:
+    """One batch resident in HBM, in the padded [B, L] row layout (row = b * L + j)."""
+
+    B: int
+    L: int
+    ids: torch.Tensor          # int32 [B*L] input symbols (masked_phonemes)
+    pos: torch.Tensor          # int32 [B*L] position ids (restart per sequence)
+    seq_start: torch.Tensor    # int32 [B]
+    q_len: torch.Tensor        # int32 [B]  (= L)
+    kv_len: torch.Tensor       # int32 [B]  (= input_lengths)
+    rows: Optional[torch.Tensor] = None       # int32 [M] masked rows
+    weights: Optional[torch.Tensor] = None    # fp32 [M]
+    labels: List[torch.Tensor] = field(default_factory=list)  # per head: int32 [M] labels at the masked rows
+    M: int = 0
+    num_valid_tokens: int = 0
+    h2d_bytes: int = 0
+
+    @property
+    def T(self) -> int:
+        return self.B * self.L
+
+
+class BatchStager:
+    """Packs a collate tuple into ONE pinned host buffer and uploads it with one async copy.
+
+    Replaces the blocking pageable copies and the CPU mask construction at R/train.py:383-386."""
+
+    SLOTS = 2  # a staged batch stays valid until SLOTS more batches have been staged
+
+    def __init__(self, device: torch.device):
+        self.device = device
+        self._pinned: List[Optional[torch.Tensor]] = [None] * self.SLOTS
+        self._dev: List[Optional[torch.Tensor]] = [None] * self.SLOTS
+        self._done: List[Optional[torch.cuda.Event]] = [None] * self.SLOTS
+        self._next = 0
+
+    def _buffers(self, n_int32: int):
+        s = self._next
+        self._next = (s + 1) % self.SLOTS
+        if self._done[s] is not None:
+            self._done[s].synchronize()  # the previous upload out of this pinned slot has finished
+        if self._pinned[s] is None or self._pinned[s].numel() < n_int32:
+            cap = max(n_int32, 1024) * 2
+            self._pinned[s] = torch.empty(cap, dtype=torch.int32, pin_memory=True)
+            self._dev[s] = torch.empty(cap, dtype=torch.int32, device=self.device)
+        return s, self._pinned[s], self._dev[s]
+
+    def stage(self, masked_phonemes: torch.Tensor, input_lengths: Sequence[int],
+              masked_indices: Optional[Sequence[Sequence[int]]] = None,
+              label_tensors: Sequence[torch.Tensor] = ()) -> DeviceBatch:
+        ids = masked_phonemes
+        if ids.dim() != 2:
+            raise ValueError("masked_phonemes must be [B, L]")
+        B, L = ids.shape
+        lengths = np.asarray([int(x) for x in input_lengths], dtype=np.int32)
+        if lengths.shape[0] != B or lengths.min() < 1 or lengths.max() > L:
+            raise ValueError("input_lengths must hold one length in [1, L] per sample")
+        T = B * L
+        ids_np = ids.reshape(-1).to(torch.int32).numpy() if ids.device.type == "cpu" else None
+        if masked_indices is not None:
+            rows, weights = flatten_masked_indices(lengths, masked_indices, L)
+        else:
+            rows, weights = np.zeros(0, np.int32), np.zeros(0, np.float32)
+        M = rows.shape[0]
+        labs = []
+        for lt in label_tensors:
+            flat = lt.reshape(-1)
+            labs.append(flat[torch.from_numpy(rows.astype(np.int64))].to(torch.int32).cpu().numpy() if M else
+                        np.zeros(0, np.int32))
+        # layout (int32 words): ids[T] | pos[T] | seq_start[B] | q_len[B] | kv_len[B] | rows[M] | weights[M] | labels..
+        n = 2 * T + 3 * B + 2 * M + len(labs) * M
+        slot, pinned, dev = self._buffers(n)
+        host = pinned.numpy()
+        o = 0
+        if ids_np is not None:
+            host[o:o + T] = ids_np
+        o += T
+        host[o:o + T] = np.tile(np.arange(L, dtype=np.int32), B); o += T
+        host[o:o + B] = np.arange(B, dtype=np.int32) * L; o += B
+        host[o:o + B] = L; o += B
+        host[o:o + B] = lengths; o += B
+        host[o:o + M] = rows; o += M
+        host[o:o + M] = weights.view(np.int32); o += M
+        for la in labs:
+            host[o:o + M] = la; o += M
+        dev[:n].copy_(pinned[:n], non_blocking=True)
+        if self._done[slot] is None:
+            self._done[slot] = torch.cuda.Event()
+        self._done[slot].record()
+        if ids_np is None:  # ids already on the device
+            dev[:T].copy_(ids.reshape(-1).to(torch.int32))
+        o = 0
+        def take(k):
+            nonlocal o
+            v = dev[o:o + k]; o += k
+            return v
+        batch = DeviceBatch(B=B, L=L, ids=take(T), pos=take(T), seq_start=take(B), q_len=take(B), kv_len=take(B))
+        batch.rows = take(M)
+        batch.weights = take(M).view(torch.float32)
+        batch.labels = [take(M) for _ in labs]
+        batch.M = M
+        batch.num_valid_tokens = int(lengths.sum())
+        batch.h2d_bytes = 4 * n
+        return batch
+
+
+def synthetic_collate_batch(batch_size: int, max_seq_length: int = 512, seed: int = 1234, *,
+                            variable_length: bool = False, min_length: int = 32, with_token_ids: bool = False,
+                            num_tokens: int = 64000, word_pred_prob: float = 0.15, phoneme_mask_prob: float = 0.8,
+                            replace_prob: float = 0.1):
+    """Synthetic batch with the statistics of the reference pipeline, in the collate tuple format.
+
+    Mirrors R/dataloader.py:59-126: words of 2..9 symbols drawn from the IPA/latin ids 52..184, each followed by the
+    separator (id 186); a word is selected with probability ``word_pred_prob`` and then masked (id 185) with
+    probability 0.8, replaced by symbols drawn from the sample itself with 0.1, or kept (and NOT recorded) with
+    0.1; separators are never selected; the sequence is cropped to ``max_seq_length``; samples are sorted by
+    length (descending) and zero-padded (PAD id 0) to the batch maximum.
+    """
+    rng = np.random.default_rng(seed)
+    samples = []
+    for _ in range(batch_size):
+        target = max_seq_length if not variable_length else int(rng.integers(min_length, max_seq_length + 1))
+        labels: List[int] = []
+        masked: List[int] = []
+        tok: List[int] = []
+        midx: List[int] = []
+        while len(labels) < target + 16:
+            wl = int(rng.integers(2, 10))
+            word = rng.integers(52, 185, size=wl)
+            t_id = int(rng.integers(5, num_tokens))
+            start = len(labels)
+            labels.extend(word.tolist()); labels.append(SEPARATOR_ID)
+            tok.extend([t_id] * wl); tok.append(87)  # word_separator placeholder, R/configs/config.yml:26
+            if rng.random() < word_pred_prob:
+                r = rng.random()
+                if r < phoneme_mask_prob:
+                    masked.extend([MASK_ID] * wl); midx.extend(range(start, start + wl))
+                elif r < phoneme_mask_prob + replace_prob:
+                    pool = labels if len(labels) > 0 else word.tolist()
+                    masked.extend(int(pool[int(k)]) for k in rng.integers(0, len(pool), size=wl))
+                    midx.extend(range(start, start + wl))
+                else:
+                    masked.extend(word.tolist())
+            else:
+                masked.extend(word.tolist())
+            masked.append(SEPARATOR_ID)
+        n = len(labels)
+        begin = int(rng.integers(0, n - target)) if n > target else 0
+        end = begin + target
+        samples.append((torch.tensor(tok[begin:end]), torch.tensor(labels[begin:end]), torch.tensor(masked[begin:end]),
+                        [i - begin for i in midx if begin <= i < end]))
+    samples.sort(key=lambda s: s[1].shape[0], reverse=True)
+    L = samples[0][1].shape[0]
+    B = batch_size
+    token_ids = torch.zeros((B, L), dtype=torch.long)
+    phoneme_labels = torch.zeros((B, L), dtype=torch.long)
+    masked_phonemes = torch.zeros((B, L), dtype=torch.long)
+    lengths = [0] * B
+    masked_indices: List[List[int]] = [[] for _ in range(B)]
+    for i, (t, l, m, mi) in enumerate(samples):
+        n = l.shape[0]
+        token_ids[i, :n], phoneme_labels[i, :n], masked_phonemes[i, :n] = t, l, m
+        lengths[i] = n
+        masked_indices[i] = mi
+    if with_token_ids:
+        return token_ids, phoneme_labels, masked_phonemes, lengths, masked_indices
+    return phoneme_labels, masked_phonemes, lengths, masked_indices

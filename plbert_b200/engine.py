@@ -1,0 +1,396 @@
+"""The B200 training engine: flat parameter arenas, activation workspace and the kernel schedule of one
+PL-BERT step (forward, masked-row loss, backward, AdamW) over the C ABI in ``include/plbert_b200.h``.
+
+Mapping to the reference: ``forward`` = HF ``AlbertModel.forward`` (HF modeling_albert.py:387-423,
+pooler skipped) ; ``loss_and_backward`` = R/train.py:381-390 ``process_batch`` + ``loss.backward()`` (R/train.py:356);
+``adamw_step`` = ``optimizer.step()`` (R/train.py:357).  Everything runs on the current CUDA stream; nothing here
+synchronises with the host.
+
+HBM layout
+  * fp32 arenas ``params / grads / exp_avg / exp_avg_sq`` share one element layout (``ParamLayout``): heads first
+    (their gradients are final first, so their all-reduce overlaps the encoder backward), then the shared ALBERT layer
+    with Wq|Wk|Wv and bq|bk|bv adjacent (so the fused [3H, H] QKV projection is a view), then the embedding-side
+    tensors, then the never-trained pooler.  ``nn.Parameter.data`` of the wrapped modules are views into ``params``
+    (``state_dict`` keeps the reference's names/shapes), ``.grad`` are views into ``grads``.
+  * a bf16 shadow of ``params`` with the same layout is what the GEMMs read; AdamW rewrites it in the same pass.
+  * activations are bf16 [T, *] row-major in the padded layout (row = b*L + j), one set per layer application.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Dict, List, Optional, Tuple
+
+import torch
+
+from . import _abi
+from ._abi import EPI_GELU, EPI_GELU_BWD, EPI_NONE, EPI_RESIDUAL, GEMM_DGRAD, GEMM_FWD, GEMM_WGRAD, call, ptr
+from .batch import DeviceBatch
+
+_LAYER = "encoder.encoder.albert_layer_groups.0.albert_layers.0."
+_EMB = "encoder.embeddings."
+ALIGN = 64  # elements: every tensor (group) starts on a 256-byte (fp32) / 128-byte (bf16) boundary
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+@dataclass
+class EngineConfig:
+    vocab_size: int
+    embedding_size: int
+    hidden_size: int
+    num_attention_heads: int
+    intermediate_size: int
+    num_hidden_layers: int
+    max_position_embeddings: int
+    type_vocab_size: int
+    layer_norm_eps: float
+    pad_token_id: int
+    num_phonemes: int
+    num_tokens: Optional[int]
+
+    @classmethod
+    def from_albert(cls, cfg, num_phonemes: int, num_tokens: Optional[int]) -> "EngineConfig":
+        problems = []
+        if getattr(cfg, "num_hidden_groups", 1) != 1 or getattr(cfg, "inner_group_num", 1) != 1:
+            problems.append("num_hidden_groups/inner_group_num must be 1 (one shared layer)")
+        if cfg.hidden_act != "gelu_new":
+            problems.append(f"hidden_act {cfg.hidden_act!r} (only gelu_new)")
+        if cfg.hidden_dropout_prob != 0 or cfg.attention_probs_dropout_prob != 0:
+            problems.append("dropout > 0 (the reference runs with dropout 0, SURVEY.md §0 row 7)")
+        if cfg.hidden_size % cfg.num_attention_heads or cfg.hidden_size // cfg.num_attention_heads != 64:
+            problems.append("head_dim must be 64")
+        if cfg.hidden_size % 8 or cfg.intermediate_size % 8 or cfg.embedding_size % 8:
+            problems.append("hidden/intermediate/embedding sizes must be multiples of 8")
+        if problems:
+            raise _abi.PlbError("AlbertConfig not supported by the B200 path: " + "; ".join(problems))
+        return cls(cfg.vocab_size, cfg.embedding_size, cfg.hidden_size, cfg.num_attention_heads, cfg.intermediate_size,
+                   cfg.num_hidden_layers, cfg.max_position_embeddings, cfg.type_vocab_size, float(cfg.layer_norm_eps),
+                   0 if cfg.pad_token_id is None else int(cfg.pad_token_id), num_phonemes, num_tokens)
+
+
+class ParamLayout:
+    """Element offsets of every state_dict tensor inside the flat arenas."""
+
+    def __init__(self, c: EngineConfig):
+        E, H, I = c.embedding_size, c.hidden_size, c.intermediate_size
+        groups: List[List[Tuple[str, Tuple[int, ...]]]] = []
+        if c.num_tokens is not None:
+            groups += [[("token_predictor.weight", (c.num_tokens, H))], [("token_predictor.bias", (c.num_tokens,))]]
+        groups += [[("phoneme_predictor.weight", (c.num_phonemes, H))], [("phoneme_predictor.bias", (c.num_phonemes,))]]
+        self.n_head_elems_end = None  # filled below: end of the head region
+        att = _LAYER + "attention."
+        enc_groups = [
+            [(att + "query.weight", (H, H)), (att + "key.weight", (H, H)), (att + "value.weight", (H, H))],
+            [(att + "query.bias", (H,)), (att + "key.bias", (H,)), (att + "value.bias", (H,))],
+            [(att + "dense.weight", (H, H))], [(att + "dense.bias", (H,))],
+            [(att + "LayerNorm.weight", (H,))], [(att + "LayerNorm.bias", (H,))],
+            [(_LAYER + "ffn.weight", (I, H))], [(_LAYER + "ffn.bias", (I,))],
+            [(_LAYER + "ffn_output.weight", (H, I))], [(_LAYER + "ffn_output.bias", (H,))],
+            [(_LAYER + "full_layer_layer_norm.weight", (H,))], [(_LAYER + "full_layer_layer_norm.bias", (H,))],
+            [("encoder.encoder.embedding_hidden_mapping_in.weight", (H, E))],
+            [("encoder.encoder.embedding_hidden_mapping_in.bias", (H,))],
+            [(_EMB + "word_embeddings.weight", (c.vocab_size, E))],
+            [(_EMB + "position_embeddings.weight", (c.max_position_embeddings, E))],
+            [(_EMB + "token_type_embeddings.weight", (c.type_vocab_size, E))],
+            [(_EMB + "LayerNorm.weight", (E,))], [(_EMB + "LayerNorm.bias", (E,))],
+        ]
+        frozen = [[("encoder.pooler.weight", (H, H))], [("encoder.pooler.bias", (H,))]]
+        self.offsets: Dict[str, int] = {}
+        self.shapes: Dict[str, Tuple[int, ...]] = {}
+        off = 0
+
+        def place(gs):
+            nonlocal off
+            for g in gs:
+                off = (off + ALIGN - 1) // ALIGN * ALIGN
+                for name, shape in g:
+                    n = 1
+                    for s in shape:
+                        n *= s
+                    self.offsets[name], self.shapes[name] = off, shape
+                    off += n
+
+        place(groups)
+        off = (off + ALIGN - 1) // ALIGN * ALIGN
+        self.head_end = off          # [0, head_end): head parameters (first all-reduce bucket)
+        place(enc_groups)
+        off = (off + ALIGN - 1) // ALIGN * ALIGN
+        self.trainable_end = off     # [0, trainable_end): everything AdamW updates
+        place(frozen)
+        self.total = (off + ALIGN - 1) // ALIGN * ALIGN
+        self.frozen = {n for g in frozen for n, _ in g}
+
+    def numel(self, name: str) -> int:
+        n = 1
+        for s in self.shapes[name]:
+            n *= s
+        return n
+
+
+class Engine:
+    def __init__(self, cfg: EngineConfig, device: torch.device):
+        _abi.load()
+        if device.type != "cuda":
+            raise _abi.PlbError("plbert_b200 runs on CUDA devices only (no CPU fallback)")
+        self.cfg, self.device = cfg, device
+        self.layout = ParamLayout(cfg)
+        n = self.layout.total
+        self.params = torch.zeros(n, dtype=torch.float32, device=device)
+        self.grads = torch.zeros(n, dtype=torch.float32, device=device)
+        self.exp_avg = torch.zeros(n, dtype=torch.float32, device=device)
+        self.exp_avg_sq = torch.zeros(n, dtype=torch.float32, device=device)
+        self.shadow = torch.zeros(n, dtype=torch.bfloat16, device=device)
+        self.shadow_valid = False
+        self.grads_clean = True       # grads arena is all zeros
+        self.have_grads = False
+        self.opt_step = 0
+        self.launches = 0             # kernels enqueued by this engine (bench.py's gpu_launches)
+        self._cap_T = 0
+        self._cap_M = 0
+        self.loss_buf = torch.zeros(1, dtype=torch.float32, device=device)
+        self.comm_stream: Optional[torch.cuda.Stream] = None
+
+    # ------------------------------------------------------------------ parameter views
+    def view(self, arena: torch.Tensor, name: str) -> torch.Tensor:
+        o = self.layout.offsets[name]
+        return arena[o:o + self.layout.numel(name)].view(self.layout.shapes[name])
+
+    def p(self, name: str) -> torch.Tensor:      # fp32 master
+        return self.view(self.params, name)
+
+    def g(self, name: str) -> torch.Tensor:      # fp32 gradient
+        return self.view(self.grads, name)
+
+    def w(self, name: str) -> torch.Tensor:      # bf16 shadow
+        return self.view(self.shadow, name)
+
+    def refresh_shadow(self) -> None:
+        call("plb_cast_bf16", ptr(self.params), ptr(self.shadow), self.layout.total, _stream())
+        self.launches += 1
+        self.shadow_valid = True
+
+    # ------------------------------------------------------------------ workspace
+    def _ensure_workspace(self, T: int, M: int, train: bool) -> None:
+        c = self.cfg
+        H, I, E = c.hidden_size, c.intermediate_size, c.embedding_size
+        dev, bf = self.device, torch.bfloat16
+        n_sets = c.num_hidden_layers if train else 2
+        if T > self._cap_T or len(getattr(self, "acts", [])) < n_sets:
+            cap = max(T, self._cap_T)
+            mk = lambda cols, dt=bf: torch.empty((cap, cols), dtype=dt, device=dev)
+            self.e, self.e_stats, self.x0 = mk(E), mk(2, torch.float32), mk(H)
+            self.acts = []
+            for _ in range(n_sets):
+                self.acts.append(dict(qkv=mk(3 * H), ctx=mk(H), lse=torch.empty((c.num_attention_heads, cap), dtype=torch.float32, device=dev),
+                                      z1=mk(H), st1=mk(2, torch.float32), a=mk(H), u=mk(I), g=mk(I), z2=mk(H),
+                                      st2=mk(2, torch.float32), y=mk(H)))
+            if train:
+                # backward scratch, reused by every layer
+                self.d_y, self.d_z, self.d_a, self.d_u, self.d_qkv, self.d_ctx = mk(H), mk(H), mk(H), mk(I), mk(3 * H), mk(H)
+                self.d_e = mk(E)
+                self.delta = torch.empty((c.num_attention_heads, cap), dtype=torch.float32, device=dev)
+            self._cap_T = cap
+        if train and M > self._cap_M:
+            cap = max(int(M * 1.25) + 64, self._cap_M)
+            vmax = max(c.num_phonemes, c.num_tokens or 0)
+            self.h_rows = torch.empty((cap, H), dtype=bf, device=dev)
+            self.dh_rows = torch.empty((cap, H), dtype=bf, device=dev)
+            self.logits = torch.empty(cap * ((vmax + 7) // 8 * 8), dtype=bf, device=dev)
+            self.row_loss = torch.empty(cap, dtype=torch.float32, device=dev)
+            self._cap_M = cap
+
+    # ------------------------------------------------------------------ kernels
+    def _gemm(self, op, epi, M, N, K, A, lda, B, ldb, C, ldc, bias=None, aux_in=None, ld_in=0, aux_out=None, ld_out=0):
+        call("plb_gemm_bf16", op, epi, M, N, K, ptr(A), lda, ptr(B), ldb, ptr(C), ldc, ptr(bias), ptr(aux_in), ld_in,
+             ptr(aux_out), ld_out, _stream())
+        self.launches += 1
+
+    def _layer_weights(self):
+        att = _LAYER + "attention."
+        c = self.cfg
+        H = c.hidden_size
+        o = self.layout.offsets
+        wqkv = self.shadow[o[att + "query.weight"]:o[att + "query.weight"] + 3 * H * H].view(3 * H, H)
+        bqkv = self.params[o[att + "query.bias"]:o[att + "query.bias"] + 3 * H]
+        return wqkv, bqkv
+
+    def forward(self, b: DeviceBatch, train: bool) -> torch.Tensor:
+        """Encoder forward; returns last_hidden_state as bf16 [T, H] (a workspace view)."""
+        c = self.cfg
+        T, H, I, E = b.T, c.hidden_size, c.intermediate_size, c.embedding_size
+        nh = c.num_attention_heads
+        if b.L > c.max_position_embeddings:
+            raise _abi.PlbError(f"sequence length {b.L} exceeds max_position_embeddings {c.max_position_embeddings}")
+        self._ensure_workspace(T, b.M, train)
+        if not self.shadow_valid:
+            self.refresh_shadow()
+        s = _stream()
+        att = _LAYER + "attention."
+        call("plb_embed_ln_fwd", ptr(b.ids), ptr(b.pos), T, E, ptr(self.p(_EMB + "word_embeddings.weight")),
+             ptr(self.p(_EMB + "position_embeddings.weight")), ptr(self.p(_EMB + "token_type_embeddings.weight")),
+             ptr(self.p(_EMB + "LayerNorm.weight")), ptr(self.p(_EMB + "LayerNorm.bias")), c.layer_norm_eps,
+             ptr(self.e), ptr(self.e_stats), s)
+        self.launches += 1
+        mp = "encoder.encoder.embedding_hidden_mapping_in."
+        self._gemm(GEMM_FWD, EPI_NONE, T, H, E, self.e, E, self.w(mp + "weight"), E, self.x0, H, bias=self.p(mp + "bias"))
+        wqkv, bqkv = self._layer_weights()
+        x = self.x0
+        for l in range(c.num_hidden_layers):
+            A = self.acts[l if train else l % 2]
+            self._gemm(GEMM_FWD, EPI_NONE, T, 3 * H, H, x, H, wqkv, H, A["qkv"], 3 * H, bias=bqkv)
+            call("plb_attn_fwd", ptr(A["qkv"]), 3 * H, ptr(b.seq_start), ptr(b.q_len), ptr(b.kv_len), b.B, nh, H // nh,
+                 b.L, self._cap_T, ptr(A["ctx"]), H, ptr(A["lse"]), s)
+            self.launches += 1
+            self._gemm(GEMM_FWD, EPI_RESIDUAL, T, H, H, A["ctx"], H, self.w(att + "dense.weight"), H, A["z1"], H,
+                       bias=self.p(att + "dense.bias"), aux_in=x, ld_in=H)
+            call("plb_ln_fwd", ptr(A["z1"]), T, H, ptr(self.p(att + "LayerNorm.weight")), ptr(self.p(att + "LayerNorm.bias")),
+                 c.layer_norm_eps, ptr(A["a"]), ptr(A["st1"]), s)
+            self._gemm(GEMM_FWD, EPI_GELU, T, I, H, A["a"], H, self.w(_LAYER + "ffn.weight"), H, A["g"], I,
+                       bias=self.p(_LAYER + "ffn.bias"), aux_out=A["u"], ld_out=I)
+            self._gemm(GEMM_FWD, EPI_RESIDUAL, T, H, I, A["g"], I, self.w(_LAYER + "ffn_output.weight"), I, A["z2"], H,
+                       bias=self.p(_LAYER + "ffn_output.bias"), aux_in=A["a"], ld_in=H)
+            call("plb_ln_fwd", ptr(A["z2"]), T, H, ptr(self.p(_LAYER + "full_layer_layer_norm.weight")),
+                 ptr(self.p(_LAYER + "full_layer_layer_norm.bias")), c.layer_norm_eps, ptr(A["y"]), ptr(A["st2"]), s)
+            self.launches += 2
+            x = A["y"]
+        return x[:T]
+
+    def head_logits(self, hidden: torch.Tensor, head: str) -> torch.Tensor:
+        """Full-position logits of one head (R/model.py:15-16), bf16 [T, V].  Compatibility / inference path."""
+        T, H = hidden.shape
+        V = self.layout.shapes[head + ".weight"][0]
+        ldv = (V + 7) // 8 * 8
+        out = torch.empty((T, ldv), dtype=torch.bfloat16, device=self.device)
+        self._gemm(GEMM_FWD, EPI_NONE, T, V, H, hidden, H, self.w(head + ".weight"), H, out, ldv, bias=self.p(head + ".bias"))
+        return out[:, :V]
+
+    # ------------------------------------------------------------------ loss + backward
+    def loss_and_backward(self, b: DeviceBatch, heads: List[str]) -> torch.Tensor:
+        """Forward, masked-row CE over ``heads`` (b.labels[i] belongs to heads[i]), full backward into the fp32
+        gradient arena.  Returns the loss as a 0-dim fp32 device tensor (sum over heads)."""
+        c = self.cfg
+        T, H, I, E = b.T, c.hidden_size, c.intermediate_size, c.embedding_size
+        nh, M = c.num_attention_heads, b.M
+        s = _stream()
+        self.begin_backward()
+        hidden = self.forward(b, train=True)
+        if M == 0:
+            # R/train.py:129: no masked rows anywhere -> loss 0 and no gradient reaches any parameter
+            self.loss_buf.zero_()
+            self.have_grads = False
+            return self.loss_buf[0]
+        self.grads_clean = False
+        self.have_grads = True
+
+        # ---- heads on the masked rows only -------------------------------------------------------
+        call("plb_gather_rows", ptr(hidden), H, ptr(b.rows), M, H, ptr(self.h_rows), H, s)
+        self.launches += 1
+        for i, head in enumerate(heads):
+            V = self.layout.shapes[head + ".weight"][0]
+            ldv = (V + 7) // 8 * 8
+            logits = self.logits[:M * ldv].view(M, ldv)
+            self._gemm(GEMM_FWD, EPI_NONE, M, V, H, self.h_rows, H, self.w(head + ".weight"), H, logits, ldv,
+                       bias=self.p(head + ".bias"))
+            call("plb_masked_ce", ptr(logits), ldv, M, V, ptr(b.labels[i]), ptr(b.weights), ptr(self.row_loss),
+                 ptr(self.loss_buf), 1 if i > 0 else 0, s)
+            call("plb_colsum", ptr(logits), ldv, M, V, ptr(self.g(head + ".bias")), s)
+            self.launches += 3
+            self._gemm(GEMM_WGRAD, EPI_NONE, V, H, M, logits, ldv, self.h_rows, H, self.g(head + ".weight"), H)
+            if i == 0:
+                self._gemm(GEMM_DGRAD, EPI_NONE, M, H, V, logits, ldv, self.w(head + ".weight"), H, self.dh_rows, H)
+            else:
+                self._gemm(GEMM_DGRAD, EPI_RESIDUAL, M, H, V, logits, ldv, self.w(head + ".weight"), H, self.dh_rows, H,
+                           aux_in=self.dh_rows, ld_in=H)
+        self._after_head_backward()
+        dy = self.d_y
+        dy[:T].zero_()
+        call("plb_scatter_add_rows", ptr(self.dh_rows), H, ptr(b.rows), M, H, ptr(dy), H, s)
+        self.launches += 1
+        self.encoder_backward(b)
+        return self.loss_buf[0]
+
+    def begin_backward(self) -> None:
+        """Gradients accumulate in place (12 applications of the shared layer), so the arena must start at zero."""
+        if not self.grads_clean:
+            self.grads[:self.layout.trainable_end].zero_()
+            self.grads_clean = True
+
+    def encoder_backward(self, b: DeviceBatch) -> None:
+        """Backward of ``forward(b, train=True)`` given d(last_hidden_state) in ``self.d_y`` (bf16 [T, H])."""
+        c = self.cfg
+        T, H, I, E = b.T, c.hidden_size, c.intermediate_size, c.embedding_size
+        nh = c.num_attention_heads
+        s = _stream()
+        att = _LAYER + "attention."
+        dy = self.d_y
+        self.grads_clean = False
+        self.have_grads = True
+        # ---- 12 applications of the shared layer, last to first ----------------------------------
+        wqkv, _ = self._layer_weights()
+        o = self.layout.offsets
+        g_wqkv = self.grads[o[att + "query.weight"]:o[att + "query.weight"] + 3 * H * H].view(3 * H, H)
+        g_bqkv = self.grads[o[att + "query.bias"]:o[att + "query.bias"] + 3 * H]
+        for l in reversed(range(c.num_hidden_layers)):
+            A = self.acts[l]
+            x_in = self.acts[l - 1]["y"] if l > 0 else self.x0
+            # y = LN2(z2), z2 = a + g W2^T + b2
+            call("plb_ln_bwd", ptr(dy), ptr(A["z2"]), ptr(A["st2"]), ptr(self.p(_LAYER + "full_layer_layer_norm.weight")), T, H,
+                 ptr(self.d_z), ptr(self.g(_LAYER + "full_layer_layer_norm.weight")),
+                 ptr(self.g(_LAYER + "full_layer_layer_norm.bias")), ptr(self.g(_LAYER + "ffn_output.bias")), s)
+            self._gemm(GEMM_WGRAD, EPI_NONE, H, I, T, self.d_z, H, A["g"], I, self.g(_LAYER + "ffn_output.weight"), I)
+            self._gemm(GEMM_DGRAD, EPI_GELU_BWD, T, I, H, self.d_z, H, self.w(_LAYER + "ffn_output.weight"), I, self.d_u, I,
+                       aux_in=A["u"], ld_in=I)
+            call("plb_colsum", ptr(self.d_u), I, T, I, ptr(self.g(_LAYER + "ffn.bias")), s)
+            self._gemm(GEMM_WGRAD, EPI_NONE, I, H, T, self.d_u, I, A["a"], H, self.g(_LAYER + "ffn.weight"), H)
+            self._gemm(GEMM_DGRAD, EPI_RESIDUAL, T, H, I, self.d_u, I, self.w(_LAYER + "ffn.weight"), H, self.d_a, H,
+                       aux_in=self.d_z, ld_in=H)
+            # a = LN1(z1), z1 = x + ctx Wo^T + bo
+            call("plb_ln_bwd", ptr(self.d_a), ptr(A["z1"]), ptr(A["st1"]), ptr(self.p(att + "LayerNorm.weight")), T, H,
+                 ptr(self.d_z), ptr(self.g(att + "LayerNorm.weight")), ptr(self.g(att + "LayerNorm.bias")),
+                 ptr(self.g(att + "dense.bias")), s)
+            self._gemm(GEMM_WGRAD, EPI_NONE, H, H, T, self.d_z, H, A["ctx"], H, self.g(att + "dense.weight"), H)
+            self._gemm(GEMM_DGRAD, EPI_NONE, T, H, H, self.d_z, H, self.w(att + "dense.weight"), H, self.d_ctx, H)
+            call("plb_attn_bwd", ptr(A["qkv"]), 3 * H, ptr(b.seq_start), ptr(b.q_len), ptr(b.kv_len), b.B, nh, H // nh, b.L,
+                 self._cap_T, ptr(A["ctx"]), ptr(self.d_ctx), H, ptr(A["lse"]), ptr(self.delta), ptr(self.d_qkv), 3 * H, s)
+            call("plb_colsum", ptr(self.d_qkv), 3 * H, T, 3 * H, ptr(g_bqkv), s)
+            self._gemm(GEMM_WGRAD, EPI_NONE, 3 * H, H, T, self.d_qkv, 3 * H, x_in, H, g_wqkv, H)
+            self._gemm(GEMM_DGRAD, EPI_RESIDUAL, T, H, 3 * H, self.d_qkv, 3 * H, wqkv, H, dy, H, aux_in=self.d_z, ld_in=H)
+            self.launches += 6  # 2 ln_bwd, 2 colsum, attention bwd = 2 kernels
+
+        # ---- embedding side -----------------------------------------------------------------------
+        mp = "encoder.encoder.embedding_hidden_mapping_in."
+        call("plb_colsum", ptr(dy), H, T, H, ptr(self.g(mp + "bias")), s)
+        self._gemm(GEMM_WGRAD, EPI_NONE, H, E, T, dy, H, self.e, E, self.g(mp + "weight"), E)
+        self._gemm(GEMM_DGRAD, EPI_NONE, T, E, H, dy, H, self.w(mp + "weight"), E, self.d_e, E)
+        call("plb_embed_ln_bwd", ptr(self.d_e), ptr(b.ids), ptr(b.pos), T, E, ptr(self.p(_EMB + "word_embeddings.weight")),
+             ptr(self.p(_EMB + "position_embeddings.weight")), ptr(self.p(_EMB + "token_type_embeddings.weight")),
+             ptr(self.p(_EMB + "LayerNorm.weight")), ptr(self.e_stats), c.pad_token_id,
+             ptr(self.g(_EMB + "word_embeddings.weight")), ptr(self.g(_EMB + "position_embeddings.weight")),
+             ptr(self.g(_EMB + "token_type_embeddings.weight")), ptr(self.g(_EMB + "LayerNorm.weight")),
+             ptr(self.g(_EMB + "LayerNorm.bias")), s)
+        self.launches += 2
+        self._after_encoder_backward()
+
+    # ------------------------------------------------------------------ data parallel hooks (ddp.py overrides)
+    def _after_head_backward(self) -> None:
+        pass
+
+    def _after_encoder_backward(self) -> None:
+        pass
+
+    # ------------------------------------------------------------------ optimizer
+    def adamw_step(self, lr: float, betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 0.01,
+                   grad_scale: float = 1.0) -> None:
+        """One fused AdamW update of every trainable parameter (R/train.py:357); also rewrites the bf16 shadow and
+        zeroes the gradient arena for the next step's in-place accumulation."""
+        if not self.have_grads:
+            return  # reference: parameters whose .grad is None are skipped entirely (no decay either)
+        self.opt_step += 1
+        n = self.layout.trainable_end
+        call("plb_adamw_step", ptr(self.params), ptr(self.grads), ptr(self.exp_avg), ptr(self.exp_avg_sq), ptr(self.shadow),
+             n, self.opt_step, lr, betas[0], betas[1], eps, weight_decay, grad_scale, 1, _stream())
+        self.launches += 1
+        self.grads_clean = True
+        self.have_grads = False

@@ -1,0 +1,261 @@
+"""Drop-in ``MultiTaskModel`` / ``PhonemeOnlyModel`` (R/model.py:5-30) backed by the B200 engine.
+
+Same constructors, same attribute names (``encoder``, ``phoneme_predictor``, ``token_predictor``), same
+``state_dict`` keys/shapes/dtypes, same ``forward(phonemes, attention_mask=None)`` contract — so
+``AlbertConfig(**model_params)`` → ``AlbertModel`` → ``MultiTaskModel(...)``, ``load_state_dict`` of a reference
+checkpoint, ``model.encoder.save_pretrained`` (R/convert_to_hf.py:49) and the StyleTTS loader keep working.
+
+Two ways to train:
+
+* reference-style (unchanged caller code, R/train.py:381-390 + :355-357)::
+
+      pred = model(masked_phonemes, attention_mask=mask)          # full [B, L, V] logits, autograd-enabled
+      loss = calculate_phoneme_loss(pred, labels, lengths, masked_indices, criterion)
+      loss.backward(); optimizer.step()
+
+  ``forward`` runs the fused encoder (no [B,H,L,L] tensor) and a custom autograd node runs the fused backward.
+
+* fused step (what ``bench.py`` measures; what ``plbert_b200.train.process_batch`` uses)::
+
+      loss = model.loss_and_backward(batch)                       # collate tuple in, device scalar out
+      optimizer.step()
+
+  which evaluates the heads and the cross-entropy on the masked rows only and never materialises logits for the
+  other positions.
+
+There is no CPU/PyTorch fallback: calling the model with CPU tensors raises.
+"""
+from __future__ import annotations
+
+import weakref
+from types import SimpleNamespace
+from typing import List, Optional, Sequence
+
+import torch
+from torch import nn
+
+from . import _abi
+from ._abi import EPI_NONE, EPI_RESIDUAL, GEMM_DGRAD, GEMM_FWD, GEMM_WGRAD, call, ptr
+from .batch import BatchStager, DeviceBatch
+from .engine import Engine, EngineConfig, _stream
+
+# id(parameter) -> engine that owns its storage (used by FusedAdamW to find the arenas)
+_ENGINE_OF_PARAM: "weakref.WeakValueDictionary[int, Engine]" = weakref.WeakValueDictionary()
+
+
+def engine_of(param: torch.Tensor) -> Optional[Engine]:
+    return _ENGINE_OF_PARAM.get(id(param))
+
+
+class _FullLogitsFn(torch.autograd.Function):
+    """forward: fused encoder + all-position head GEMMs; backward: fused head/encoder backward.
+    The parameters are passed only so autograd routes gradients to them."""
+
+    @staticmethod
+    def forward(ctx, model, batch: DeviceBatch, heads, need_grad, *params):
+        eng: Engine = model._engine
+        hidden = eng.forward(batch, train=need_grad)
+        outs = []
+        for h in heads:
+            outs.append(eng.head_logits(hidden, h).float().view(batch.B, batch.L, -1))
+        ctx.model, ctx.batch, ctx.heads = model, batch, heads
+        ctx.hidden = hidden
+        ctx.n_params = len(params)
+        return tuple(outs)
+
+    @staticmethod
+    def backward(ctx, *dlogits):
+        model, b, heads = ctx.model, ctx.batch, ctx.heads
+        eng: Engine = model._engine
+        H, T = eng.cfg.hidden_size, b.T
+        eng.begin_backward()
+        eng.grads_clean = False
+        first = True
+        for h, dl in zip(heads, dlogits):
+            if dl is None:
+                continue
+            V = dl.shape[-1]
+            ldv = (V + 7) // 8 * 8
+            dz = torch.zeros((T, ldv), dtype=torch.bfloat16, device=dl.device)
+            dz[:, :V] = dl.reshape(T, V)
+            call("plb_colsum", ptr(dz), ldv, T, V, ptr(eng.g(h + ".bias")), _stream())
+            eng.launches += 1
+            eng._gemm(GEMM_WGRAD, EPI_NONE, V, H, T, dz, ldv, ctx.hidden, H, eng.g(h + ".weight"), H)
+            if first:
+                eng._gemm(GEMM_DGRAD, EPI_NONE, T, H, V, dz, ldv, eng.w(h + ".weight"), H, eng.d_y, H)
+            else:
+                eng._gemm(GEMM_DGRAD, EPI_RESIDUAL, T, H, V, dz, ldv, eng.w(h + ".weight"), H, eng.d_y, H,
+                          aux_in=eng.d_y, ld_in=H)
+            first = False
+        if first:
+            return (None, None, None, None) + (None,) * ctx.n_params
+        eng._after_head_backward()
+        eng.encoder_backward(b)
+        grads = []
+        for name, p in model._arena_params():
+            grads.append(eng.g(name) if (p.requires_grad and name not in eng.layout.frozen) else None)
+        return (None, None, None, None) + tuple(grads)
+
+
+class _FusedModel(nn.Module):
+    _heads: List[str] = []
+
+    def _init_fused(self):
+        self._engine: Optional[Engine] = None
+        self._stager: Optional[BatchStager] = None
+        self._versions: List[int] = []
+
+    # ------------------------------------------------------------------ engine / arena management
+    def _arena_params(self):
+        """(state_dict name, parameter) for every parameter, in ``self.parameters()`` order."""
+        return list(self.named_parameters())
+
+    def _num_tokens(self) -> Optional[int]:
+        tp = getattr(self, "token_predictor", None)
+        return None if tp is None else tp.out_features
+
+    def _ensure_engine(self, device: torch.device) -> Engine:
+        if device.type != "cuda":
+            raise _abi.PlbError("plbert_b200 computes on CUDA only; move the model and inputs to a B200 (no CPU fallback)")
+        eng = self._engine
+        named = self._arena_params()
+        if eng is None or eng.device != device:
+            cfg = EngineConfig.from_albert(self.encoder.config, self.phoneme_predictor.out_features, self._num_tokens())
+            eng = Engine(cfg, device)
+            missing = set(eng.layout.offsets) ^ {n for n, _ in named}
+            if missing:
+                raise _abi.PlbError(f"parameter set does not match the PL-BERT layout: {sorted(missing)}")
+            self._engine = eng
+            self._stager = BatchStager(device)
+            self._versions = []
+        # (re)adopt: parameters whose storage is not the arena view (first call, .to(), load with assign=True ...)
+        stale = False
+        for name, p in named:
+            view = eng.p(name)
+            if p.data_ptr() != view.data_ptr() or p.dtype != torch.float32:
+                if tuple(p.shape) != tuple(view.shape):
+                    raise _abi.PlbError(f"{name}: shape {tuple(p.shape)} does not match the layout {tuple(view.shape)}")
+                with torch.no_grad():
+                    view.copy_(p.detach().to(device=device, dtype=torch.float32))
+                p.data = view
+                _ENGINE_OF_PARAM[id(p)] = eng
+                stale = True
+        versions = [p._version for _, p in named]
+        if stale or versions != self._versions:
+            eng.shadow_valid = False  # someone wrote the fp32 weights through torch (load_state_dict, init, ...)
+            self._versions = versions
+        return eng
+
+    def _publish_grads(self) -> None:
+        eng = self._engine
+        for name, p in self._arena_params():
+            if name in eng.layout.frozen or not p.requires_grad:
+                continue
+            p.grad = eng.g(name) if eng.have_grads else None
+
+    # ------------------------------------------------------------------ reference-compatible forward
+    def _stage_inputs(self, phonemes: torch.Tensor, attention_mask: Optional[torch.Tensor]) -> DeviceBatch:
+        if phonemes.dim() != 2:
+            raise ValueError("phonemes must be [B, L]")
+        B, L = phonemes.shape
+        if attention_mask is None:
+            lengths = [L] * B
+        else:
+            am = attention_mask.to("cpu") != 0
+            lengths = am.sum(dim=1).tolist()
+            # the reference only ever builds prefix masks (R/train.py:34-44); anything else is not this path
+            if not torch.equal(am, torch.arange(L)[None, :] < torch.tensor(lengths)[:, None]):
+                raise _abi.PlbError("attention_mask must be a right-padded prefix mask (R/train.py:34-44)")
+        return self._stager.stage(phonemes, lengths)
+
+    def _forward_logits(self, phonemes, attention_mask):
+        eng = self._ensure_engine(phonemes.device)
+        batch = self._stage_inputs(phonemes, attention_mask)
+        params = [p for _, p in self._arena_params()]
+        need_grad = torch.is_grad_enabled() and any(p.requires_grad for p in params)
+        return _FullLogitsFn.apply(self, batch, list(self._heads), need_grad, *params)
+
+    def encode(self, phonemes: torch.Tensor, attention_mask: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Encoder-only forward (``AlbertModel(...).last_hidden_state``, R/README.md:91): bf16 [B, L, H], no grad."""
+        eng = self._ensure_engine(phonemes.device)
+        batch = self._stage_inputs(phonemes, attention_mask)
+        with torch.no_grad():
+            hidden = eng.forward(batch, train=False)
+        return hidden.view(batch.B, batch.L, -1).clone()  # the workspace is reused by the next call
+
+    # ------------------------------------------------------------------ fused training step
+    def loss_and_backward(self, batch: Sequence) -> torch.Tensor:
+        """R/train.py:381-390 ``process_batch`` + ``loss.backward()`` in one call.
+
+        ``batch`` is the collate tuple: ``(phoneme_labels, masked_phonemes, input_lengths, masked_indices)`` or, with
+        token ids, ``(token_ids, phoneme_labels, masked_phonemes, input_lengths, masked_indices)``.  Returns the loss
+        (mean over non-empty samples of the per-sample mean CE over masked rows; heads summed) as a device scalar and
+        leaves the gradients in ``p.grad``."""
+        if len(batch) == 5:
+            token_ids, labels, masked, lengths, midx = batch
+        else:
+            labels, masked, lengths, midx = batch
+            token_ids = None
+        device = next(self.parameters()).device
+        eng = self._ensure_engine(device)
+        label_tensors = [labels]
+        heads = ["phoneme_predictor"]
+        if "token_predictor" in self._heads:
+            if token_ids is None:
+                raise _abi.PlbError("MultiTaskModel.loss_and_backward needs the 5-tuple batch with token_ids")
+            label_tensors.append(token_ids)
+            heads.append("token_predictor")
+        db = self._stager.stage(masked, lengths, midx, label_tensors)
+        self.last_batch = db
+        loss = eng.loss_and_backward(db, heads)
+        self._publish_grads()
+        return loss
+
+
+class MultiTaskModel(_FusedModel):
+    """R/model.py:5-18."""
+
+    _heads = ["phoneme_predictor", "token_predictor"]
+
+    def __init__(self, model, num_phonemes, num_tokens, hidden_size):
+        super().__init__()
+        self.encoder = model
+        self.phoneme_predictor = nn.Linear(hidden_size, num_phonemes)
+        self.token_predictor = nn.Linear(hidden_size, num_tokens)
+        self._init_fused()
+
+    def forward(self, phonemes, attention_mask=None):
+        phoneme_pred, token_pred = self._forward_logits(phonemes, attention_mask)
+        return phoneme_pred, token_pred
+
+
+class PhonemeOnlyModel(_FusedModel):
+    """R/model.py:19-30."""
+
+    _heads = ["phoneme_predictor"]
+
+    def __init__(self, model, num_phonemes, hidden_size):
+        super().__init__()
+        self.encoder = model
+        self.phoneme_predictor = nn.Linear(hidden_size, num_phonemes)
+        self._init_fused()
+
+    def forward(self, phonemes, attention_mask=None):
+        (phoneme_pred,) = self._forward_logits(phonemes, attention_mask)
+        return phoneme_pred
+
+
+# upstream (yl4579/PL-BERT) checkpoints call the heads mask_predictor / word_predictor
+UPSTREAM_ALIASES = {"mask_predictor.": "phoneme_predictor.", "word_predictor.": "token_predictor."}
+
+
+def normalize_state_dict_keys(state_dict):
+    """Strip the DDP ``module.`` prefix (R/train.py:98, R/convert_to_hf.py:40) and map upstream head names."""
+    out = {}
+    for k, v in state_dict.items():
+        k = k.replace("module.", "")
+        for old, new in UPSTREAM_ALIASES.items():
+            if k.startswith(old):
+                k = new + k[len(old):]
+        out[k] = v
+    return out

@@ -1,0 +1,330 @@
+"""Per-kernel parity on the device, through the C ABI (ctypes), against plain PyTorch fp32 references of the same
+op on the same bf16-rounded inputs.  Integer / index work is compared bit-exactly; floating point with the
+tolerance stated at each assert (bf16 outputs carry 2^-8 relative rounding)."""
+import math
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from plbert_b200 import _abi  # noqa: E402
+from plbert_b200._abi import call, ptr  # noqa: E402
+
+BF = torch.bfloat16
+
+
+@pytest.fixture(scope="module")
+def dev():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    _abi.load()
+    torch.manual_seed(0)
+    return torch.device("cuda:0")
+
+
+def S():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def rel(a, b):
+    return ((a.double() - b.double()).norm() / b.double().norm().clamp_min(1e-30)).item()
+
+
+def gelu_new(u):
+    return 0.5 * u * (1 + torch.tanh(math.sqrt(2 / math.pi) * (u + 0.044715 * u ** 3)))
+
+
+# ------------------------------------------------------------------------------------------ a1
+def test_length_to_mask_golden_bit_exact(dev, golden_dir):
+    z = np.load(os.path.join(golden_dir, "length_to_mask.npz"))
+    i = 0
+    while f"lengths_{i}" in z.files:
+        lens = torch.tensor(z[f"lengths_{i}"], dtype=torch.int32, device=dev)
+        B, L = lens.numel(), int(lens.max())
+        out = torch.empty((B, L), dtype=torch.int32, device=dev)
+        call("plb_length_to_mask", ptr(lens), B, L, ptr(out), S())
+        assert np.array_equal(out.cpu().numpy(), z[f"attn_mask_{i}"])
+        from plbert_b200.train import length_to_mask
+        assert np.array_equal(length_to_mask(lens).cpu().numpy(), z[f"pad_mask_{i}"])
+        assert np.array_equal(length_to_mask(lens.cpu()).numpy(), z[f"pad_mask_{i}"])
+        i += 1
+    assert i >= 4
+
+
+# ------------------------------------------------------------------------------------------ GEMM
+def _gemm(op, epi, M, N, K, A, B, C, bias=None, aux_in=None, aux_out=None, fn="plb_gemm_bf16"):
+    call(fn, op, epi, M, N, K, ptr(A), A.stride(0), ptr(B), B.stride(0), ptr(C), C.stride(0), ptr(bias), ptr(aux_in),
+         0 if aux_in is None else aux_in.stride(0), ptr(aux_out), 0 if aux_out is None else aux_out.stride(0), S())
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 256, 64), (1000, 188, 768), (4096, 2304, 768), (777, 768, 2048), (300, 768, 128)])
+@pytest.mark.parametrize("epi", [_abi.EPI_NONE, _abi.EPI_RESIDUAL, _abi.EPI_GELU])
+def test_gemm_fwd(dev, M, N, K, epi):
+    ldn = (N + 7) // 8 * 8
+    A = torch.randn(M, K, device=dev).to(BF)
+    W = (torch.randn(N, K, device=dev) / math.sqrt(K)).to(BF)
+    bias = torch.randn(N, device=dev)
+    R = torch.randn(M, ldn, device=dev).to(BF)
+    C = torch.zeros(M, ldn, device=dev, dtype=BF)
+    U = torch.zeros(M, ldn, device=dev, dtype=BF)
+    _gemm(_abi.GEMM_FWD, epi, M, N, K, A, W, C, bias, R if epi == _abi.EPI_RESIDUAL else None, U if epi == _abi.EPI_GELU else None)
+    ref = A.float() @ W.float().T + bias
+    if epi == _abi.EPI_RESIDUAL:
+        ref = ref + R[:, :N].float()
+    if epi == _abi.EPI_GELU:
+        assert rel(U[:, :N].float(), ref) < 6e-3  # bf16 output rounding
+        ref = gelu_new(ref.to(BF).float())
+    assert rel(C[:, :N].float(), ref) < 6e-3
+    assert torch.isfinite(C.float()).all()
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 256, 64), (999, 768, 188), (4096, 768, 2304), (2048, 2048, 768), (500, 128, 768)])
+@pytest.mark.parametrize("epi", [_abi.EPI_NONE, _abi.EPI_RESIDUAL, _abi.EPI_GELU_BWD])
+def test_gemm_dgrad(dev, M, N, K, epi):
+    ldk, ldn = (K + 7) // 8 * 8, (N + 7) // 8 * 8
+    A = torch.zeros(M, ldk, device=dev, dtype=BF)
+    A[:, :K] = torch.randn(M, K, device=dev).to(BF)
+    W = torch.zeros(K, ldn, device=dev, dtype=BF)
+    W[:, :N] = (torch.randn(K, N, device=dev) / math.sqrt(K)).to(BF)
+    X = torch.randn(M, ldn, device=dev).to(BF)
+    C = torch.zeros(M, ldn, device=dev, dtype=BF)
+    _gemm(_abi.GEMM_DGRAD, epi, M, N, K, A, W, C, None, X if epi != _abi.EPI_NONE else None)
+    ref = A[:, :K].float() @ W[:, :N].float()
+    if epi == _abi.EPI_RESIDUAL:
+        ref = ref + X[:, :N].float()
+    if epi == _abi.EPI_GELU_BWD:
+        u = X[:, :N].float().requires_grad_(True)
+        (g,) = torch.autograd.grad(gelu_new(u).sum(), u)
+        ref = ref * g
+    assert rel(C[:, :N].float(), ref) < 6e-3
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 256, 64), (188, 768, 1000), (2304, 768, 20000), (768, 2048, 4096), (768, 128, 3000)])
+def test_gemm_wgrad_accumulates(dev, M, N, K):
+    ldm = (M + 7) // 8 * 8
+    A = torch.zeros(K, ldm, device=dev, dtype=BF)
+    A[:, :M] = torch.randn(K, M, device=dev).to(BF)
+    B = torch.randn(K, N, device=dev).to(BF)
+    C = torch.randn(M, N, device=dev)
+    ref = C.double() + A[:, :M].double().T @ B.double()
+    _gemm(_abi.GEMM_WGRAD, _abi.EPI_NONE, M, N, K, A, B, C)
+    assert rel(C, ref) < 1e-5  # fp32 accumulate, only the summation order differs
+    _gemm(_abi.GEMM_WGRAD, _abi.EPI_NONE, M, N, K, A, B, C)  # second application sums in place (shared layer)
+    assert rel(C, ref + A[:, :M].double().T @ B.double()) < 1e-5
+
+
+def test_gemm_linearity_at_full_size(dev):
+    """Size-independent property at the BASELINE size (T = 192 x 512): (A1 + A2) W^T == A1 W^T + A2 W^T for
+    operands chosen so that every product and sum is exact in bf16/fp32."""
+    T, N, K = 98304, 768, 768
+    A1 = torch.randint(-2, 3, (T, K), device=dev).to(BF)
+    A2 = torch.randint(-2, 3, (T, K), device=dev).to(BF)
+    W = torch.randint(-1, 2, (N, K), device=dev).to(BF)
+    outs = []
+    for A in (A1, A2, (A1.float() + A2.float()).to(BF)):
+        C = torch.empty(T, N, device=dev, dtype=BF)
+        _gemm(_abi.GEMM_FWD, _abi.EPI_NONE, T, N, K, A, W, C)
+        outs.append(C.float())
+    # |sum| <= 4*768 = 3072 needs 12 bits > bf16's 8: compare in the exactly-representable subset via rounding bound
+    assert (outs[2] - (outs[0] + outs[1])).abs().max() <= 2 ** -7 * (outs[0] + outs[1]).abs().max()
+    idx = torch.randint(0, T, (64,), device=dev)
+    ref = (A1[idx].float() + A2[idx].float()) @ W.float().T
+    assert (outs[2][idx] - ref).abs().max() <= 2 ** -8 * ref.abs().max() + 1e-6
+
+
+def test_gemm_rejects_bad_arguments(dev):
+    A = torch.zeros(16, 16, device=dev, dtype=BF)
+    with pytest.raises(_abi.PlbError):
+        call("plb_gemm_bf16", 0, 0, 16, 16, 16, ptr(A), 12, ptr(A), 16, ptr(A), 16, 0, 0, 0, 0, 0, S())  # lda % 8
+    with pytest.raises(_abi.PlbError):
+        call("plb_gemm_bf16", 0, 0, 0, 16, 16, ptr(A), 16, ptr(A), 16, ptr(A), 16, 0, 0, 0, 0, 0, S())  # M == 0
+    with pytest.raises(_abi.PlbError):
+        call("plb_gemm_bf16", 2, 1, 16, 16, 16, ptr(A), 16, ptr(A), 16, ptr(A), 16, 0, 0, 0, 0, 0, S())  # wgrad + epilogue
+
+
+# ------------------------------------------------------------------------------------------ LayerNorm
+@pytest.mark.parametrize("T,H", [(1000, 768), (513, 128), (64, 1024), (7, 8)])
+def test_layernorm_fwd_bwd(dev, T, H):
+    z = (torch.randn(T, H, device=dev) * 2 + 0.3).to(BF)
+    w = torch.randn(H, device=dev)
+    b = torch.randn(H, device=dev)
+    y = torch.empty_like(z)
+    stats = torch.empty(T, 2, device=dev)
+    call("plb_ln_fwd", ptr(z), T, H, ptr(w), ptr(b), 1e-12, ptr(y), ptr(stats), S())
+    zf = z.float().requires_grad_(True)
+    wf, bf_ = w.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    ref = torch.nn.functional.layer_norm(zf, (H,), wf, bf_, 1e-12)
+    assert rel(y.float(), ref) < 5e-3
+    assert rel(stats[:, 0], zf.mean(1)) < 1e-5 and rel(stats[:, 1], 1 / torch.sqrt(zf.var(1, unbiased=False) + 1e-12)) < 1e-4
+    dy = torch.randn(T, H, device=dev).to(BF)
+    ref.backward(dy.float())
+    dz = torch.empty_like(z)
+    dw = torch.ones(H, device=dev)
+    db = torch.ones(H, device=dev)
+    cs = torch.ones(H, device=dev)
+    call("plb_ln_bwd", ptr(dy), ptr(z), ptr(stats), ptr(w), T, H, ptr(dz), ptr(dw), ptr(db), ptr(cs), S())
+    assert rel(dz.float(), zf.grad) < 5e-3
+    assert rel(dw - 1, wf.grad) < 1e-4 and rel(db - 1, bf_.grad) < 1e-4  # accumulated on top of the 1s
+    assert rel(cs - 1, dz.float().sum(0)) < 1e-4  # bias gradient = column sum of the stored (rounded) dz
+
+
+def test_layernorm_constant_row_is_finite(dev):
+    z = torch.full((4, 768), 3.0, device=dev).to(BF)
+    w, b = torch.ones(768, device=dev), torch.zeros(768, device=dev)
+    y, stats = torch.empty_like(z), torch.empty(4, 2, device=dev)
+    call("plb_ln_fwd", ptr(z), 4, 768, ptr(w), ptr(b), 1e-12, ptr(y), ptr(stats), S())
+    assert torch.isfinite(y.float()).all() and (y.float() == 0).all()
+
+
+# ------------------------------------------------------------------------------------------ embeddings
+@pytest.mark.parametrize("T,E,V,P", [(2000, 128, 188, 512), (333, 32, 188, 64)])
+def test_embed_ln_fwd_bwd(dev, T, E, V, P):
+    ids = torch.randint(0, V, (T,), device=dev, dtype=torch.int32)
+    ids[:5] = 0
+    pos = torch.randint(0, P, (T,), device=dev, dtype=torch.int32)
+    word = torch.randn(V, E, device=dev, requires_grad=True)
+    pe = torch.randn(P, E, device=dev, requires_grad=True)
+    typ = torch.randn(2, E, device=dev, requires_grad=True)
+    w = torch.randn(E, device=dev, requires_grad=True)
+    b = torch.randn(E, device=dev, requires_grad=True)
+    out = torch.empty(T, E, device=dev, dtype=BF)
+    stats = torch.empty(T, 2, device=dev)
+    call("plb_embed_ln_fwd", ptr(ids), ptr(pos), T, E, ptr(word), ptr(pe), ptr(typ), ptr(w), ptr(b), 1e-12, ptr(out), ptr(stats), S())
+    ref = torch.nn.functional.layer_norm((word[ids.long()] + typ[0]) + pe[pos.long()], (E,), w, b, 1e-12)
+    assert rel(out.float(), ref) < 5e-3
+    de = torch.randn(T, E, device=dev).to(BF)
+    ref.backward(de.float())
+    g = [torch.zeros_like(t) for t in (word, pe, typ[0], w, b)]
+    call("plb_embed_ln_bwd", ptr(de), ptr(ids), ptr(pos), T, E, ptr(word), ptr(pe), ptr(typ), ptr(w), ptr(stats), 0,
+         ptr(g[0]), ptr(g[1]), ptr(g[2]), ptr(g[3]), ptr(g[4]), S())
+    wg = word.grad.clone()
+    wg[0] = 0  # padding_idx row
+    assert not g[0][0].any()
+    assert rel(g[0], wg) < 1e-4 and rel(g[1], pe.grad) < 1e-4 and rel(g[2], typ.grad[0]) < 1e-4
+    assert rel(g[3], w.grad) < 1e-4 and rel(g[4], b.grad) < 1e-4
+
+
+# ------------------------------------------------------------------------------------------ attention
+def _attn_ref(qkv, B, L, nh, lens):
+    T, H3 = qkv.shape
+    H = H3 // 3
+    q, k, v = [t.view(B, L, nh, 64).transpose(1, 2) for t in qkv.split(H, dim=1)]
+    s = q @ k.transpose(-1, -2) / 8.0
+    key_ok = torch.arange(L, device=qkv.device)[None, :] < lens[:, None]
+    s = s.masked_fill(~key_ok[:, None, None, :], float("-inf"))
+    p = torch.softmax(s, dim=-1)
+    return (p @ v).transpose(1, 2).reshape(T, H), torch.logsumexp(s, dim=-1)
+
+
+@pytest.mark.parametrize("B,L,nh,lens", [(2, 64, 2, [64, 64]), (3, 200, 2, [200, 77, 1]), (2, 512, 12, [512, 300]),
+                                         (4, 130, 3, [130, 129, 65, 64])])
+def test_attention_fwd_bwd(dev, B, L, nh, lens):
+    H, T = nh * 64, B * L
+    qkv = torch.randn(T, 3 * H, device=dev).to(BF)
+    lens_t = torch.tensor(lens, device=dev, dtype=torch.int32)
+    seq_start = torch.arange(B, device=dev, dtype=torch.int32) * L
+    q_len = torch.full((B,), L, device=dev, dtype=torch.int32)
+    ctx = torch.full((T, H), float("nan"), device=dev, dtype=BF)
+    lse = torch.zeros(nh, T, device=dev)
+    call("plb_attn_fwd", ptr(qkv), 3 * H, ptr(seq_start), ptr(q_len), ptr(lens_t), B, nh, 64, L, T, ptr(ctx), H, ptr(lse), S())
+    qf = qkv.float().requires_grad_(True)
+    ref, ref_lse = _attn_ref(qf, B, L, nh, lens_t.long())
+    assert torch.isfinite(ctx.float()).all()  # padded QUERY rows are computed too, like the reference
+    assert rel(ctx.float(), ref) < 8e-3
+    got_lse = lse.view(nh, B, L).permute(1, 0, 2) * math.log(2.0)
+    assert (got_lse - ref_lse).abs().max() < 2e-3
+
+    dctx = torch.randn(T, H, device=dev).to(BF)
+    valid = (torch.arange(L, device=dev)[None, :] < lens_t[:, None]).reshape(T)
+    dctx[~valid] = 0  # the loss never reads padded rows (R/train.py:125), so their upstream gradient is zero
+    ref.backward(dctx.float())
+    dqkv = torch.full((T, 3 * H), float("nan"), device=dev, dtype=BF)
+    delta = torch.zeros(nh, T, device=dev)
+    call("plb_attn_bwd", ptr(qkv), 3 * H, ptr(seq_start), ptr(q_len), ptr(lens_t), B, nh, 64, L, T, ptr(ctx), ptr(dctx), H,
+         ptr(lse), ptr(delta), ptr(dqkv), 3 * H, S())
+    assert torch.isfinite(dqkv.float()).all()
+    for name, sl in (("dq", slice(0, H)), ("dk", slice(H, 2 * H)), ("dv", slice(2 * H, 3 * H))):
+        assert rel(dqkv[:, sl].float(), qf.grad[:, sl]) < 2e-2, name
+    # masked keys: exactly zero gradient for K and V
+    assert not dqkv[~valid][:, H:].any()
+
+
+# ------------------------------------------------------------------------------------------ masked-row loss path
+def test_gather_scatter_bit_exact(dev):
+    T, H, M = 5000, 768, 700
+    src = torch.randn(T, H, device=dev).to(BF)
+    rows = torch.randperm(T, device=dev)[:M].to(torch.int32)
+    dst = torch.empty(M, H, device=dev, dtype=BF)
+    call("plb_gather_rows", ptr(src), H, ptr(rows), M, H, ptr(dst), H, S())
+    assert torch.equal(dst, src[rows.long()])
+    acc = torch.zeros(T, H, device=dev, dtype=BF)
+    call("plb_scatter_add_rows", ptr(dst), H, ptr(rows), M, H, ptr(acc), H, S())
+    ref = torch.zeros_like(acc)
+    ref[rows.long()] = dst
+    assert torch.equal(acc, ref)
+    # duplicates accumulate
+    rows2 = torch.zeros(4, device=dev, dtype=torch.int32)
+    ones = torch.ones(4, H, device=dev, dtype=BF)
+    acc.zero_()
+    call("plb_scatter_add_rows", ptr(ones), H, ptr(rows2), 4, H, ptr(acc), H, S())
+    assert (acc[0] == 4).all() and not acc[1:].any()
+
+
+@pytest.mark.parametrize("M,V", [(1000, 188), (37, 97), (300, 5000)])
+def test_masked_ce(dev, M, V):
+    ld = (V + 7) // 8 * 8
+    z = torch.zeros(M, ld, device=dev, dtype=BF)
+    z[:, :V] = (torch.randn(M, V, device=dev) * 3).to(BF)
+    z[:, V:] = 7.0  # padding columns must be ignored and then zeroed
+    labels = torch.randint(0, V, (M,), device=dev, dtype=torch.int32)
+    w = torch.rand(M, device=dev) / M
+    zf = z[:, :V].float().requires_grad_(True)
+    ref_rows = torch.nn.functional.cross_entropy(zf, labels.long(), reduction="none") * w
+    ref_rows.sum().backward()
+    row_loss = torch.empty(M, device=dev)
+    loss = torch.full((1,), 5.0, device=dev)
+    call("plb_masked_ce", ptr(z), ld, M, V, ptr(labels), ptr(w), ptr(row_loss), ptr(loss), 0, S())
+    assert rel(row_loss, ref_rows) < 1e-5
+    assert abs(loss.item() - ref_rows.sum().item()) < 1e-5 * abs(ref_rows.sum().item()) + 1e-7
+    assert rel(z[:, :V].float(), zf.grad) < 6e-3
+    assert not z[:, V:].any()
+    z2 = torch.zeros(M, ld, device=dev, dtype=BF)
+    call("plb_masked_ce", ptr(z2), ld, M, V, ptr(labels), ptr(w), ptr(row_loss), ptr(loss), 1, S())  # accumulate
+    assert abs(loss.item() - (ref_rows.sum().item() + (w * math.log(V)).sum().item())) < 1e-4
+    call("plb_masked_ce", ptr(z2), ld, 0, V, ptr(labels), ptr(w), ptr(row_loss), ptr(loss), 0, S())  # empty -> 0
+    assert loss.item() == 0.0
+
+
+@pytest.mark.parametrize("T,N", [(3000, 2304), (100, 188), (98304, 768)])
+def test_colsum(dev, T, N):
+    ld = (N + 7) // 8 * 8
+    x = torch.zeros(T, ld, device=dev, dtype=BF)
+    x[:, :N] = torch.randn(T, N, device=dev).to(BF)
+    out = torch.ones(N, device=dev)
+    call("plb_colsum", ptr(x), ld, T, N, ptr(out), S())
+    assert rel(out - 1, x[:, :N].float().sum(0)) < 1e-4
+
+
+# ------------------------------------------------------------------------------------------ AdamW
+def test_adamw_matches_torch(dev):
+    n = 4096 * 3 + 64
+    p = torch.randn(n, device=dev)
+    ref_p = p.clone().requires_grad_(True)
+    opt = torch.optim.AdamW([ref_p], lr=7e-5)
+    m, v = torch.zeros(n, device=dev), torch.zeros(n, device=dev)
+    shadow = torch.zeros(n, device=dev, dtype=BF)
+    for step in range(1, 4):
+        g = torch.randn(n, device=dev) * 0.01
+        ref_p.grad = g.clone()
+        opt.step()
+        gg = (g * 2).contiguous()  # grad_scale 0.5 undoes this (1/world after a SUM all-reduce)
+        call("plb_adamw_step", ptr(p), ptr(gg), ptr(m), ptr(v), ptr(shadow), n, step, 7e-5, 0.9, 0.999, 1e-8, 0.01, 0.5, 1, S())
+        assert not gg.any()  # gradient arena zeroed for the next accumulation
+        upd, upd_ref = p - ref_p.detach(), None
+        assert (p - ref_p.detach()).abs().max() < 2e-7
+    assert torch.equal(shadow, p.to(BF))
+    st = opt.state[ref_p]
+    assert rel(m, st["exp_avg"]) < 1e-6 and rel(v, st["exp_avg_sq"]) < 1e-6
