@@ -324,7 +324,7 @@ def test_adamw_matches_torch(dev):
         call("plb_adamw_step", ptr(p), ptr(gg), ptr(m), ptr(v), ptr(shadow), n, step, 7e-5, 0.9, 0.999, 1e-8, 0.01, 0.5, 1, S())
         assert not gg.any()  # gradient arena zeroed for the next accumulation
         upd, upd_ref = p - ref_p.detach(), None
-        assert (p - ref_p.detach()).abs().max() < 2e-7
+        assert (p - ref_p.detach()).abs().max() < 1e-6  # a few fp32 ulps at |p| ~ 4 (op order differs from torch)
     assert torch.equal(shadow, p.to(BF))
     st = opt.state[ref_p]
     assert rel(m, st["exp_avg"]) < 1e-6 and rel(v, st["exp_avg_sq"]) < 1e-6
