@@ -133,6 +133,12 @@ int plb_attn_bwd(const void* qkv, int ld_qkv, const int32_t* seq_start, const in
                  const void* ctx, const void* dctx, int ld_ctx, const float* lse2, float* delta,
                  void* dqkv, int ld_dqkv, plb_stream_t stream);
 
+/* tcgen05 / TMEM implementation of the same contract (sequences up to 512 rows): K and V of a (sequence, head)
+ * are TMA-loaded once into shared memory, S and O accumulate in tensor memory. */
+int plb_attn_fwd_tc(const void* qkv, int ld_qkv, const int32_t* seq_start, const int32_t* q_len,
+                    const int32_t* kv_len, int B, int heads, int head_dim, int max_q_len, int total_rows,
+                    void* ctx, int ld_ctx, float* lse2, plb_stream_t stream);
+
 /* ---- a8: masked-row loss ----------------------------------------------------------------------------
  * R/train.py:107-131 calculate_phoneme_loss.  The host flattens masked_indices into rows[M] (= b*L + i, in the
  * reference's order) and weights[M] = 1 / (count * n_b); only those rows go through the heads.

@@ -240,7 +240,7 @@ class Engine:
         for l in range(c.num_hidden_layers):
             A = self.acts[l if train else l % 2]
             self._gemm(GEMM_FWD, EPI_NONE, T, 3 * H, H, x, H, wqkv, H, A["qkv"], 3 * H, bias=bqkv)
-            call("plb_attn_fwd", ptr(A["qkv"]), 3 * H, ptr(b.seq_start), ptr(b.q_len), ptr(b.kv_len), b.B, nh, H // nh,
+            call("plb_attn_fwd_tc", ptr(A["qkv"]), 3 * H, ptr(b.seq_start), ptr(b.q_len), ptr(b.kv_len), b.B, nh, H // nh,
                  b.L, self._cap_T, ptr(A["ctx"]), H, ptr(A["lse"]), s)
             self.launches += 1
             self._gemm(GEMM_FWD, EPI_RESIDUAL, T, H, H, A["ctx"], H, self.w(att + "dense.weight"), H, A["z1"], H,

@@ -1,0 +1,50 @@
+"""Times the attention kernels at the BASELINE shape (192 sequences x 512 rows x 12 heads x 64) through the C ABI."""
+import math
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch  # noqa: E402
+
+from plbert_b200._abi import call, load, ptr  # noqa: E402
+
+
+def main():
+    load()
+    dev = torch.device("cuda:0")
+    B, L, nh = 192, 512, 12
+    H, T = nh * 64, B * L
+    qkv = torch.randn(T, 3 * H, device=dev).to(torch.bfloat16)
+    lens = torch.full((B,), L, device=dev, dtype=torch.int32)
+    seq_start = torch.arange(B, device=dev, dtype=torch.int32) * L
+    ctx = torch.empty(T, H, device=dev, dtype=torch.bfloat16)
+    dctx = torch.randn(T, H, device=dev).to(torch.bfloat16)
+    dqkv = torch.empty(T, 3 * H, device=dev, dtype=torch.bfloat16)
+    lse = torch.empty(nh, T, device=dev)
+    delta = torch.empty(nh, T, device=dev)
+    S = torch.cuda.current_stream().cuda_stream
+    fwd_flops = 4.0 * B * nh * L * L * 64
+
+    def timeit(fn, flops, label, iters=10):
+        for _ in range(3):
+            fn()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / iters
+        print(f"{label:28s} {ms * 1e3:9.1f} us  {flops / ms * 1e-9:8.1f} TFLOP/s (algorithmic)")
+
+    names = [n for n in ("plb_attn_fwd", "plb_attn_fwd_tc") if hasattr(load(), n)]
+    for n in names:
+        timeit(lambda: call(n, ptr(qkv), 3 * H, ptr(seq_start), ptr(lens), ptr(lens), B, nh, 64, L, T, ptr(ctx), H, ptr(lse), S),
+               fwd_flops, n)
+    for n in [n for n in ("plb_attn_bwd", "plb_attn_bwd_tc") if hasattr(load(), n)]:
+        timeit(lambda: call(n, ptr(qkv), 3 * H, ptr(seq_start), ptr(lens), ptr(lens), B, nh, 64, L, T, ptr(ctx), ptr(dctx), H,
+                            ptr(lse), ptr(delta), ptr(dqkv), 3 * H, S), 2.5 * fwd_flops, n)
+
+
+if __name__ == "__main__":
+    main()

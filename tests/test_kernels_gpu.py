@@ -221,7 +221,8 @@ def _attn_ref(qkv, B, L, nh, lens):
 
 @pytest.mark.parametrize("B,L,nh,lens", [(2, 64, 2, [64, 64]), (3, 200, 2, [200, 77, 1]), (2, 512, 12, [512, 300]),
                                          (4, 130, 3, [130, 129, 65, 64])])
-def test_attention_fwd_bwd(dev, B, L, nh, lens):
+@pytest.mark.parametrize("fwd", ["plb_attn_fwd", "plb_attn_fwd_tc"])
+def test_attention_fwd_bwd(dev, B, L, nh, lens, fwd):
     H, T = nh * 64, B * L
     qkv = torch.randn(T, 3 * H, device=dev).to(BF)
     lens_t = torch.tensor(lens, device=dev, dtype=torch.int32)
@@ -229,7 +230,7 @@ def test_attention_fwd_bwd(dev, B, L, nh, lens):
     q_len = torch.full((B,), L, device=dev, dtype=torch.int32)
     ctx = torch.full((T, H), float("nan"), device=dev, dtype=BF)
     lse = torch.zeros(nh, T, device=dev)
-    call("plb_attn_fwd", ptr(qkv), 3 * H, ptr(seq_start), ptr(q_len), ptr(lens_t), B, nh, 64, L, T, ptr(ctx), H, ptr(lse), S())
+    call(fwd, ptr(qkv), 3 * H, ptr(seq_start), ptr(q_len), ptr(lens_t), B, nh, 64, L, T, ptr(ctx), H, ptr(lse), S())
     qf = qkv.float().requires_grad_(True)
     ref, ref_lse = _attn_ref(qf, B, L, nh, lens_t.long())
     assert torch.isfinite(ctx.float()).all()  # padded QUERY rows are computed too, like the reference
