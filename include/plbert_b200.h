@@ -159,12 +159,13 @@ int plb_colsum(const void* x, int ld, int T, int N, float* out_accum, plb_stream
 /* ---- a10: fused AdamW --------------------------------------------------------------------------------
  * torch.optim.AdamW as built at R/train.py:272 (rule: torch/optim/adam.py:417-419,457,476,531-547) over flat
  * fp32 arenas of n elements (n % 4 == 0).  `step` is the 1-based step count of these parameters; gradients are
- * multiplied by grad_scale first (1/world_size after a SUM all-reduce).  If bf16_shadow != NULL the updated
+ * multiplied by grad_scale first (1/world_size after a SUM all-reduce).  Hyper-parameters are host doubles (torch keeps
+ * them as python floats and rounds derived scalars once).  If bf16_shadow != NULL the updated
  * parameters are also written as bf16 (the copy the GEMMs read); if zero_grad != 0 the gradient arena is
  * zeroed for the next step's in-place accumulation. */
 int plb_adamw_step(float* params, float* grads, float* exp_avg, float* exp_avg_sq, void* bf16_shadow,
-                   long n, int step, float lr, float beta1, float beta2, float eps, float weight_decay,
-                   float grad_scale, int zero_grad, plb_stream_t stream);
+                   long n, int step, double lr, double beta1, double beta2, double eps, double weight_decay,
+                   double grad_scale, int zero_grad, plb_stream_t stream);
 int plb_cast_bf16(const float* src, void* dst, long n, plb_stream_t stream);
 
 #ifdef __cplusplus

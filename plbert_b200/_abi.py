@@ -7,7 +7,7 @@ from __future__ import annotations
 
 import ctypes
 import os
-from ctypes import c_char_p, c_float, c_int, c_long, c_void_p
+from ctypes import c_char_p, c_double, c_float, c_int, c_long, c_void_p
 
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(PKG_DIR, "libplbert_b200.so")
@@ -43,7 +43,7 @@ SIGNATURES = {
     "plb_scatter_add_rows": [P, c_int, P, c_int, c_int, P, c_int, P],
     "plb_masked_ce": [P, c_int, c_int, c_int, P, P, P, P, c_int, P],
     "plb_colsum": [P, c_int, c_int, c_int, P, P],
-    "plb_adamw_step": [P, P, P, P, P, c_long, c_int, c_float, c_float, c_float, c_float, c_float, c_float, c_int, P],
+    "plb_adamw_step": [P, P, P, P, P, c_long, c_int, c_double, c_double, c_double, c_double, c_double, c_double, c_int, P],
     "plb_cast_bf16": [P, P, c_long, P],
 }
 

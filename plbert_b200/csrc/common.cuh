@@ -219,6 +219,13 @@ __device__ __forceinline__ uint4 lds128(uint32_t saddr) {
   return v;
 }
 
+// read-only shared data (no memory clobber: the compiler may hoist / batch these loads)
+__device__ __forceinline__ float4 lds128_ro(uint32_t saddr) {
+  float4 v;
+  asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr));
+  return v;
+}
+
 // ---- small math / packing ---------------------------------------------------------------------
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);

@@ -56,7 +56,8 @@ struct SmemLayout {
   static constexpr int kBarOff = kEpiOff + kBufs * EPI_BUF_BYTES;
   // full[kStages], empty[kStages], tmem_full[2], tmem_empty[2], epi_in[kBufs], tmem ptr
   static constexpr int kNumBars = 2 * kStages + 4 + kBufs;
-  static constexpr int kBytes = kBarOff + kNumBars * 8 + 16;
+  static constexpr int kBiasOff = kBarOff + kNumBars * 8 + 16;   // fp32 bias of the current tile: BN floats
+  static constexpr int kBytes = kBiasOff + BN * 4;
   static constexpr int kAlloc = kBytes + 1024;  // slack for manual 1024 B alignment
 };
 
@@ -188,6 +189,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CU
     const int row = quad * 32 + lane;      // accumulator row owned by this thread
     const bool leader = (threadIdx.x == 64);
     uint8_t* epi_smem = smem + L::kEpiOff;
+    float* s_bias = reinterpret_cast<float*>(smem + L::kBiasOff);
+    const uint32_t s_bias_addr = smem_u32(s_bias);
+    const int epi_tid = threadIdx.x - 64;
     constexpr bool kHasAuxIn = (kEpi == kResidual || kEpi == kGeluBwd);
     constexpr bool kDual = (kEpi == kGelu);
     constexpr int kSlots = kDual ? kBufs / 2 : kBufs;
@@ -226,6 +230,16 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CU
       int m_blk, n_blk, k_begin, k_end;
       unit_coords(p, u, m_blk, n_blk, k_begin, k_end);
       const int m0 = m_blk * BM, n0 = n_blk * BN;
+      if (kEpi != kAtomicF32 && p.bias != nullptr) {
+        // stage this tile's bias in shared memory: the per-element __ldg it replaces serialised the epilogue
+        // (the compiler cannot hoist global loads across the generic staging stores)
+#pragma unroll
+        for (int i = 0; i < BN / EPI_THREADS; ++i) {
+          const int n = n0 + epi_tid + i * EPI_THREADS;
+          s_bias[epi_tid + i * EPI_THREADS] = (n < p.N) ? __ldg(p.bias + n) : 0.f;
+        }
+        epi_bar_sync();
+      }
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BN;
@@ -263,7 +277,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CU
           if (nc >= p.N) break;
           const int slot = seq % kSlots;
           uint8_t* buf = epi_smem + (kDual ? 2 * slot : slot) * EPI_BUF_BYTES;
-          uint8_t* my_row = buf + row * 128;
+          const uint32_t my_row = smem_u32(buf) + row * 128;
 
           uint32_t v0[32], v1[32];
           tmem_ld_32x32(taddr + c * EPI_COLS, v0);
@@ -277,21 +291,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CU
 #pragma unroll
             for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(j < 4 ? v0[j * 8 + i] : v1[(j - 4) * 8 + i]);
             if (p.bias != nullptr) {
-              const int n = nc + j * 8;
-              if (n + 7 < p.N) {
-                const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + n));
-                const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + n + 4));
-                f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
-                f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
-              } else {
-#pragma unroll
-                for (int i = 0; i < 8; ++i)
-                  if (n + i < p.N) f[i] += __ldg(p.bias + n + i);
-              }
+              const float4 b0 = lds128_ro(s_bias_addr + (c * EPI_COLS + j * 8) * 4);
+              const float4 b1 = lds128_ro(s_bias_addr + (c * EPI_COLS + j * 8 + 4) * 4);
+              f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
+              f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
             }
-            uint4* piece = reinterpret_cast<uint4*>(my_row + ((j ^ (row & 7)) << 4));
+            const uint32_t piece = my_row + ((j ^ (row & 7)) << 4);
             if (kHasAuxIn) {
-              const uint4 a = *piece;
+              const uint4 a = lds128(piece);
               const uint32_t aw[4] = {a.x, a.y, a.z, a.w};
 #pragma unroll
               for (int i = 0; i < 4; ++i) {
@@ -310,7 +317,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CU
               uint4 pu;
               pu.x = pack_bf16x2(f[0], f[1]); pu.y = pack_bf16x2(f[2], f[3]);
               pu.z = pack_bf16x2(f[4], f[5]); pu.w = pack_bf16x2(f[6], f[7]);
-              *reinterpret_cast<uint4*>(my_row + EPI_BUF_BYTES + ((j ^ (row & 7)) << 4)) = pu;
+              sts128(my_row + EPI_BUF_BYTES + ((j ^ (row & 7)) << 4), pu);
               // gelu is evaluated on the bf16-rounded u so that forward and backward see the same value
               const uint32_t uw[4] = {pu.x, pu.y, pu.z, pu.w};
 #pragma unroll
@@ -322,7 +329,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CU
             uint4 o;
             o.x = pack_bf16x2(f[0], f[1]); o.y = pack_bf16x2(f[2], f[3]);
             o.z = pack_bf16x2(f[4], f[5]); o.w = pack_bf16x2(f[6], f[7]);
-            *piece = o;
+            sts128(piece, o);
           }
           fence_proxy_async_smem();
           if (leader && !kHasAuxIn) {

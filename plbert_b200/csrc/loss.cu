@@ -107,7 +107,24 @@ __global__ void __launch_bounds__(256) colsum_kernel(const __nv_bfloat16* __rest
   const int col = blockIdx.x * 256 + lane * 8;
   float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   if (col < N) {
-    for (int t = blockIdx.y * 8 + warp; t < T; t += gridDim.y * 8) {
+    const int stride = gridDim.y * 8;
+    int t = blockIdx.y * 8 + warp;
+    // four independent 16-byte loads in flight per lane
+    for (; t + 3 * stride < T; t += 4 * stride) {
+      uint4 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) v[u] = *reinterpret_cast<const uint4*>(x + static_cast<size_t>(t + u * stride) * ld + col);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const uint32_t w[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          acc[2 * i] += bf16_lo(w[i]);
+          acc[2 * i + 1] += bf16_hi(w[i]);
+        }
+      }
+    }
+    for (; t < T; t += stride) {
       const uint4 v = *reinterpret_cast<const uint4*>(x + static_cast<size_t>(t) * ld + col);
       const uint32_t w[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
@@ -186,7 +203,7 @@ extern "C" int plb_colsum(const void* x, int ld, int T, int N, float* out_accum,
   PLB_REQUIRE(ld % 8 == 0 && ld >= (N + 7) / 8 * 8 && (reinterpret_cast<uintptr_t>(x) % 16) == 0, PLB_ERR_ARG,
               "colsum: ld must be a multiple of 8 covering N rounded up to 8, x 16-byte aligned");
   const int gx = (N + 255) / 256;
-  int gy = (2 * sm_count() + gx - 1) / gx;
+  int gy = (8 * sm_count() + gx - 1) / gx;
   if (gy > (T + 7) / 8) gy = (T + 7) / 8;
   colsum_kernel<<<dim3(gx, gy), 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const __nv_bfloat16*>(x), ld, T, N,
                                                                             out_accum);

@@ -81,83 +81,93 @@ __global__ void __launch_bounds__(WARPS * 32) ln_fwd_kernel(const __nv_bfloat16*
 }
 
 // dz = LN'(dy); dw += sum dy*xhat; db += sum dy; colsum += sum dz (bias gradient of the producing Linear)
-template <int MAXC>
-__global__ void __launch_bounds__(WARPS * 32)
+// A row is split over WPR warps (each lane owns ONE 16-byte chunk), so the per-thread column partials are only
+// 3 x 8 registers and two 12-warp CTAs fit per SM; the two row statistics cross the WPR warps through shared memory.
+constexpr int LNB_ROWS = 4;  // rows in flight per CTA
+template <int WPR>
+__global__ void __launch_bounds__(LNB_ROWS * WPR * 32)
 ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ z,
               const float* __restrict__ stats, const float* __restrict__ w, int T, int H,
               __nv_bfloat16* __restrict__ dz, float* __restrict__ dw_acc, float* __restrict__ db_acc,
               float* __restrict__ colsum_acc) {
-  extern __shared__ float s_red[];  // [3][H]
+  extern __shared__ float s_red[];                      // [3][H] column partials of the CTA
+  __shared__ float s_row[2][LNB_ROWS][WPR][2];          // per-row partial statistics (double buffered)
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int rslot = warp / WPR, wr = warp % WPR;        // row slot of this warp, position within the row
+  const int c = wr * 32 + lane;                         // 16-byte chunk of the row owned by this thread
   const int nchunk = H >> 3;
+  const bool active = c < nchunk;
   for (int i = threadIdx.x; i < 3 * H; i += blockDim.x) s_red[i] = 0.f;
   __syncthreads();
 
-  float ww[MAXC][8], pdw[MAXC][8], pdb[MAXC][8], pcs[MAXC][8];
+  float ww[8], pdw[8], pdb[8], pcs[8];
 #pragma unroll
-  for (int i = 0; i < MAXC; ++i) {
-    const int c = lane + 32 * i;
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      ww[i][k] = (c < nchunk) ? __ldg(w + c * 8 + k) : 0.f;
-      pdw[i][k] = pdb[i][k] = pcs[i][k] = 0.f;
-    }
+  for (int k = 0; k < 8; ++k) {
+    ww[k] = active ? __ldg(w + c * 8 + k) : 0.f;
+    pdw[k] = pdb[k] = pcs[k] = 0.f;
   }
   const float invH = 1.f / H;
-  for (int row = blockIdx.x * WARPS + warp; row < T; row += gridDim.x * WARPS) {
-    const uint4* zr = reinterpret_cast<const uint4*>(z + static_cast<size_t>(row) * H);
-    const uint4* gr = reinterpret_cast<const uint4*>(dy + static_cast<size_t>(row) * H);
-    const float mean = stats[2 * row], rstd = stats[2 * row + 1];
-    float xh[MAXC][8], g[MAXC][8];
-    float s1 = 0.f, s2 = 0.f;
-#pragma unroll
-    for (int i = 0; i < MAXC; ++i) {
-      const int c = lane + 32 * i;
-      if (c < nchunk) {
-        float zz[8], dd[8];
-        unpack8(zr[c], zz);
-        unpack8(gr[c], dd);
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          xh[i][k] = (zz[k] - mean) * rstd;
-          pdw[i][k] += dd[k] * xh[i][k];
-          pdb[i][k] += dd[k];
-          g[i][k] = dd[k] * ww[i][k];
-          s1 += g[i][k];
-          s2 += g[i][k] * xh[i][k];
-        }
-      }
+  int it = 0;
+  for (int row0 = blockIdx.x * LNB_ROWS; row0 < T; row0 += gridDim.x * LNB_ROWS, ++it) {
+    const int row = row0 + rslot;
+    const bool rv = row < T;
+    float xh[8], g[8];
+    float s1 = 0.f, s2 = 0.f, mean = 0.f, rstd = 0.f;
+    if (rv) {
+      mean = stats[2 * row];
+      rstd = stats[2 * row + 1];
     }
-    s1 = warp_sum(s1) * invH;
-    s2 = warp_sum(s2) * invH;
-    uint4* outr = reinterpret_cast<uint4*>(dz + static_cast<size_t>(row) * H);
-#pragma unroll
-    for (int i = 0; i < MAXC; ++i) {
-      const int c = lane + 32 * i;
-      if (c < nchunk) {
-        float o[8];
-#pragma unroll
-        for (int k = 0; k < 8; ++k) o[k] = rstd * (g[i][k] - s1 - xh[i][k] * s2);
-        const uint4 packed = pack8(o);
-        outr[c] = packed;
-        // the bias gradient must see exactly the values the GEMMs will read -> sum the rounded outputs
-        float r[8];
-        unpack8(packed, r);
-#pragma unroll
-        for (int k = 0; k < 8; ++k) pcs[i][k] += r[k];
-      }
-    }
-  }
-#pragma unroll
-  for (int i = 0; i < MAXC; ++i) {
-    const int c = lane + 32 * i;
-    if (c < nchunk) {
+    if (rv && active) {
+      float zz[8], dd[8];
+      unpack8(*reinterpret_cast<const uint4*>(z + static_cast<size_t>(row) * H + c * 8), zz);
+      unpack8(*reinterpret_cast<const uint4*>(dy + static_cast<size_t>(row) * H + c * 8), dd);
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
-        atomicAdd(&s_red[c * 8 + k], pdw[i][k]);
-        atomicAdd(&s_red[H + c * 8 + k], pdb[i][k]);
-        atomicAdd(&s_red[2 * H + c * 8 + k], pcs[i][k]);
+        xh[k] = (zz[k] - mean) * rstd;
+        pdw[k] += dd[k] * xh[k];
+        pdb[k] += dd[k];
+        g[k] = dd[k] * ww[k];
+        s1 += g[k];
+        s2 += g[k] * xh[k];
       }
+    }
+    s1 = warp_sum(s1);
+    s2 = warp_sum(s2);
+    if (WPR > 1) {
+      if (lane == 0) {
+        s_row[it & 1][rslot][wr][0] = s1;
+        s_row[it & 1][rslot][wr][1] = s2;
+      }
+      asm volatile("bar.sync %0, %1;" ::"r"(1 + rslot), "n"(WPR * 32) : "memory");
+      s1 = 0.f;
+      s2 = 0.f;
+#pragma unroll
+      for (int q = 0; q < WPR; ++q) {
+        s1 += s_row[it & 1][rslot][q][0];
+        s2 += s_row[it & 1][rslot][q][1];
+      }
+    }
+    s1 *= invH;
+    s2 *= invH;
+    if (rv && active) {
+      float o[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) o[k] = rstd * (g[k] - s1 - xh[k] * s2);
+      const uint4 packed = pack8(o);
+      *reinterpret_cast<uint4*>(dz + static_cast<size_t>(row) * H + c * 8) = packed;
+      // the bias gradient must see exactly the values the GEMMs will read -> sum the rounded outputs
+      float r[8];
+      unpack8(packed, r);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) pcs[k] += r[k];
+    }
+  }
+  if (active) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      atomicAdd(&s_red[c * 8 + k], pdw[k]);
+      atomicAdd(&s_red[H + c * 8 + k], pdb[k]);
+      atomicAdd(&s_red[2 * H + c * 8 + k], pcs[k]);
     }
   }
   __syncthreads();
@@ -339,7 +349,8 @@ extern "C" int plb_ln_bwd(const void* dy, const void* z, const float* stats, con
               8 * 32 * LN_MAXC);
   const int nc = (H / 8 + 31) / 32;
   auto kern = nc == 1 ? ln_bwd_kernel<1> : nc == 2 ? ln_bwd_kernel<2> : nc == 3 ? ln_bwd_kernel<3> : ln_bwd_kernel<4>;
-  kern<<<row_grid(T, 4), WARPS * 32, 3 * H * sizeof(float), static_cast<cudaStream_t>(stream)>>>(
+  const int need = (T + LNB_ROWS - 1) / LNB_ROWS, cap = sm_count() * 4;
+  kern<<<need < cap ? need : cap, LNB_ROWS * nc * 32, 3 * H * sizeof(float), static_cast<cudaStream_t>(stream)>>>(
       static_cast<const __nv_bfloat16*>(dy), static_cast<const __nv_bfloat16*>(z), stats, w, T, H,
       static_cast<__nv_bfloat16*>(dz), dw_accum, db_accum, colsum_accum);
   return check_launch("plb_ln_bwd");

@@ -13,8 +13,9 @@ namespace {
 
 __global__ void __launch_bounds__(256)
 adamw_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
-             __nv_bfloat16* __restrict__ shadow, long n, float lr, float beta1, float beta2, float eps, float decay,
-             float step_size, float inv_bc2_sqrt, float grad_scale, int zero_grad) {
+             __nv_bfloat16* __restrict__ shadow, long n, float beta1, float beta2, float one_minus_beta1,
+             float one_minus_beta2, float eps, float decay, float step_size, float inv_bc2_sqrt, float grad_scale,
+             int zero_grad) {
   const long n4 = n >> 2;
   const long stride = static_cast<long>(gridDim.x) * blockDim.x;
   for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < n4; i += stride) {
@@ -30,8 +31,8 @@ adamw_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m
     for (int k = 0; k < 4; ++k) {
       const float gk = ga[k] * grad_scale;
       pa[k] *= decay;
-      ma[k] = ma[k] * beta1 + gk * (1.f - beta1);
-      va[k] = va[k] * beta2 + gk * gk * (1.f - beta2);
+      ma[k] = ma[k] * beta1 + gk * one_minus_beta1;
+      va[k] = va[k] * beta2 + gk * gk * one_minus_beta2;
       const float denom = sqrtf(va[k]) * inv_bc2_sqrt + eps;
       pa[k] -= step_size * (ma[k] / denom);
     }
@@ -72,8 +73,8 @@ int flat_grid(long n4) {
 using namespace plb;
 
 extern "C" int plb_adamw_step(float* params, float* grads, float* exp_avg, float* exp_avg_sq, void* bf16_shadow,
-                              long n, int step, float lr, float beta1, float beta2, float eps, float weight_decay,
-                              float grad_scale, int zero_grad, plb_stream_t stream) {
+                              long n, int step, double lr, double beta1, double beta2, double eps, double weight_decay,
+                              double grad_scale, int zero_grad, plb_stream_t stream) {
   PLB_REQUIRE(params && grads && exp_avg && exp_avg_sq && n > 0 && step >= 1, PLB_ERR_ARG, "adamw: bad arguments");
   PLB_REQUIRE(n % 4 == 0, PLB_ERR_ARG, "adamw: arena length must be a multiple of 4 (pad the arena)");
   PLB_REQUIRE((reinterpret_cast<uintptr_t>(params) % 16) == 0 && (reinterpret_cast<uintptr_t>(grads) % 16) == 0 &&
@@ -81,14 +82,16 @@ extern "C" int plb_adamw_step(float* params, float* grads, float* exp_avg, float
                   (reinterpret_cast<uintptr_t>(bf16_shadow) % 8) == 0,
               PLB_ERR_ARG, "adamw: arenas must be 16-byte aligned");
   // bias corrections in double on the host, exactly like torch's python-scalar path (adam.py:531-547)
-  const double bc1 = 1.0 - pow(static_cast<double>(beta1), step);
-  const double bc2 = 1.0 - pow(static_cast<double>(beta2), step);
-  const float step_size = static_cast<float>(static_cast<double>(lr) / bc1);
+  // every derived scalar is formed in double from the caller's doubles and rounded once, like torch's python scalars
+  const double bc1 = 1.0 - pow(beta1, step);
+  const double bc2 = 1.0 - pow(beta2, step);
+  const float step_size = static_cast<float>(lr / bc1);
   const float inv_bc2_sqrt = static_cast<float>(1.0 / sqrt(bc2));
-  const float decay = static_cast<float>(1.0 - static_cast<double>(lr) * weight_decay);
+  const float decay = static_cast<float>(1.0 - lr * weight_decay);
   adamw_kernel<<<flat_grid(n / 4), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      params, grads, exp_avg, exp_avg_sq, static_cast<__nv_bfloat16*>(bf16_shadow), n, lr, beta1, beta2, eps, decay,
-      step_size, inv_bc2_sqrt, grad_scale, zero_grad);
+      params, grads, exp_avg, exp_avg_sq, static_cast<__nv_bfloat16*>(bf16_shadow), n, static_cast<float>(beta1),
+      static_cast<float>(beta2), static_cast<float>(1.0 - beta1), static_cast<float>(1.0 - beta2), static_cast<float>(eps),
+      decay, step_size, inv_bc2_sqrt, static_cast<float>(grad_scale), zero_grad);
   return check_launch("plb_adamw_step");
 }
 
