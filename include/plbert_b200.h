@@ -139,6 +139,11 @@ int plb_attn_fwd_tc(const void* qkv, int ld_qkv, const int32_t* seq_start, const
                     const int32_t* kv_len, int B, int heads, int head_dim, int max_q_len, int total_rows,
                     void* ctx, int ld_ctx, float* lse2, plb_stream_t stream);
 
+int plb_attn_bwd_tc(const void* qkv, int ld_qkv, const int32_t* seq_start, const int32_t* q_len,
+                    const int32_t* kv_len, int B, int heads, int head_dim, int max_q_len, int total_rows,
+                    const void* ctx, const void* dctx, int ld_ctx, const float* lse2, float* delta,
+                    void* dqkv, int ld_dqkv, plb_stream_t stream);
+
 /* ---- a8: masked-row loss ----------------------------------------------------------------------------
  * R/train.py:107-131 calculate_phoneme_loss.  The host flattens masked_indices into rows[M] (= b*L + i, in the
  * reference's order) and weights[M] = 1 / (count * n_b); only those rows go through the heads.

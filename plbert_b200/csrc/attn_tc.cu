@@ -346,3 +346,593 @@ extern "C" int plb_attn_fwd_tc(const void* qkv, int ld_qkv, const int32_t* seq_s
       tm, p, static_cast<__nv_bfloat16*>(ctx), ld_ctx, lse2);
   return check_launch("plb_attn_fwd_tc");
 }
+
+// =================================================================================================================
+// Backward.  dS = P o (dP - delta), dQ = scale dS K, dK = scale dS^T Q, dV = P^T dO  (SURVEY.md appendix A), with
+// P recomputed from the saved log-sum-exp.  Two kernels so that every accumulator has ONE owner and no atomics are
+// needed: the dQ kernel owns query tiles, the dK/dV kernel owns key tiles.  Both use the forward's structure: one CTA
+// per (sequence, head), three warpgroups (control / softmax group 0 / softmax group 1), tiles alternate between the
+// groups, the single MMA thread serves whichever group is ready, 64-wide chunks along the contracted sequence axis.
+// =================================================================================================================
+namespace plb {
+namespace {
+
+constexpr int BC = 64;                       // chunk width (keys in the dQ kernel, queries in the dK/dV kernel)
+constexpr int CHUNK8K = BC * 128;            // 64 rows of a swizzled [rows x 64] bf16 tile
+
+// delta[h, row] = sum_d dO[row, h*64 + d] * O[row, h*64 + d]   (one warp per row, 16-byte loads)
+__global__ void __launch_bounds__(256) attn_delta_kernel(const __nv_bfloat16* __restrict__ dctx,
+                                                         const __nv_bfloat16* __restrict__ ctx, int ld, int T, int heads,
+                                                         int total_rows, float* __restrict__ delta) {
+  const int lane = threadIdx.x & 31;
+  const int chunks = heads * 8;  // 16-byte chunks per row; 8 chunks per head
+  for (int row = blockIdx.x * 8 + (threadIdx.x >> 5); row < T; row += gridDim.x * 8) {
+    for (int c0 = 0; c0 < chunks; c0 += 32) {
+      const int c = c0 + lane;
+      float acc = 0.f;
+      if (c < chunks) {
+        const uint4 a = *reinterpret_cast<const uint4*>(dctx + static_cast<size_t>(row) * ld + c * 8);
+        const uint4 o = *reinterpret_cast<const uint4*>(ctx + static_cast<size_t>(row) * ld + c * 8);
+        const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, ow[4] = {o.x, o.y, o.z, o.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) acc += bf16_lo(aw[i]) * bf16_lo(ow[i]) + bf16_hi(aw[i]) * bf16_hi(ow[i]);
+      }
+      acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+      acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+      acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+      if ((lane & 7) == 0 && c < chunks) delta[static_cast<size_t>(c >> 3) * total_rows + row] = acc;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ dQ kernel
+struct DqSmem {
+  static constexpr int kK = 0;                               // K of the head, resident: 4 boxes of [128 x 64]
+  static constexpr int kV = kK + MAX_BOXES * TILE16K;        // V of the head, resident
+  static constexpr int kQ = kV + MAX_BOXES * TILE16K;        // Q tile per group
+  static constexpr int kDO = kQ + 2 * TILE16K;               // dO tile per group
+  static constexpr int kDS = kDO + 2 * TILE16K;              // dS chunk [128 x 64] per group (also dQ staging)
+  static constexpr int kBar = kDS + 2 * TILE16K;
+  static constexpr int kNumBars = 2 * MAX_BOXES + 2 * 7;
+  static constexpr int kAlloc = kBar + kNumBars * 8 + 16;
+};
+static_assert(DqSmem::kAlloc <= 232448, "dQ kernel exceeds the 227 KB shared-memory limit");
+enum { QDO_FULL = 0, QDO_EMPTY, SD_FULL, SD_FREE, DS_READY, DQ_DONE, DQ_FREE };
+
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_dctx,
+                      const AttnTcParams p, const float* __restrict__ lse2, const float* __restrict__ delta,
+                      __nv_bfloat16* __restrict__ dqkv, int ld_dqkv) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if (smem_u32(smem) & 1023u) __trap();
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + DqSmem::kBar);
+  uint64_t* k_full = bars;
+  uint64_t* v_full = bars + MAX_BOXES;
+  uint64_t* gbar = bars + 2 * MAX_BOXES;  // [2][7]
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + DqSmem::kNumBars);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.x / p.heads, h = blockIdx.x % p.heads;
+  const int row_base = p.seq_start[b], nq = p.q_len[b], nk = p.kv_len[b];
+  const int H = p.heads * D;
+  const int n_chunks = (nk + BC - 1) / BC;
+  const int n_boxes = (nk + 127) / 128;
+  const int n_tiles = (nq + QT - 1) / QT;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tm_qkv);
+    tma_prefetch_desc(&tm_dctx);
+    for (int i = 0; i < 2 * MAX_BOXES; ++i) mbar_init(&bars[i], 1);
+    for (int g = 0; g < 2; ++g) {
+      uint64_t* gb = gbar + g * 7;
+      mbar_init(&gb[QDO_FULL], 1);
+      mbar_init(&gb[QDO_EMPTY], 1);
+      mbar_init(&gb[SD_FULL], 1);
+      mbar_init(&gb[SD_FREE], 4);
+      mbar_init(&gb[DS_READY], 4);
+      mbar_init(&gb[DQ_DONE], 1);
+      mbar_init(&gb[DQ_FREE], 4);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_ptr_smem, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+  // TMEM columns per group g: S [g*192, +64), dP [g*192 + 64, +64), dQ [g*192 + 128, +64)
+
+  if (warp < 4) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_CONTROL));
+    if (warp == 0 && lane == 0) {
+      // ====================================== TMA producer ======================================
+      auto load_tile = [&](int g, int t) {
+        uint64_t* gb = gbar + g * 7;
+        mbar_arrive_expect_tx(&gb[QDO_FULL], 2 * TILE16K);
+        tma_load_2d(smem + DqSmem::kQ + g * TILE16K, &tm_qkv, &gb[QDO_FULL], h * D, row_base + t * QT);
+        tma_load_2d(smem + DqSmem::kDO + g * TILE16K, &tm_dctx, &gb[QDO_FULL], h * D, row_base + t * QT);
+      };
+      load_tile(0, 0);
+      mbar_arrive_expect_tx(&k_full[0], TILE16K);
+      tma_load_2d(smem + DqSmem::kK, &tm_qkv, &k_full[0], H + h * D, row_base);
+      mbar_arrive_expect_tx(&v_full[0], TILE16K);
+      tma_load_2d(smem + DqSmem::kV, &tm_qkv, &v_full[0], 2 * H + h * D, row_base);
+      if (n_tiles > 1) load_tile(1, 1);
+      for (int j = 1; j < n_boxes; ++j) {
+        mbar_arrive_expect_tx(&k_full[j], TILE16K);
+        tma_load_2d(smem + DqSmem::kK + j * TILE16K, &tm_qkv, &k_full[j], H + h * D, row_base + j * 128);
+        mbar_arrive_expect_tx(&v_full[j], TILE16K);
+        tma_load_2d(smem + DqSmem::kV + j * TILE16K, &tm_qkv, &v_full[j], 2 * H + h * D, row_base + j * 128);
+      }
+      for (int t = 2; t < n_tiles; ++t) {
+        const int g = t & 1, k = t >> 1;
+        mbar_wait(&gbar[g * 7 + QDO_EMPTY], (k - 1) & 1);
+        load_tile(g, t);
+      }
+    } else if (warp == 1 && lane == 0) {
+      // ====================================== MMA issuer ======================================
+      constexpr uint32_t idesc_sd = umma_idesc_bf16(128, BC, 0, 0);  // S = Q K^T, dP = dO V^T : all K-major
+      constexpr uint32_t idesc_dq = umma_idesc_bf16(128, D, 0, 1);   // dQ = dS K : A K-major, B MN-major
+      const uint32_t sK = smem_u32(smem + DqSmem::kK), sV = smem_u32(smem + DqSmem::kV);
+      int ks[2] = {0, 0}, js[2] = {0, 0}, kp[2] = {0, 0}, jp[2] = {0, 0};
+      uint32_t cs[2] = {0, 0}, cp[2] = {0, 0};
+      const int tiles_of[2] = {(n_tiles + 1) >> 1, n_tiles >> 1};
+      while (kp[0] < tiles_of[0] || kp[1] < tiles_of[1]) {
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {
+          uint64_t* gb = gbar + g * 7;
+          const uint32_t tg = tmem_base + g * 192;
+          // ---- dQ += dS_j K_j ----
+          if (kp[g] < tiles_of[g] && mbar_test(&gb[DS_READY], cp[g] & 1) &&
+              (jp[g] > 0 || mbar_test(&gb[DQ_FREE], (kp[g] & 1) ^ 1))) {
+            const int j = jp[g];
+            tc_fence_after();
+            const uint32_t sDS = smem_u32(smem + DqSmem::kDS + g * TILE16K);
+#pragma unroll
+            for (int kk = 0; kk < BC / 16; ++kk)
+              umma_bf16(tg + 128, umma_smem_desc(sDS + kk * 32, 16, 1024),
+                        umma_smem_desc(sK + j * CHUNK8K + kk * 2048, TILE16K, 1024), idesc_dq, (j > 0 || kk > 0));
+            umma_commit(&gb[DQ_DONE]);
+            ++cp[g];
+            if (++jp[g] == n_chunks) { jp[g] = 0; ++kp[g]; }
+          }
+          // ---- S_j = Q K_j^T and dP_j = dO V_j^T ----
+          if (ks[g] < tiles_of[g] && (cs[g] == 0 || mbar_test(&gb[SD_FREE], (cs[g] - 1) & 1)) &&
+              (js[g] > 0 || mbar_test(&gb[QDO_FULL], ks[g] & 1))) {
+            const int j = js[g];
+            mbar_wait(&k_full[j >> 1], 0);
+            mbar_wait(&v_full[j >> 1], 0);
+            tc_fence_after();
+            const uint32_t sQ = smem_u32(smem + DqSmem::kQ + g * TILE16K);
+            const uint32_t sDO = smem_u32(smem + DqSmem::kDO + g * TILE16K);
+#pragma unroll
+            for (int kk = 0; kk < D / 16; ++kk)
+              umma_bf16(tg, umma_smem_desc(sQ + kk * 32, 16, 1024),
+                        umma_smem_desc(sK + j * CHUNK8K + kk * 32, 16, 1024), idesc_sd, kk > 0);
+#pragma unroll
+            for (int kk = 0; kk < D / 16; ++kk)
+              umma_bf16(tg + 64, umma_smem_desc(sDO + kk * 32, 16, 1024),
+                        umma_smem_desc(sV + j * CHUNK8K + kk * 32, 16, 1024), idesc_sd, kk > 0);
+            umma_commit(&gb[SD_FULL]);
+            ++cs[g];
+            if (++js[g] == n_chunks) {
+              umma_commit(&gb[QDO_EMPTY]);
+              js[g] = 0;
+              ++ks[g];
+            }
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS_SOFTMAX));
+    // ====================================== dS producers + dQ epilogue (two groups) ======================================
+    const int grp = (warp - 4) >> 2;
+    const int quad = warp & 3;
+    const int row = quad * 32 + lane;
+    const int gtid = threadIdx.x - 128 - grp * 128;
+    const uint32_t lane_addr = static_cast<uint32_t>(quad * 32) << 16;
+    const uint32_t tg = tmem_base + lane_addr + grp * 192;
+    uint64_t* gb = gbar + grp * 7;
+    const uint32_t sDS = smem_u32(smem + DqSmem::kDS + grp * TILE16K);
+    const uint32_t sDS_row = sDS + row * 128;
+    uint32_t c = 0;
+    for (int t = grp; t < n_tiles; t += 2) {
+      const int qrow = t * QT + row;
+      const size_t stat_idx = static_cast<size_t>(h) * p.total_rows + row_base + qrow;
+      // rows beyond the sequence hold another sequence's data: lse = +inf makes their P (and dS) exactly 0
+      const float lse = qrow < nq ? lse2[stat_idx] : INFINITY;
+      const float dlt = qrow < nq ? delta[stat_idx] : 0.f;
+      for (int j = 0; j < n_chunks; ++j, ++c) {
+        mbar_wait(&gb[SD_FULL], c & 1);
+        tc_fence_after();
+        uint32_t sv[BC], dv[BC];
+        tmem_ld_32x32(tg, *reinterpret_cast<uint32_t(*)[32]>(&sv[0]));
+        tmem_ld_32x32(tg + 32, *reinterpret_cast<uint32_t(*)[32]>(&sv[32]));
+        tmem_ld_32x32(tg + 64, *reinterpret_cast<uint32_t(*)[32]>(&dv[0]));
+        tmem_ld_32x32(tg + 96, *reinterpret_cast<uint32_t(*)[32]>(&dv[32]));
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&gb[SD_FREE]);
+        const int valid = nk - j * BC;  // keys >= kv_len are masked: P = 0
+        if (c >= 1) mbar_wait(&gb[DQ_DONE], (c - 1) & 1);  // the dS buffer has been consumed by the previous dQ MMA
+#pragma unroll
+        for (int cc = 0; cc < BC / 8; ++cc) {
+          float e[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float pr = ex2_fast(fmaf(__uint_as_float(sv[cc * 8 + i]), p.scale_log2, -lse));
+            const float ds = pr * (__uint_as_float(dv[cc * 8 + i]) - dlt);
+            e[i] = (cc * 8 + i < valid) ? ds : 0.f;
+          }
+          uint4 o;
+          o.x = pack_bf16x2(e[0], e[1]); o.y = pack_bf16x2(e[2], e[3]);
+          o.z = pack_bf16x2(e[4], e[5]); o.w = pack_bf16x2(e[6], e[7]);
+          sts128(sDS_row + ((cc ^ (row & 7)) << 4), o);
+        }
+        fence_proxy_async_smem();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&gb[DS_READY]);
+      }
+      // ---- tile epilogue: dQ * scale -> bf16 -> staging (dS buffer) -> global ----
+      mbar_wait(&gb[DQ_DONE], (c - 1) & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        uint32_t o[32];
+        tmem_ld_32x32(tg + 128 + q * 32, o);
+        tmem_ld_wait();
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc) {
+          uint4 v;
+          v.x = pack_bf16x2(__uint_as_float(o[cc * 8 + 0]) * p.scale, __uint_as_float(o[cc * 8 + 1]) * p.scale);
+          v.y = pack_bf16x2(__uint_as_float(o[cc * 8 + 2]) * p.scale, __uint_as_float(o[cc * 8 + 3]) * p.scale);
+          v.z = pack_bf16x2(__uint_as_float(o[cc * 8 + 4]) * p.scale, __uint_as_float(o[cc * 8 + 5]) * p.scale);
+          v.w = pack_bf16x2(__uint_as_float(o[cc * 8 + 6]) * p.scale, __uint_as_float(o[cc * 8 + 7]) * p.scale);
+          sts128(sDS_row + (((q * 4 + cc) ^ (row & 7)) << 4), v);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&gb[DQ_FREE]);
+      group_bar_sync(grp);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int idx = gtid + i * 128;
+        const int r = idx >> 3, cc = idx & 7;
+        if (t * QT + r < nq) {
+          const uint4 v = lds128(sDS + r * 128 + ((cc ^ (r & 7)) << 4));
+          *reinterpret_cast<uint4*>(dqkv + static_cast<size_t>(row_base + t * QT + r) * ld_dqkv + h * D + cc * 8) = v;
+        }
+      }
+      group_bar_sync(grp);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+// ------------------------------------------------------------------------------------------------ dK/dV kernel
+// Group g owns key tiles t = g, g+2 (128 keys each): K_t, V_t are the A operands and stay in shared memory for the
+// tile; Q and dO stream through a per-group two-slot ring in 64-row chunks and are used twice from the same slot —
+// K-major as the B operand of S^T = K Q^T / dP^T = V dO^T and MN-major as the B operand of dV += P^T dO /
+// dK += dS^T Q.  Thread r of a group owns key row r (TMEM lane r): it needs the log-sum-exp and delta of all 64
+// query COLUMNS of the chunk, which the group stages in shared memory.
+struct DkvSmem {
+  static constexpr int kGroup = 6 * TILE16K;                 // per group: K | V | ring (2 x (Q 8K + dO 8K)) | P^T | dS^T
+  static constexpr int kK = 0, kV = TILE16K, kRing = 2 * TILE16K, kPT = 4 * TILE16K, kDST = 5 * TILE16K;
+  static constexpr int kStat = 2 * kGroup;                   // per group: float [2 slots][2 (lse, delta)][64]
+  static constexpr int kBar = kStat + 2 * 2 * 2 * 64 * 4;
+  static constexpr int kBarsPerGroup = 11;
+  static constexpr int kAlloc = kBar + 2 * kBarsPerGroup * 8 + 16;
+};
+static_assert(DkvSmem::kAlloc <= 232448, "dK/dV kernel exceeds the 227 KB shared-memory limit");
+enum { KV_FULL = 0, KV_EMPTY, RING_FULL0, RING_FULL1, RING_FREE0, RING_FREE1, ST_FULL, ST_FREE, PDS_READY, DKV_DONE, ACC_FREE };
+
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv128, const __grid_constant__ CUtensorMap tm_qkv64,
+                       const __grid_constant__ CUtensorMap tm_dctx64, const AttnTcParams p,
+                       const float* __restrict__ lse2, const float* __restrict__ delta,
+                       __nv_bfloat16* __restrict__ dqkv, int ld_dqkv) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if (smem_u32(smem) & 1023u) __trap();
+  uint64_t* gbar = reinterpret_cast<uint64_t*>(smem + DkvSmem::kBar);  // [2][11]
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(gbar + 2 * DkvSmem::kBarsPerGroup);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.x / p.heads, h = blockIdx.x % p.heads;
+  const int row_base = p.seq_start[b], nq = p.q_len[b], nk = p.kv_len[b];
+  const int H = p.heads * D;
+  const int n_qc = (nq + BC - 1) / BC;            // query chunks streamed per key tile
+  const int n_kt = (nk + 127) / 128;              // key tiles that hold at least one valid key
+  const int tiles_of[2] = {(n_kt + 1) >> 1, n_kt >> 1};
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tm_qkv128);
+    tma_prefetch_desc(&tm_qkv64);
+    tma_prefetch_desc(&tm_dctx64);
+    for (int g = 0; g < 2; ++g) {
+      uint64_t* gb = gbar + g * DkvSmem::kBarsPerGroup;
+      for (int i = 0; i < DkvSmem::kBarsPerGroup; ++i) mbar_init(&gb[i], 1);
+      mbar_init(&gb[ST_FREE], 4);
+      mbar_init(&gb[PDS_READY], 4);
+      mbar_init(&gb[ACC_FREE], 4);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_ptr_smem, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+  // TMEM columns per group g: S^T [g*256, +64), dP^T [+64, +64), dK [+128, +64), dV [+192, +64)
+
+  if (warp < 4) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_CONTROL));
+    if (warp == 0 && lane == 0) {
+      // ====================================== TMA producer (two independent streams) ======================================
+      int kl[2] = {0, 0}, jl[2] = {0, 0};
+      uint32_t lc[2] = {0, 0};
+      while (kl[0] < tiles_of[0] || kl[1] < tiles_of[1]) {
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {
+          if (kl[g] >= tiles_of[g]) continue;
+          uint64_t* gb = gbar + g * DkvSmem::kBarsPerGroup;
+          uint8_t* gs = smem + g * DkvSmem::kGroup;
+          if (jl[g] == 0) {
+            // new key tile: K_t / V_t buffers are free once every S^T / dP^T MMA of the previous tile has run
+            if (kl[g] > 0 && !mbar_test(&gb[KV_EMPTY], (kl[g] - 1) & 1)) continue;
+            const int t = g + 2 * kl[g];
+            mbar_arrive_expect_tx(&gb[KV_FULL], 2 * TILE16K);
+            tma_load_2d(gs + DkvSmem::kK, &tm_qkv128, &gb[KV_FULL], H + h * D, row_base + t * 128);
+            tma_load_2d(gs + DkvSmem::kV, &tm_qkv128, &gb[KV_FULL], 2 * H + h * D, row_base + t * 128);
+          }
+          const int slot = lc[g] & 1;
+          if (lc[g] >= 2 && !mbar_test(&gb[RING_FREE0 + slot], ((lc[g] >> 1) - 1) & 1)) {
+            if (jl[g] == 0) jl[g] = -1;  // K/V already issued for this tile: do not issue them again
+            continue;
+          }
+          if (jl[g] < 0) jl[g] = 0;
+          uint8_t* ring = gs + DkvSmem::kRing + slot * TILE16K;
+          mbar_arrive_expect_tx(&gb[RING_FULL0 + slot], TILE16K);
+          tma_load_2d(ring, &tm_qkv64, &gb[RING_FULL0 + slot], h * D, row_base + jl[g] * BC);
+          tma_load_2d(ring + CHUNK8K, &tm_dctx64, &gb[RING_FULL0 + slot], h * D, row_base + jl[g] * BC);
+          ++lc[g];
+          if (++jl[g] == n_qc) { jl[g] = 0; ++kl[g]; }
+        }
+      }
+    } else if (warp == 1 && lane == 0) {
+      // ====================================== MMA issuer ======================================
+      constexpr uint32_t idesc_st = umma_idesc_bf16(128, BC, 0, 0);  // S^T = K Q^T, dP^T = V dO^T : all K-major
+      constexpr uint32_t idesc_acc = umma_idesc_bf16(128, D, 0, 1);  // dV = P^T dO, dK = dS^T Q : B MN-major
+      int ks[2] = {0, 0}, js[2] = {0, 0}, kp[2] = {0, 0}, jp[2] = {0, 0};
+      uint32_t cs[2] = {0, 0}, cp[2] = {0, 0};
+      while (kp[0] < tiles_of[0] || kp[1] < tiles_of[1]) {
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {
+          uint64_t* gb = gbar + g * DkvSmem::kBarsPerGroup;
+          const uint32_t gs = smem_u32(smem + g * DkvSmem::kGroup);
+          const uint32_t tg = tmem_base + g * 256;
+          // ---- dV += P^T dO_c ; dK += dS^T Q_c ----
+          if (kp[g] < tiles_of[g] && mbar_test(&gb[PDS_READY], cp[g] & 1) &&
+              (jp[g] > 0 || mbar_test(&gb[ACC_FREE], (kp[g] & 1) ^ 1))) {
+            const int slot = cp[g] & 1;
+            tc_fence_after();
+            const uint32_t ring = gs + DkvSmem::kRing + slot * TILE16K;
+#pragma unroll
+            for (int kk = 0; kk < BC / 16; ++kk)
+              umma_bf16(tg + 192, umma_smem_desc(gs + DkvSmem::kPT + kk * 32, 16, 1024),
+                        umma_smem_desc(ring + CHUNK8K + kk * 2048, TILE16K, 1024), idesc_acc, (jp[g] > 0 || kk > 0));
+#pragma unroll
+            for (int kk = 0; kk < BC / 16; ++kk)
+              umma_bf16(tg + 128, umma_smem_desc(gs + DkvSmem::kDST + kk * 32, 16, 1024),
+                        umma_smem_desc(ring + kk * 2048, TILE16K, 1024), idesc_acc, (jp[g] > 0 || kk > 0));
+            umma_commit(&gb[DKV_DONE]);
+            umma_commit(&gb[RING_FREE0 + slot]);
+            ++cp[g];
+            if (++jp[g] == n_qc) { jp[g] = 0; ++kp[g]; }
+          }
+          // ---- S^T = K_t Q_c^T ; dP^T = V_t dO_c^T ----
+          if (ks[g] < tiles_of[g] && (cs[g] == 0 || mbar_test(&gb[ST_FREE], (cs[g] - 1) & 1)) &&
+              mbar_test(&gb[RING_FULL0 + (cs[g] & 1)], (cs[g] >> 1) & 1) &&
+              (js[g] > 0 || mbar_test(&gb[KV_FULL], ks[g] & 1))) {
+            tc_fence_after();
+            const uint32_t ring = gs + DkvSmem::kRing + (cs[g] & 1) * TILE16K;
+#pragma unroll
+            for (int kk = 0; kk < D / 16; ++kk)
+              umma_bf16(tg, umma_smem_desc(gs + DkvSmem::kK + kk * 32, 16, 1024),
+                        umma_smem_desc(ring + kk * 32, 16, 1024), idesc_st, kk > 0);
+#pragma unroll
+            for (int kk = 0; kk < D / 16; ++kk)
+              umma_bf16(tg + 64, umma_smem_desc(gs + DkvSmem::kV + kk * 32, 16, 1024),
+                        umma_smem_desc(ring + CHUNK8K + kk * 32, 16, 1024), idesc_st, kk > 0);
+            umma_commit(&gb[ST_FULL]);
+            ++cs[g];
+            if (++js[g] == n_qc) {
+              umma_commit(&gb[KV_EMPTY]);
+              js[g] = 0;
+              ++ks[g];
+            }
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS_SOFTMAX));
+    // ====================================== P^T / dS^T producers + dK/dV epilogue (two groups) ======================================
+    const int grp = (warp - 4) >> 2;
+    const int quad = warp & 3;
+    const int row = quad * 32 + lane;
+    const int gtid = threadIdx.x - 128 - grp * 128;
+    const uint32_t lane_addr = static_cast<uint32_t>(quad * 32) << 16;
+    const uint32_t tg = tmem_base + lane_addr + grp * 256;
+    uint64_t* gb = gbar + grp * DkvSmem::kBarsPerGroup;
+    const uint32_t gs = smem_u32(smem + grp * DkvSmem::kGroup);
+    const uint32_t sPT_row = gs + DkvSmem::kPT + row * 128, sDST_row = gs + DkvSmem::kDST + row * 128;
+    float* stat = reinterpret_cast<float*>(smem + DkvSmem::kStat) + grp * 256;  // [2 slots][2][64]
+    const uint32_t stat_addr = smem_u32(stat);
+    const float* lse_seq = lse2 + static_cast<size_t>(h) * p.total_rows + row_base;
+    const float* dl_seq = delta + static_cast<size_t>(h) * p.total_rows + row_base;
+
+    // key rows in [128 * n_kt, nq): padded keys inside the allocated sequence -> their gradients are exactly zero
+    for (int t = n_kt + grp; t * 128 < nq; t += 2) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int idx = gtid + i * 128;
+        const int r = t * 128 + (idx >> 3), cc = idx & 7;
+        if (r < nq) {
+          __nv_bfloat16* dst = dqkv + static_cast<size_t>(row_base + r) * ld_dqkv + h * D + cc * 8;
+          *reinterpret_cast<uint4*>(dst + H) = make_uint4(0, 0, 0, 0);
+          *reinterpret_cast<uint4*>(dst + 2 * H) = make_uint4(0, 0, 0, 0);
+        }
+      }
+    }
+
+    uint32_t c = 0;
+    for (int t = grp; t < n_kt; t += 2) {
+      const bool key_valid = (t * 128 + row) < nk;
+      for (int j = 0; j < n_qc; ++j, ++c) {
+        // stage lse / delta of this chunk's 64 query columns (rows beyond the sequence: lse = +inf -> P = 0)
+        if (gtid < 64) {
+          const int q = j * BC + gtid;
+          stat[(c & 1) * 128 + gtid] = q < nq ? lse_seq[q] : INFINITY;
+          stat[(c & 1) * 128 + 64 + gtid] = q < nq ? dl_seq[q] : 0.f;
+        }
+        group_bar_sync(grp);
+        mbar_wait(&gb[ST_FULL], c & 1);
+        tc_fence_after();
+        uint32_t sv[BC], dv[BC];
+        tmem_ld_32x32(tg, *reinterpret_cast<uint32_t(*)[32]>(&sv[0]));
+        tmem_ld_32x32(tg + 32, *reinterpret_cast<uint32_t(*)[32]>(&sv[32]));
+        tmem_ld_32x32(tg + 64, *reinterpret_cast<uint32_t(*)[32]>(&dv[0]));
+        tmem_ld_32x32(tg + 96, *reinterpret_cast<uint32_t(*)[32]>(&dv[32]));
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&gb[ST_FREE]);
+        if (c >= 1) mbar_wait(&gb[DKV_DONE], (c - 1) & 1);  // P^T / dS^T buffers consumed by the previous dV / dK MMAs
+        const uint32_t st = stat_addr + (c & 1) * 512;
+#pragma unroll
+        for (int cc = 0; cc < BC / 8; ++cc) {
+          const float4 l0 = lds128_ro(st + cc * 32), l1 = lds128_ro(st + cc * 32 + 16);
+          const float4 d0 = lds128_ro(st + 256 + cc * 32), d1 = lds128_ro(st + 256 + cc * 32 + 16);
+          const float ls[8] = {l0.x, l0.y, l0.z, l0.w, l1.x, l1.y, l1.z, l1.w};
+          const float dl[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
+          float pr[8], ds[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float e = ex2_fast(fmaf(__uint_as_float(sv[cc * 8 + i]), p.scale_log2, -ls[i]));
+            pr[i] = key_valid ? e : 0.f;
+            ds[i] = pr[i] * (__uint_as_float(dv[cc * 8 + i]) - dl[i]);
+          }
+          uint4 o;
+          o.x = pack_bf16x2(pr[0], pr[1]); o.y = pack_bf16x2(pr[2], pr[3]);
+          o.z = pack_bf16x2(pr[4], pr[5]); o.w = pack_bf16x2(pr[6], pr[7]);
+          sts128(sPT_row + ((cc ^ (row & 7)) << 4), o);
+          o.x = pack_bf16x2(ds[0], ds[1]); o.y = pack_bf16x2(ds[2], ds[3]);
+          o.z = pack_bf16x2(ds[4], ds[5]); o.w = pack_bf16x2(ds[6], ds[7]);
+          sts128(sDST_row + ((cc ^ (row & 7)) << 4), o);
+        }
+        fence_proxy_async_smem();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&gb[PDS_READY]);
+      }
+      // ---- tile epilogue: dK * scale, dV -> bf16 -> staging (P^T / dS^T buffers) -> global ----
+      mbar_wait(&gb[DKV_DONE], (c - 1) & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int which = 0; which < 2; ++which) {  // 0: dK (cols 128..191), 1: dV (cols 192..255)
+        const float mul = which == 0 ? p.scale : 1.f;
+        const uint32_t dst_row = which == 0 ? sPT_row : sDST_row;
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          uint32_t o[32];
+          tmem_ld_32x32(tg + 128 + which * 64 + q * 32, o);
+          tmem_ld_wait();
+#pragma unroll
+          for (int cc = 0; cc < 4; ++cc) {
+            uint4 v;
+            v.x = pack_bf16x2(__uint_as_float(o[cc * 8 + 0]) * mul, __uint_as_float(o[cc * 8 + 1]) * mul);
+            v.y = pack_bf16x2(__uint_as_float(o[cc * 8 + 2]) * mul, __uint_as_float(o[cc * 8 + 3]) * mul);
+            v.z = pack_bf16x2(__uint_as_float(o[cc * 8 + 4]) * mul, __uint_as_float(o[cc * 8 + 5]) * mul);
+            v.w = pack_bf16x2(__uint_as_float(o[cc * 8 + 6]) * mul, __uint_as_float(o[cc * 8 + 7]) * mul);
+            sts128(dst_row + (((q * 4 + cc) ^ (row & 7)) << 4), v);
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&gb[ACC_FREE]);
+      group_bar_sync(grp);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int idx = gtid + i * 128;
+        const int r = idx >> 3, cc = idx & 7;
+        const int key = t * 128 + r;
+        if (key < nq) {  // rows in [nk, nq) were masked above: their accumulators are exact zeros
+          __nv_bfloat16* dst = dqkv + static_cast<size_t>(row_base + key) * ld_dqkv + h * D + cc * 8;
+          *reinterpret_cast<uint4*>(dst + H) = lds128(gs + DkvSmem::kPT + r * 128 + ((cc ^ (r & 7)) << 4));
+          *reinterpret_cast<uint4*>(dst + 2 * H) = lds128(gs + DkvSmem::kDST + r * 128 + ((cc ^ (r & 7)) << 4));
+        }
+      }
+      group_bar_sync(grp);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+}  // namespace
+}  // namespace plb
+
+using namespace plb;
+
+extern "C" int plb_attn_bwd_tc(const void* qkv, int ld_qkv, const int32_t* seq_start, const int32_t* q_len,
+                               const int32_t* kv_len, int B, int heads, int head_dim, int max_q_len, int total_rows,
+                               const void* ctx, const void* dctx, int ld_ctx, const float* lse2, float* delta,
+                               void* dqkv, int ld_dqkv, plb_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  PLB_REQUIRE(qkv && seq_start && q_len && kv_len && ctx && dctx && lse2 && delta && dqkv, PLB_ERR_ARG, "attn_bwd_tc: null pointer");
+  PLB_REQUIRE(head_dim == D, PLB_ERR_UNSUPPORTED, "attn_bwd_tc: head_dim %d not supported (only 64)", head_dim);
+  PLB_REQUIRE(B > 0 && heads > 0 && total_rows > 0, PLB_ERR_ARG, "attn_bwd_tc: bad sizes");
+  PLB_REQUIRE(max_q_len > 0 && max_q_len <= MAX_BOXES * 128, PLB_ERR_UNSUPPORTED,
+              "attn_bwd_tc: sequences longer than %d rows are not supported (got %d)", MAX_BOXES * 128, max_q_len);
+  PLB_REQUIRE(ld_qkv % 8 == 0 && ld_ctx % 8 == 0 && ld_dqkv % 8 == 0 && (reinterpret_cast<uintptr_t>(qkv) % 16) == 0 &&
+                  (reinterpret_cast<uintptr_t>(ctx) % 16) == 0 && (reinterpret_cast<uintptr_t>(dctx) % 16) == 0 &&
+                  (reinterpret_cast<uintptr_t>(dqkv) % 16) == 0,
+              PLB_ERR_ARG, "attn_bwd_tc: operands must be 16-byte aligned with ld %% 8 == 0");
+  CUtensorMap tm_qkv128, tm_qkv64, tm_dctx128, tm_dctx64;
+  if (!tensor_map_bf16(&tm_qkv128, qkv, total_rows, 3 * heads * D, ld_qkv, 128, 64) ||
+      !tensor_map_bf16(&tm_qkv64, qkv, total_rows, 3 * heads * D, ld_qkv, 64, 64) ||
+      !tensor_map_bf16(&tm_dctx128, dctx, total_rows, heads * D, ld_ctx, 128, 64) ||
+      !tensor_map_bf16(&tm_dctx64, dctx, total_rows, heads * D, ld_ctx, 64, 64))
+    return PLB_ERR_CUDA;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e1 = cudaFuncSetAttribute(attn_bwd_dq_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DqSmem::kAlloc);
+    cudaError_t e2 = cudaFuncSetAttribute(attn_bwd_dkv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DkvSmem::kAlloc);
+    PLB_REQUIRE(e1 == cudaSuccess && e2 == cudaSuccess, PLB_ERR_CUDA, "attn_bwd_tc: cudaFuncSetAttribute failed");
+    configured = true;
+  }
+  AttnTcParams p{seq_start, q_len, kv_len, heads, total_rows, 1.4426950408889634f / sqrtf((float)head_dim),
+                 1.f / sqrtf((float)head_dim)};
+  const int dgrid = (total_rows + 7) / 8 < sm_count() * 8 ? (total_rows + 7) / 8 : sm_count() * 8;
+  attn_delta_kernel<<<dgrid, 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(dctx), static_cast<const __nv_bfloat16*>(ctx),
+                                               ld_ctx, total_rows, heads, total_rows, delta);
+  int rc = check_launch("plb_attn_bwd_tc(delta)");
+  if (rc) return rc;
+  attn_bwd_dq_tc_kernel<<<B * heads, NUM_THREADS, DqSmem::kAlloc, stream>>>(tm_qkv128, tm_dctx128, p, lse2, delta,
+                                                                            static_cast<__nv_bfloat16*>(dqkv), ld_dqkv);
+  rc = check_launch("plb_attn_bwd_tc(dq)");
+  if (rc) return rc;
+  attn_bwd_dkv_tc_kernel<<<B * heads, NUM_THREADS, DkvSmem::kAlloc, stream>>>(tm_qkv128, tm_qkv64, tm_dctx64, p, lse2, delta,
+                                                                              static_cast<__nv_bfloat16*>(dqkv), ld_dqkv);
+  return check_launch("plb_attn_bwd_tc(dkv)");
+}

@@ -352,12 +352,12 @@ class Engine:
                  ptr(self.g(att + "dense.bias")), s)
             self._gemm(GEMM_WGRAD, EPI_NONE, H, H, T, self.d_z, H, A["ctx"], H, self.g(att + "dense.weight"), H)
             self._gemm(GEMM_DGRAD, EPI_NONE, T, H, H, self.d_z, H, self.w(att + "dense.weight"), H, self.d_ctx, H)
-            call("plb_attn_bwd", ptr(A["qkv"]), 3 * H, ptr(b.seq_start), ptr(b.q_len), ptr(b.kv_len), b.B, nh, H // nh, b.L,
+            call("plb_attn_bwd_tc", ptr(A["qkv"]), 3 * H, ptr(b.seq_start), ptr(b.q_len), ptr(b.kv_len), b.B, nh, H // nh, b.L,
                  self._cap_T, ptr(A["ctx"]), ptr(self.d_ctx), H, ptr(A["lse"]), ptr(self.delta), ptr(self.d_qkv), 3 * H, s)
             call("plb_colsum", ptr(self.d_qkv), 3 * H, T, 3 * H, ptr(g_bqkv), s)
             self._gemm(GEMM_WGRAD, EPI_NONE, 3 * H, H, T, self.d_qkv, 3 * H, x_in, H, g_wqkv, H)
             self._gemm(GEMM_DGRAD, EPI_RESIDUAL, T, H, 3 * H, self.d_qkv, 3 * H, wqkv, H, dy, H, aux_in=self.d_z, ld_in=H)
-            self.launches += 6  # 2 ln_bwd, 2 colsum, attention bwd = 2 kernels
+            self.launches += 7  # 2 ln_bwd, 2 colsum, attention bwd = 3 kernels (delta, dQ, dK/dV)
 
         # ---- embedding side -----------------------------------------------------------------------
         mp = "encoder.encoder.embedding_hidden_mapping_in."

@@ -221,8 +221,8 @@ def _attn_ref(qkv, B, L, nh, lens):
 
 @pytest.mark.parametrize("B,L,nh,lens", [(2, 64, 2, [64, 64]), (3, 200, 2, [200, 77, 1]), (2, 512, 12, [512, 300]),
                                          (4, 130, 3, [130, 129, 65, 64])])
-@pytest.mark.parametrize("fwd", ["plb_attn_fwd", "plb_attn_fwd_tc"])
-def test_attention_fwd_bwd(dev, B, L, nh, lens, fwd):
+@pytest.mark.parametrize("fwd,bwd", [("plb_attn_fwd", "plb_attn_bwd"), ("plb_attn_fwd_tc", "plb_attn_bwd_tc")])
+def test_attention_fwd_bwd(dev, B, L, nh, lens, fwd, bwd):
     H, T = nh * 64, B * L
     qkv = torch.randn(T, 3 * H, device=dev).to(BF)
     lens_t = torch.tensor(lens, device=dev, dtype=torch.int32)
@@ -244,7 +244,7 @@ def test_attention_fwd_bwd(dev, B, L, nh, lens, fwd):
     ref.backward(dctx.float())
     dqkv = torch.full((T, 3 * H), float("nan"), device=dev, dtype=BF)
     delta = torch.zeros(nh, T, device=dev)
-    call("plb_attn_bwd", ptr(qkv), 3 * H, ptr(seq_start), ptr(q_len), ptr(lens_t), B, nh, 64, L, T, ptr(ctx), ptr(dctx), H,
+    call(bwd, ptr(qkv), 3 * H, ptr(seq_start), ptr(q_len), ptr(lens_t), B, nh, 64, L, T, ptr(ctx), ptr(dctx), H,
          ptr(lse), ptr(delta), ptr(dqkv), 3 * H, S())
     assert torch.isfinite(dqkv.float()).all()
     for name, sl in (("dq", slice(0, H)), ("dk", slice(H, 2 * H)), ("dv", slice(2 * H, 3 * H))):
