@@ -233,21 +233,21 @@ def run_b200(args):
 
     # ---- roofline of the dominant kernel (the tcgen05 GEMM): CUDA events around every GEMM launch of one more step ----
     roof = None
+    records = []
+    orig = eng._gemm
+
+    def timed(op, epi, M, N, K, *a, **k):
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        orig(op, epi, M, N, K, *a, **k)
+        e.record()
+        records.append((2.0 * M * N * K, s, e))
+
+    eng._gemm = timed
+    device_step(0)  # every rank runs it (the step contains collectives); rank 0 reports
+    torch.cuda.synchronize()
+    eng._gemm = orig
     if rank == 0:
-        records = []
-        orig = eng._gemm
-
-        def timed(op, epi, M, N, K, *a, **k):
-            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            s.record()
-            orig(op, epi, M, N, K, *a, **k)
-            e.record()
-            records.append((2.0 * M * N * K, s, e))
-
-        eng._gemm = timed
-        device_step(0)
-        torch.cuda.synchronize()
-        eng._gemm = orig
         fl = sum(r[0] for r in records)
         tt = sum(r[1].elapsed_time(r[2]) for r in records) * 1e-3
         pk = measured_peaks()
