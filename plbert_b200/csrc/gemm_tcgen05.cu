@@ -15,8 +15,7 @@
 // pre-activation operand comes in by TMA into the same staging buffer and is updated in place.
 #include "common.cuh"
 
-#include <mutex>
-#include <unordered_map>
+#include <cstdlib>
 
 namespace plb {
 
@@ -27,8 +26,7 @@ constexpr int BN = 256;
 constexpr int BK = 64;
 constexpr int UMMA_K = 16;
 constexpr int A_TILE_BYTES = BM * BK * 2;       // 16 KB
-constexpr int B_TILE_BYTES = BN * BK * 2;       // 32 KB
-constexpr int STAGE_BYTES = A_TILE_BYTES + B_TILE_BYTES;
+constexpr int B_TILE_BYTES = BN * BK * 2;       // 32 KB (one CTA) or 16 KB per CTA of a pair
 constexpr int EPI_COLS = 64;                    // columns per epilogue chunk (128 B of bf16)
 constexpr int EPI_BUF_BYTES = BM * EPI_COLS * 2;  // 16 KB
 constexpr int MN_BOX_BYTES = 64 * 64 * 2;       // one MN-major TMA box: 64 K-rows x 64 elements
@@ -43,16 +41,17 @@ struct GemmParams {
   int m_tiles, n_tiles, splits;
   int k_iters;        // ceil(K / BK)
   int k_per_split;    // k iterations per split
-  int num_units;      // m_tiles * n_tiles * splits
+  int num_units;      // m_tiles * n_tiles * splits (m_tiles counts 128*kCta-row tiles)
   const float* bias;  // [N] or null
   float* c_f32;       // WGRAD output
   int ldc;
 };
 
-template <int kStages, int kBufs>
+template <int kStages, int kBufs, int kCta>
 struct SmemLayout {
+  static constexpr int kStageBytes = A_TILE_BYTES + B_TILE_BYTES / kCta;  // bytes THIS CTA stages per k-iteration
   static constexpr int kStageOff = 0;
-  static constexpr int kEpiOff = kStages * STAGE_BYTES;
+  static constexpr int kEpiOff = kStages * kStageBytes;
   static constexpr int kBarOff = kEpiOff + kBufs * EPI_BUF_BYTES;
   // full[kStages], empty[kStages], tmem_full[2], tmem_empty[2], epi_in[kBufs], tmem ptr
   static constexpr int kNumBars = 2 * kStages + 4 + kBufs;
@@ -74,12 +73,18 @@ __device__ __forceinline__ void unit_coords(const GemmParams& p, int u, int& m_b
 
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory"); }
 
-template <bool kAMn, bool kBMn, int kEpi, int kStages, int kBufs>
+template <bool kAMn, bool kBMn, int kEpi, int kStages, int kBufs, int kCta>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
             const __grid_constant__ CUtensorMap tm_c, const __grid_constant__ CUtensorMap tm_aux_in,
             const __grid_constant__ CUtensorMap tm_aux_out, const GemmParams p) {
-  using L = SmemLayout<kStages, kBufs>;
+  using L = SmemLayout<kStages, kBufs, kCta>;
+  constexpr int STAGE_BYTES = L::kStageBytes;
+  constexpr int B_ROWS = BN / kCta;  // rows (FWD) / columns (MN-major) of the B tile this CTA loads
+  // CTA pair (kCta == 2): the two CTAs of a cluster own rows [0,128) and [128,256) of a 256-row tile and each stages half
+  // of the B tile; one tcgen05.mma.cta_group::2 issued by the leader (rank 0) drives both tensor cores.
+  const uint32_t rank = (kCta == 2) ? cluster_ctarank() : 0;
+  const int unit0 = blockIdx.x / kCta, unit_stride = gridDim.x / kCta;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
 
@@ -99,19 +104,21 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CU
     tma_prefetch_desc(&tm_b);
     if (kEpi != kAtomicF32) tma_prefetch_desc(&tm_c);
     for (int i = 0; i < kStages; ++i) {
-      mbar_init(&full_bar[i], 1);
+      mbar_init(&full_bar[i], kCta);  // leader: own arrive.expect_tx + the peer's remote arrive
       mbar_init(&empty_bar[i], 1);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
-      mbar_init(&tmem_empty[i], 4);  // one arrive per epilogue warp
+      mbar_init(&tmem_empty[i], 4 * kCta);  // one arrive per epilogue warp of every CTA of the pair
     }
     for (int i = 0; i < kBufs; ++i) mbar_init(&epi_in[i], 1);
     fence_mbar_init();
   }
-  if (warp == 1) tmem_alloc(tmem_ptr_smem, TMEM_COLS);
+  if (warp == 1) {
+    if (kCta == 2) tmem_alloc_2cta(tmem_ptr_smem, TMEM_COLS); else tmem_alloc(tmem_ptr_smem, TMEM_COLS);
+  }
   tc_fence_before();
-  __syncthreads();
+  if (kCta == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
 
@@ -120,28 +127,47 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CU
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int u = blockIdx.x; u < p.num_units; u += gridDim.x) {
+      for (int u = unit0; u < p.num_units; u += unit_stride) {
         int m_blk, n_blk, k_begin, k_end;
         unit_coords(p, u, m_blk, n_blk, k_begin, k_end);
-        const int m0 = m_blk * BM, n0 = n_blk * BN;
+        const int m0 = (m_blk * kCta + rank) * BM, n0 = n_blk * BN + rank * B_ROWS;
         for (int kb = k_begin; kb < k_end; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * STAGE_BYTES;
           uint8_t* sb = sa + A_TILE_BYTES;
-          mbar_arrive_expect_tx(&full_bar[stage], STAGE_BYTES);
-          if (!kAMn) {
-            tma_load_2d(sa, &tm_a, &full_bar[stage], kb * BK, m0);
-          } else {
+          if (kCta == 1) {
+            mbar_arrive_expect_tx(&full_bar[stage], STAGE_BYTES);
+            if (!kAMn) {
+              tma_load_2d(sa, &tm_a, &full_bar[stage], kb * BK, m0);
+            } else {
 #pragma unroll
-            for (int j = 0; j < BM / 64; ++j)
-              tma_load_2d(sa + j * MN_BOX_BYTES, &tm_a, &full_bar[stage], m0 + j * 64, kb * BK);
-          }
-          if (!kBMn) {
-            tma_load_2d(sb, &tm_b, &full_bar[stage], kb * BK, n0);
-          } else {
+              for (int j = 0; j < BM / 64; ++j)
+                tma_load_2d(sa + j * MN_BOX_BYTES, &tm_a, &full_bar[stage], m0 + j * 64, kb * BK);
+            }
+            if (!kBMn) {
+              tma_load_2d(sb, &tm_b, &full_bar[stage], kb * BK, n0);
+            } else {
 #pragma unroll
-            for (int j = 0; j < BN / 64; ++j)
-              tma_load_2d(sb + j * MN_BOX_BYTES, &tm_b, &full_bar[stage], n0 + j * 64, kb * BK);
+              for (int j = 0; j < B_ROWS / 64; ++j)
+                tma_load_2d(sb + j * MN_BOX_BYTES, &tm_b, &full_bar[stage], n0 + j * 64, kb * BK);
+            }
+          } else {
+            // both CTAs load their halves into their own shared memory; every byte completes on the LEADER's barrier
+            const uint32_t lead_bar = mapa_u32(smem_u32(&full_bar[stage]), 0);
+            if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], kCta * STAGE_BYTES);
+            else mbar_arrive_cluster(lead_bar);
+            if (!kAMn) {
+              tma_load_2d_2sm(sa, &tm_a, lead_bar, kb * BK, m0);
+            } else {
+#pragma unroll
+              for (int j = 0; j < BM / 64; ++j) tma_load_2d_2sm(sa + j * MN_BOX_BYTES, &tm_a, lead_bar, m0 + j * 64, kb * BK);
+            }
+            if (!kBMn) {
+              tma_load_2d_2sm(sb, &tm_b, lead_bar, kb * BK, n0);
+            } else {
+#pragma unroll
+              for (int j = 0; j < B_ROWS / 64; ++j) tma_load_2d_2sm(sb + j * MN_BOX_BYTES, &tm_b, lead_bar, n0 + j * 64, kb * BK);
+            }
           }
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
@@ -150,13 +176,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CU
     __syncwarp();
   } else if (warp == 1) {
     // =========================== MMA issuer ===========================
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, kAMn ? 1 : 0, kBMn ? 1 : 0);
+    if (lane == 0 && rank == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(BM * kCta, BN, kAMn ? 1 : 0, kBMn ? 1 : 0);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int u = blockIdx.x; u < p.num_units; u += gridDim.x) {
+      for (int u = unit0; u < p.num_units; u += unit_stride) {
         int m_blk, n_blk, k_begin, k_end;
         unit_coords(p, u, m_blk, n_blk, k_begin, k_end);
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
@@ -173,12 +199,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CU
                                      : umma_smem_desc(sa + k * (UMMA_K * 2), 16, 1024);
             const uint64_t db = kBMn ? umma_smem_desc(sb + k * (UMMA_K * 128), MN_BOX_BYTES, 1024)
                                      : umma_smem_desc(sb + k * (UMMA_K * 2), 16, 1024);
-            umma_bf16(tmem_d, da, db, idesc, (kb > k_begin || k > 0) ? 1u : 0u);
+            if (kCta == 2) umma_bf16_2cta(tmem_d, da, db, idesc, (kb > k_begin || k > 0) ? 1u : 0u);
+            else umma_bf16(tmem_d, da, db, idesc, (kb > k_begin || k > 0) ? 1u : 0u);
           }
-          umma_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs have read it
+          // smem slot reusable (in BOTH CTAs) once these MMAs have read it
+          if (kCta == 2) umma_commit_2cta(&empty_bar[stage], 3); else umma_commit(&empty_bar[stage]);
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&tmem_full[acc]);  // accumulator complete
+        if (kCta == 2) umma_commit_2cta(&tmem_full[acc], 3); else umma_commit(&tmem_full[acc]);  // accumulator complete
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
@@ -202,7 +230,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CU
     uint32_t seq = 0;  // running chunk sequence number (staging slot = seq % kSlots)
 
     // look-ahead iterator for the aux-in prefetch (leader only)
-    int la_u = blockIdx.x, la_c = 0;
+    int la_u = unit0, la_c = 0;
     uint32_t la_seq = 0;
     auto la_issue = [&]() {
       // issue the aux load for the next not-yet-issued chunk, if any
@@ -213,12 +241,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CU
         if (la_c < BN / EPI_COLS && n0 < p.N) {
           const int slot = la_seq % kSlots;
           mbar_arrive_expect_tx(&epi_in[slot], EPI_BUF_BYTES);
-          tma_load_2d(epi_smem + slot * EPI_BUF_BYTES, &tm_aux_in, &epi_in[slot], n0, m_blk * BM);
+          tma_load_2d(epi_smem + slot * EPI_BUF_BYTES, &tm_aux_in, &epi_in[slot], n0, (m_blk * kCta + rank) * BM);
           ++la_seq;
           ++la_c;
           return;
         }
-        la_u += gridDim.x;
+        la_u += unit_stride;
         la_c = 0;
       }
     };
@@ -226,10 +254,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CU
       for (int i = 0; i < kSlots - 1; ++i) la_issue();
     }
 
-    for (int u = blockIdx.x; u < p.num_units; u += gridDim.x) {
+    const uint32_t lead_tmem_empty0 = (kCta == 2) ? mapa_u32(smem_u32(&tmem_empty[0]), 0) : 0;
+    for (int u = unit0; u < p.num_units; u += unit_stride) {
       int m_blk, n_blk, k_begin, k_end;
       unit_coords(p, u, m_blk, n_blk, k_begin, k_end);
-      const int m0 = m_blk * BM, n0 = n_blk * BN;
+      const int m0 = (m_blk * kCta + rank) * BM, n0 = n_blk * BN;
       if (kEpi != kAtomicF32 && p.bias != nullptr) {
         // stage this tile's bias in shared memory: the per-element __ldg it replaces serialised the epilogue
         // (the compiler cannot hoist global loads across the generic staging stores)
@@ -352,25 +381,31 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CU
       // accumulator drained -> hand the TMEM buffer back to the MMA warp
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      if (lane == 0) {
+        if (kCta == 2) mbar_arrive_cluster(lead_tmem_empty0 + acc * 8);  // the leader's MMA warp waits for both CTAs
+        else mbar_arrive(&tmem_empty[acc]);
+      }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
     if (leader && kEpi != kAtomicF32) bulk_wait<0>();  // all stores globally visible before exit
   }
 
   tc_fence_before();
-  __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
+  if (kCta == 2) cluster_sync_all(); else __syncthreads();  // the peer may still read this CTA's smem / signal its barriers
+  if (warp == 1) {
+    if (kCta == 2) tmem_dealloc_2cta(tmem_base, TMEM_COLS); else tmem_dealloc(tmem_base, TMEM_COLS);
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
-template <bool kAMn, bool kBMn, int kEpi, int kStages, int kBufs>
+template <bool kAMn, bool kBMn, int kEpi, int kStages, int kBufs, int kCta>
 int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const CUtensorMap& tin,
            const CUtensorMap& tout, const GemmParams& p, cudaStream_t stream) {
-  using L = SmemLayout<kStages, kBufs>;
-  auto kern = gemm_kernel<kAMn, kBMn, kEpi, kStages, kBufs>;
+  using L = SmemLayout<kStages, kBufs, kCta>;
+  static_assert(L::kAlloc <= 232448, "GEMM stage ring exceeds the 227 KB shared-memory limit");
+  auto kern = gemm_kernel<kAMn, kBMn, kEpi, kStages, kBufs, kCta>;
   static bool configured = false;  // benign race: the attribute call is idempotent
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kAlloc);
@@ -378,8 +413,22 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, 
                 cudaGetErrorString(e));
     configured = true;
   }
-  const int grid = p.num_units < sm_count() ? p.num_units : sm_count();
-  kern<<<grid, NUM_THREADS, L::kAlloc, stream>>>(ta, tb, tc, tin, tout, p);
+  const int max_clusters = sm_count() / kCta;
+  const int clusters = p.num_units < max_clusters ? p.num_units : max_clusters;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(clusters * kCta);
+  cfg.blockDim = dim3(NUM_THREADS);
+  cfg.dynamicSmemBytes = L::kAlloc;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = kCta;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ta, tb, tc, tin, tout, p);
+  PLB_REQUIRE(e == cudaSuccess, PLB_ERR_CUDA, "plb_gemm_bf16: launch failed: %s", cudaGetErrorString(e));
   return check_launch("plb_gemm_bf16");
 }
 
@@ -388,6 +437,18 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, 
 }  // namespace plb
 
 using namespace plb;
+
+// CTA pairs (cta_group::2) halve the B-operand shared-memory traffic per SM; a single CTA is kept for problems with
+// fewer than two 128-row tiles.  PLB_GEMM_CTA=1 forces the single-CTA kernel (bring-up / A-B measurements only).
+static int pick_ctas(int M) {
+  static int forced = -1;
+  if (forced < 0) {
+    const char* e = getenv("PLB_GEMM_CTA");
+    forced = e ? atoi(e) : 0;
+  }
+  if (forced == 1 || forced == 2) return forced;
+  return M > BM ? 2 : 1;
+}
 
 extern "C" int plb_gemm_bf16(int op, int epilogue, int M, int N, int K, const void* A, int lda, const void* B,
                              int ldb, void* C, int ldc, const float* bias, const void* aux_in, int ld_aux_in,
@@ -400,9 +461,10 @@ extern "C" int plb_gemm_bf16(int op, int epilogue, int M, int N, int K, const vo
               lda, ldb);
   PLB_REQUIRE(((uintptr_t)A % 16) == 0 && ((uintptr_t)B % 16) == 0, PLB_ERR_ARG, "gemm: A/B must be 16-byte aligned");
 
+  const int ctas = pick_ctas(M);
   GemmParams p{};
   p.M = M; p.N = N; p.K = K;
-  p.m_tiles = (M + BM - 1) / BM;
+  p.m_tiles = (M + BM * ctas - 1) / (BM * ctas);
   p.n_tiles = (N + BN - 1) / BN;
   p.k_iters = (K + BK - 1) / BK;
   p.bias = bias;
@@ -411,7 +473,7 @@ extern "C" int plb_gemm_bf16(int op, int epilogue, int M, int N, int K, const vo
   CUtensorMap ta, tb, tc, tin, tout;
   bool ok;
   if (op == PLB_GEMM_FWD) {
-    ok = tensor_map_bf16(&ta, A, M, K, lda, BM, 64) && tensor_map_bf16(&tb, B, N, K, ldb, BN, 64);
+    ok = tensor_map_bf16(&ta, A, M, K, lda, BM, 64) && tensor_map_bf16(&tb, B, N, K, ldb, BN / ctas, 64);
   } else if (op == PLB_GEMM_DGRAD) {
     ok = tensor_map_bf16(&ta, A, M, K, lda, BM, 64) && tensor_map_bf16(&tb, B, K, N, ldb, 64, 64);
   } else {
@@ -419,12 +481,16 @@ extern "C" int plb_gemm_bf16(int op, int epilogue, int M, int N, int K, const vo
   }
   if (!ok) return PLB_ERR_CUDA;
 
+#define PLB_LAUNCH(AMN, BMN, EPI, S1, B1, S2, B2)                                                      \
+  return ctas == 2 ? launch<AMN, BMN, EPI, S2, B2, 2>(ta, tb, tc, tin, tout, p, stream)                \
+                   : launch<AMN, BMN, EPI, S1, B1, 1>(ta, tb, tc, tin, tout, p, stream)
+
   if (op == PLB_GEMM_WGRAD) {
     PLB_REQUIRE(epilogue == PLB_EPI_NONE && bias == nullptr, PLB_ERR_ARG, "gemm: WGRAD takes no epilogue/bias");
     PLB_REQUIRE(ldc >= N, PLB_ERR_ARG, "gemm: ldc < N");
     // split K so that every SM gets about two units; each unit keeps at least 8 k-iterations
     const int tiles = p.m_tiles * p.n_tiles;
-    int splits = (2 * sm_count() + tiles - 1) / tiles;
+    int splits = (2 * (sm_count() / ctas) + tiles - 1) / tiles;
     const int max_splits = p.k_iters / 8 > 0 ? p.k_iters / 8 : 1;
     if (splits > max_splits) splits = max_splits;
     if (splits < 1) splits = 1;
@@ -433,7 +499,8 @@ extern "C" int plb_gemm_bf16(int op, int epilogue, int M, int N, int K, const vo
     p.num_units = tiles * p.splits;
     p.c_f32 = static_cast<float*>(C);
     p.ldc = ldc;
-    return launch<true, true, kAtomicF32, 4, 2>(ta, tb, ta, ta, ta, p, stream);
+    tc = tin = tout = ta;
+    PLB_LAUNCH(true, true, kAtomicF32, 4, 2, 6, 2);
   }
 
   PLB_REQUIRE((ldc % 8) == 0 && ((uintptr_t)C % 16) == 0, PLB_ERR_ARG, "gemm: C must be 16-byte aligned, ldc %% 8 == 0");
@@ -454,19 +521,20 @@ extern "C" int plb_gemm_bf16(int op, int epilogue, int M, int N, int K, const vo
 
   if (op == PLB_GEMM_FWD) {
     switch (epilogue) {
-      case PLB_EPI_NONE:     return launch<false, false, kNone, 4, 2>(ta, tb, tc, tin, tout, p, stream);
-      case PLB_EPI_RESIDUAL: return launch<false, false, kResidual, 3, 4>(ta, tb, tc, tin, tout, p, stream);
-      case PLB_EPI_GELU:     return launch<false, false, kGelu, 3, 4>(ta, tb, tc, tin, tout, p, stream);
+      case PLB_EPI_NONE:     PLB_LAUNCH(false, false, kNone, 4, 2, 6, 2);
+      case PLB_EPI_RESIDUAL: PLB_LAUNCH(false, false, kResidual, 3, 4, 5, 4);
+      case PLB_EPI_GELU:     PLB_LAUNCH(false, false, kGelu, 3, 4, 5, 4);
       default: break;
     }
   } else {
     switch (epilogue) {
-      case PLB_EPI_NONE:     return launch<false, true, kNone, 4, 2>(ta, tb, tc, tin, tout, p, stream);
-      case PLB_EPI_RESIDUAL: return launch<false, true, kResidual, 3, 4>(ta, tb, tc, tin, tout, p, stream);
-      case PLB_EPI_GELU_BWD: return launch<false, true, kGeluBwd, 3, 4>(ta, tb, tc, tin, tout, p, stream);
+      case PLB_EPI_NONE:     PLB_LAUNCH(false, true, kNone, 4, 2, 6, 2);
+      case PLB_EPI_RESIDUAL: PLB_LAUNCH(false, true, kResidual, 3, 4, 5, 4);
+      case PLB_EPI_GELU_BWD: PLB_LAUNCH(false, true, kGeluBwd, 3, 4, 5, 4);
       default: break;
     }
   }
+#undef PLB_LAUNCH
   set_error("gemm: op %d does not support epilogue %d", op, epilogue);
   return PLB_ERR_UNSUPPORTED;
 }
