@@ -251,22 +251,23 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const AttnTcParam
             tmem_st_wait();
           }
         }
-        // P = exp2(S*k - m) -> bf16 -> swizzled smem (A operand of the PV MMA).  One P buffer per group: the previous
-        // PV (issued about one chunk of work ago) must have finished reading it.
-        if (c >= 1) mbar_wait(&gb[PV_DONE], (c - 1) & 1);
+        // P = exp2(S*k - m) -> bf16, packed in registers FIRST: the exponentials then overlap the previous PV MMA,
+        // which still reads the group's single P buffer; only the stores wait for it.
         float ls[2] = {0.f, 0.f};
         const float mneg = -m_used;
+        uint4 pk[KC / 8];
 #pragma unroll
         for (int cc = 0; cc < KC / 8; ++cc) {  // sixteen 16-byte pieces = 128 keys (masked keys: exp2(-inf) = 0)
           float e[8];
 #pragma unroll
           for (int i = 0; i < 8; ++i) e[i] = ex2_fast(fmaf(__uint_as_float(sv[cc * 8 + i]), p.scale_log2, mneg));
           ls[cc & 1] += ((e[0] + e[1]) + (e[2] + e[3])) + ((e[4] + e[5]) + (e[6] + e[7]));
-          uint4 o;
-          o.x = pack_bf16x2(e[0], e[1]); o.y = pack_bf16x2(e[2], e[3]);
-          o.z = pack_bf16x2(e[4], e[5]); o.w = pack_bf16x2(e[6], e[7]);
-          sts128(sP_row + (cc >> 3) * TILE16K + (((cc & 7) ^ (row & 7)) << 4), o);
+          pk[cc].x = pack_bf16x2(e[0], e[1]); pk[cc].y = pack_bf16x2(e[2], e[3]);
+          pk[cc].z = pack_bf16x2(e[4], e[5]); pk[cc].w = pack_bf16x2(e[6], e[7]);
         }
+        if (c >= 1) mbar_wait(&gb[PV_DONE], (c - 1) & 1);  // the previous PV has finished reading the P buffer
+#pragma unroll
+        for (int cc = 0; cc < KC / 8; ++cc) sts128(sP_row + (cc >> 3) * TILE16K + (((cc & 7) ^ (row & 7)) << 4), pk[cc]);
         l_run += ls[0] + ls[1];
         fence_proxy_async_smem();
         tc_fence_before();
@@ -557,7 +558,7 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_c
         __syncwarp();
         if (lane == 0) mbar_arrive(&gb[SD_FREE]);
         const int valid = nk - j * BC;  // keys >= kv_len are masked: P = 0
-        if (c >= 1) mbar_wait(&gb[DQ_DONE], (c - 1) & 1);  // the dS buffer has been consumed by the previous dQ MMA
+        uint4 pk[BC / 8];
 #pragma unroll
         for (int cc = 0; cc < BC / 8; ++cc) {
           float e[8];
@@ -567,11 +568,12 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_c
             const float ds = pr * (__uint_as_float(dv[cc * 8 + i]) - dlt);
             e[i] = (cc * 8 + i < valid) ? ds : 0.f;
           }
-          uint4 o;
-          o.x = pack_bf16x2(e[0], e[1]); o.y = pack_bf16x2(e[2], e[3]);
-          o.z = pack_bf16x2(e[4], e[5]); o.w = pack_bf16x2(e[6], e[7]);
-          sts128(sDS_row + ((cc ^ (row & 7)) << 4), o);
+          pk[cc].x = pack_bf16x2(e[0], e[1]); pk[cc].y = pack_bf16x2(e[2], e[3]);
+          pk[cc].z = pack_bf16x2(e[4], e[5]); pk[cc].w = pack_bf16x2(e[6], e[7]);
         }
+        if (c >= 1) mbar_wait(&gb[DQ_DONE], (c - 1) & 1);  // the dS buffer has been consumed by the previous dQ MMA
+#pragma unroll
+        for (int cc = 0; cc < BC / 8; ++cc) sts128(sDS_row + ((cc ^ (row & 7)) << 4), pk[cc]);
         fence_proxy_async_smem();
         tc_fence_before();
         __syncwarp();
@@ -815,8 +817,8 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv128, const __gr
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&gb[ST_FREE]);
-        if (c >= 1) mbar_wait(&gb[DKV_DONE], (c - 1) & 1);  // P^T / dS^T buffers consumed by the previous dV / dK MMAs
         const uint32_t st = stat_addr + (c & 1) * 512;
+        uint4 pkp[BC / 8], pkd[BC / 8];
 #pragma unroll
         for (int cc = 0; cc < BC / 8; ++cc) {
           const float4 l0 = lds128_ro(st + cc * 32), l1 = lds128_ro(st + cc * 32 + 16);
@@ -830,13 +832,16 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv128, const __gr
             pr[i] = key_valid ? e : 0.f;
             ds[i] = pr[i] * (__uint_as_float(dv[cc * 8 + i]) - dl[i]);
           }
-          uint4 o;
-          o.x = pack_bf16x2(pr[0], pr[1]); o.y = pack_bf16x2(pr[2], pr[3]);
-          o.z = pack_bf16x2(pr[4], pr[5]); o.w = pack_bf16x2(pr[6], pr[7]);
-          sts128(sPT_row + ((cc ^ (row & 7)) << 4), o);
-          o.x = pack_bf16x2(ds[0], ds[1]); o.y = pack_bf16x2(ds[2], ds[3]);
-          o.z = pack_bf16x2(ds[4], ds[5]); o.w = pack_bf16x2(ds[6], ds[7]);
-          sts128(sDST_row + ((cc ^ (row & 7)) << 4), o);
+          pkp[cc].x = pack_bf16x2(pr[0], pr[1]); pkp[cc].y = pack_bf16x2(pr[2], pr[3]);
+          pkp[cc].z = pack_bf16x2(pr[4], pr[5]); pkp[cc].w = pack_bf16x2(pr[6], pr[7]);
+          pkd[cc].x = pack_bf16x2(ds[0], ds[1]); pkd[cc].y = pack_bf16x2(ds[2], ds[3]);
+          pkd[cc].z = pack_bf16x2(ds[4], ds[5]); pkd[cc].w = pack_bf16x2(ds[6], ds[7]);
+        }
+        if (c >= 1) mbar_wait(&gb[DKV_DONE], (c - 1) & 1);  // P^T / dS^T buffers consumed by the previous dV / dK MMAs
+#pragma unroll
+        for (int cc = 0; cc < BC / 8; ++cc) {
+          sts128(sPT_row + ((cc ^ (row & 7)) << 4), pkp[cc]);
+          sts128(sDST_row + ((cc ^ (row & 7)) << 4), pkd[cc]);
         }
         fence_proxy_async_smem();
         tc_fence_before();
