@@ -95,12 +95,12 @@ int plb_gemm_bf16_check(int op, int epilogue, int M, int N, int K,
  * ids/pos: int32 [T] (pos restarts at 0 per sequence, HF/:85-86).  Tables are fp32 [*, E]; `type0` points at
  * row 0 of token_type_embeddings.  out: bf16 [T, E]; stats: fp32 [T, 2] = (mean, rstd) saved for backward.
  * Backward: `de` = gradient of the LN output (bf16 [T, E]); accumulates (+=, fp32 atomics) into dword [V, E]
- * (row pad_id skipped: padding_idx, HF/:56), dpos, dtype0 [E], dln_w, dln_b. */
+ * (row pad_id skipped: padding_idx, HF/:56; V = rows of the word table), dpos, dtype0 [E], dln_w, dln_b. */
 int plb_embed_ln_fwd(const int32_t* ids, const int32_t* pos, int T, int E,
                      const float* word, const float* posemb, const float* type0,
                      const float* ln_w, const float* ln_b, float eps,
                      void* out, float* stats, plb_stream_t stream);
-int plb_embed_ln_bwd(const void* de, const int32_t* ids, const int32_t* pos, int T, int E,
+int plb_embed_ln_bwd(const void* de, const int32_t* ids, const int32_t* pos, int T, int E, int V,
                      const float* word, const float* posemb, const float* type0,
                      const float* ln_w, const float* stats, int pad_id,
                      float* dword, float* dpos, float* dtype0, float* dln_w, float* dln_b,
@@ -139,10 +139,12 @@ int plb_attn_fwd_tc(const void* qkv, int ld_qkv, const int32_t* seq_start, const
                     const int32_t* kv_len, int B, int heads, int head_dim, int max_q_len, int total_rows,
                     void* ctx, int ld_ctx, float* lse2, plb_stream_t stream);
 
+/* Backward on tcgen05 (delta + dQ kernel + dK/dV kernel).  If dbias_qkv_accum != NULL (fp32 [3*heads*64]) the column
+ * sums of dqkv — the bias gradient of the fused QKV projection — are accumulated into it by the same kernels. */
 int plb_attn_bwd_tc(const void* qkv, int ld_qkv, const int32_t* seq_start, const int32_t* q_len,
                     const int32_t* kv_len, int B, int heads, int head_dim, int max_q_len, int total_rows,
                     const void* ctx, const void* dctx, int ld_ctx, const float* lse2, float* delta,
-                    void* dqkv, int ld_dqkv, plb_stream_t stream);
+                    void* dqkv, int ld_dqkv, float* dbias_qkv_accum, plb_stream_t stream);
 
 /* ---- a8: masked-row loss ----------------------------------------------------------------------------
  * R/train.py:107-131 calculate_phoneme_loss.  The host flattens masked_indices into rows[M] (= b*L + i, in the

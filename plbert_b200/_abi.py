@@ -33,13 +33,13 @@ SIGNATURES = {
     "plb_gemm_bf16": _GEMM_ARGS,
     "plb_gemm_bf16_check": _GEMM_ARGS,
     "plb_embed_ln_fwd": [P, P, c_int, c_int, P, P, P, P, P, c_float, P, P, P],
-    "plb_embed_ln_bwd": [P, P, P, c_int, c_int, P, P, P, P, P, c_int, P, P, P, P, P, P],
+    "plb_embed_ln_bwd": [P, P, P, c_int, c_int, c_int, P, P, P, P, P, c_int, P, P, P, P, P, P],
     "plb_ln_fwd": [P, c_int, c_int, P, P, c_float, P, P, P],
     "plb_ln_bwd": [P, P, P, P, c_int, c_int, P, P, P, P, P],
     "plb_attn_fwd": [P, c_int, P, P, P, c_int, c_int, c_int, c_int, c_int, P, c_int, P, P],
     "plb_attn_fwd_tc": [P, c_int, P, P, P, c_int, c_int, c_int, c_int, c_int, P, c_int, P, P],
     "plb_attn_bwd": [P, c_int, P, P, P, c_int, c_int, c_int, c_int, c_int, P, P, c_int, P, P, P, c_int, P],
-    "plb_attn_bwd_tc": [P, c_int, P, P, P, c_int, c_int, c_int, c_int, c_int, P, P, c_int, P, P, P, c_int, P],
+    "plb_attn_bwd_tc": [P, c_int, P, P, P, c_int, c_int, c_int, c_int, c_int, P, P, c_int, P, P, P, c_int, P, P],
     "plb_gather_rows": [P, c_int, P, c_int, c_int, P, c_int, P],
     "plb_scatter_add_rows": [P, c_int, P, c_int, c_int, P, c_int, P],
     "plb_masked_ce": [P, c_int, c_int, c_int, P, P, P, P, c_int, P],

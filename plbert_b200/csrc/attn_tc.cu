@@ -386,6 +386,26 @@ __global__ void __launch_bounds__(256) attn_delta_kernel(const __nv_bfloat16* __
   }
 }
 
+
+// Bias gradient of the QKV projection fused into the backward kernels: column sums of a staged [128 x 64] bf16 tile
+// (rows < n_rows only), added to dbias[col] with atomics.  One column PAIR per lane (32-bit loads), 32 rows per warp.
+// The sums run over the ROUNDED values, i.e. exactly what the weight-gradient GEMM reads.
+__device__ __forceinline__ void tile_colsum_atomic(uint32_t tile_smem, int n_rows, int gtid, float* dbias_cols) {
+  const int cp = gtid & 31, quarter = gtid >> 5;
+  float a0 = 0.f, a1 = 0.f;
+  const int r_end = min(n_rows, quarter * 32 + 32);
+  for (int r = quarter * 32; r < r_end; ++r) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(tile_smem + r * 128 + (((cp >> 2) ^ (r & 7)) << 4) + (cp & 3) * 4));
+    a0 += bf16_lo(v);
+    a1 += bf16_hi(v);
+  }
+  if (n_rows > quarter * 32) {
+    atomicAdd(dbias_cols + 2 * cp, a0);
+    atomicAdd(dbias_cols + 2 * cp + 1, a1);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ dQ kernel
 struct DqSmem {
   static constexpr int kK = 0;                               // K of the head, resident: 4 boxes of [128 x 64]
@@ -403,7 +423,7 @@ enum { QDO_FULL = 0, QDO_EMPTY, SD_FULL, SD_FREE, DS_READY, DQ_DONE, DQ_FREE };
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_dctx,
                       const AttnTcParams p, const float* __restrict__ lse2, const float* __restrict__ delta,
-                      __nv_bfloat16* __restrict__ dqkv, int ld_dqkv) {
+                      __nv_bfloat16* __restrict__ dqkv, int ld_dqkv, float* __restrict__ dbias) {
   extern __shared__ __align__(1024) uint8_t smem[];
   if (smem_u32(smem) & 1023u) __trap();
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + DqSmem::kBar);
@@ -610,6 +630,7 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_c
           *reinterpret_cast<uint4*>(dqkv + static_cast<size_t>(row_base + t * QT + r) * ld_dqkv + h * D + cc * 8) = v;
         }
       }
+      if (dbias != nullptr) tile_colsum_atomic(sDS, min(QT, nq - t * QT), gtid, dbias + h * D);
       group_bar_sync(grp);
     }
   }
@@ -639,7 +660,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
 attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv128, const __grid_constant__ CUtensorMap tm_qkv64,
                        const __grid_constant__ CUtensorMap tm_dctx64, const AttnTcParams p,
                        const float* __restrict__ lse2, const float* __restrict__ delta,
-                       __nv_bfloat16* __restrict__ dqkv, int ld_dqkv) {
+                       __nv_bfloat16* __restrict__ dqkv, int ld_dqkv, float* __restrict__ dbias) {
   extern __shared__ __align__(1024) uint8_t smem[];
   if (smem_u32(smem) & 1023u) __trap();
   uint64_t* gbar = reinterpret_cast<uint64_t*>(smem + DkvSmem::kBar);  // [2][11]
@@ -886,6 +907,11 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv128, const __gr
           *reinterpret_cast<uint4*>(dst + 2 * H) = lds128(gs + DkvSmem::kDST + r * 128 + ((cc ^ (r & 7)) << 4));
         }
       }
+      if (dbias != nullptr) {
+        // (the key-bias gradient is mathematically zero; it is accumulated anyway so the tensor holds what autograd would)
+        tile_colsum_atomic(gs + DkvSmem::kPT, min(128, nk - t * 128), gtid, dbias + H + h * D);
+        tile_colsum_atomic(gs + DkvSmem::kDST, min(128, nk - t * 128), gtid, dbias + 2 * H + h * D);
+      }
       group_bar_sync(grp);
     }
   }
@@ -902,7 +928,7 @@ using namespace plb;
 extern "C" int plb_attn_bwd_tc(const void* qkv, int ld_qkv, const int32_t* seq_start, const int32_t* q_len,
                                const int32_t* kv_len, int B, int heads, int head_dim, int max_q_len, int total_rows,
                                const void* ctx, const void* dctx, int ld_ctx, const float* lse2, float* delta,
-                               void* dqkv, int ld_dqkv, plb_stream_t stream_) {
+                               void* dqkv, int ld_dqkv, float* dbias_qkv_accum, plb_stream_t stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   PLB_REQUIRE(qkv && seq_start && q_len && kv_len && ctx && dctx && lse2 && delta && dqkv, PLB_ERR_ARG, "attn_bwd_tc: null pointer");
   PLB_REQUIRE(head_dim == D, PLB_ERR_UNSUPPORTED, "attn_bwd_tc: head_dim %d not supported (only 64)", head_dim);
@@ -934,10 +960,12 @@ extern "C" int plb_attn_bwd_tc(const void* qkv, int ld_qkv, const int32_t* seq_s
   int rc = check_launch("plb_attn_bwd_tc(delta)");
   if (rc) return rc;
   attn_bwd_dq_tc_kernel<<<B * heads, NUM_THREADS, DqSmem::kAlloc, stream>>>(tm_qkv128, tm_dctx128, p, lse2, delta,
-                                                                            static_cast<__nv_bfloat16*>(dqkv), ld_dqkv);
+                                                                            static_cast<__nv_bfloat16*>(dqkv), ld_dqkv,
+                                                                            dbias_qkv_accum);
   rc = check_launch("plb_attn_bwd_tc(dq)");
   if (rc) return rc;
   attn_bwd_dkv_tc_kernel<<<B * heads, NUM_THREADS, DkvSmem::kAlloc, stream>>>(tm_qkv128, tm_qkv64, tm_dctx64, p, lse2, delta,
-                                                                              static_cast<__nv_bfloat16*>(dqkv), ld_dqkv);
+                                                                              static_cast<__nv_bfloat16*>(dqkv), ld_dqkv,
+                                                                              dbias_qkv_accum);
   return check_launch("plb_attn_bwd_tc(dkv)");
 }

@@ -84,6 +84,79 @@ __global__ void masked_ce_kernel(__nv_bfloat16* __restrict__ logits, int ld, int
   }
 }
 
+// Large vocabularies (the 64 k token head): one CTA per row, 16-byte accesses.  Pass 1 streams the row from HBM, passes 2
+// and 3 re-read it from L1/L2 (a 64 k row is 128 KB), so the traffic is one read and one write of the logits.
+__global__ void __launch_bounds__(256)
+masked_ce_wide_kernel(__nv_bfloat16* __restrict__ logits, int ld, int M, int V, const int32_t* __restrict__ labels,
+                      const float* __restrict__ weights, float* __restrict__ row_loss) {
+  __shared__ float s_red[8];
+  const int m = blockIdx.x, tid = threadIdx.x;
+  __nv_bfloat16* z = logits + static_cast<size_t>(m) * ld;
+  const int nvec = V >> 3;  // full 8-element chunks; the tail (V % 8) and the padding columns are handled scalar
+  auto block_reduce = [&](float v, bool is_max) -> float {
+    v = is_max ? warp_max(v) : warp_sum(v);
+    __syncthreads();
+    if ((tid & 31) == 0) s_red[tid >> 5] = v;
+    __syncthreads();
+    float r = s_red[0];
+#pragma unroll
+    for (int i = 1; i < 8; ++i) r = is_max ? fmaxf(r, s_red[i]) : r + s_red[i];
+    return r;
+  };
+  float mx = -INFINITY;
+  for (int c = tid; c < nvec; c += 256) {
+    const uint4 v = *reinterpret_cast<const uint4*>(z + c * 8);
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) mx = fmaxf(mx, fmaxf(bf16_lo(w[i]), bf16_hi(w[i])));
+  }
+  for (int j = nvec * 8 + tid; j < V; j += 256) mx = fmaxf(mx, __bfloat162float(z[j]));
+  mx = block_reduce(mx, true);
+  const float mx2 = mx * 1.4426950408889634f;
+  float se = 0.f;
+  for (int c = tid; c < nvec; c += 256) {
+    const uint4 v = *reinterpret_cast<const uint4*>(z + c * 8);
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      se += ex2_fast(fmaf(bf16_lo(w[i]), 1.4426950408889634f, -mx2)) + ex2_fast(fmaf(bf16_hi(w[i]), 1.4426950408889634f, -mx2));
+  }
+  for (int j = nvec * 8 + tid; j < V; j += 256) se += ex2_fast(fmaf(__bfloat162float(z[j]), 1.4426950408889634f, -mx2));
+  se = block_reduce(se, false);
+  const int y = labels[m];
+  const float wgt = weights[m];
+  if (tid == 0) row_loss[m] = (y >= 0 && y < V) ? wgt * (__logf(se) + mx - __bfloat162float(z[y])) : 0.f;
+  __syncthreads();  // z[y] has been read before anyone overwrites it
+  const float inv = wgt / se;
+  for (int c = tid; c < nvec; c += 256) {
+    const uint4 v = *reinterpret_cast<const uint4*>(z + c * 8);
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+    float g[8];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      g[2 * i] = ex2_fast(fmaf(bf16_lo(w[i]), 1.4426950408889634f, -mx2)) * inv;
+      g[2 * i + 1] = ex2_fast(fmaf(bf16_hi(w[i]), 1.4426950408889634f, -mx2)) * inv;
+    }
+    if (y >= c * 8 && y < c * 8 + 8) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        if (c * 8 + i == y) g[i] -= wgt;
+    }
+    uint4 o;
+    o.x = pack_bf16x2(g[0], g[1]); o.y = pack_bf16x2(g[2], g[3]);
+    o.z = pack_bf16x2(g[4], g[5]); o.w = pack_bf16x2(g[6], g[7]);
+    *reinterpret_cast<uint4*>(z + c * 8) = o;
+  }
+  for (int j = nvec * 8 + tid; j < ld; j += 256) {
+    float g = 0.f;
+    if (j < V) {
+      g = ex2_fast(fmaf(__bfloat162float(z[j]), 1.4426950408889634f, -mx2)) * inv;
+      if (j == y) g -= wgt;
+    }
+    z[j] = __float2bfloat16(g);
+  }
+}
+
 // deterministic sum of row_loss -> out[0] (+= when accumulate)
 __global__ void sum_rows_kernel(const float* __restrict__ v, int n, float* __restrict__ out, int accumulate) {
   __shared__ float s[32];
@@ -191,7 +264,7 @@ extern "C" int plb_masked_ce(void* logits, int ld, int M, int V, const int32_t* 
   if (V <= 2048)
     masked_ce_kernel<32><<<(M + 7) / 8, 256, 0, stream>>>(z, ld, M, V, labels, weights, row_loss);
   else
-    masked_ce_kernel<256><<<M, 256, 0, stream>>>(z, ld, M, V, labels, weights, row_loss);
+    masked_ce_wide_kernel<<<M, 256, 0, stream>>>(z, ld, M, V, labels, weights, row_loss);
   int rc = check_launch("plb_masked_ce");
   if (rc) return rc;
   sum_rows_kernel<<<1, 1024, 0, stream>>>(row_loss, M, loss_out, accumulate);

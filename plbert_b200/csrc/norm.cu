@@ -85,7 +85,7 @@ __global__ void __launch_bounds__(WARPS * 32) ln_fwd_kernel(const __nv_bfloat16*
 // 3 x 8 registers and two 12-warp CTAs fit per SM; the two row statistics cross the WPR warps through shared memory.
 constexpr int LNB_ROWS = 4;  // rows in flight per CTA
 template <int WPR>
-__global__ void __launch_bounds__(LNB_ROWS * WPR * 32)
+__global__ void __launch_bounds__(LNB_ROWS * WPR * 32, (LNB_ROWS * WPR * 32 <= 384) ? 2 : 1)
 ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ z,
               const float* __restrict__ stats, const float* __restrict__ w, int T, int H,
               __nv_bfloat16* __restrict__ dz, float* __restrict__ dw_acc, float* __restrict__ db_acc,
@@ -108,19 +108,33 @@ ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restr
   }
   const float invH = 1.f / H;
   int it = 0;
+  // software pipeline: the loads of the next row are in flight while the current row is reduced
+  uint4 nz = make_uint4(0, 0, 0, 0), nd = make_uint4(0, 0, 0, 0);
+  float nmean = 0.f, nrstd = 0.f;
+  auto prefetch = [&](int row0) {
+    const int row = row0 + rslot;
+    if (row < T) {
+      nmean = stats[2 * row];
+      nrstd = stats[2 * row + 1];
+      if (active) {
+        nz = *reinterpret_cast<const uint4*>(z + static_cast<size_t>(row) * H + c * 8);
+        nd = *reinterpret_cast<const uint4*>(dy + static_cast<size_t>(row) * H + c * 8);
+      }
+    }
+  };
+  prefetch(blockIdx.x * LNB_ROWS);
   for (int row0 = blockIdx.x * LNB_ROWS; row0 < T; row0 += gridDim.x * LNB_ROWS, ++it) {
     const int row = row0 + rslot;
     const bool rv = row < T;
     float xh[8], g[8];
-    float s1 = 0.f, s2 = 0.f, mean = 0.f, rstd = 0.f;
-    if (rv) {
-      mean = stats[2 * row];
-      rstd = stats[2 * row + 1];
-    }
+    float s1 = 0.f, s2 = 0.f;
+    const float mean = nmean, rstd = nrstd;
+    const uint4 cz = nz, cd = nd;
+    if (row0 + gridDim.x * LNB_ROWS < T) prefetch(row0 + gridDim.x * LNB_ROWS);
     if (rv && active) {
       float zz[8], dd[8];
-      unpack8(*reinterpret_cast<const uint4*>(z + static_cast<size_t>(row) * H + c * 8), zz);
-      unpack8(*reinterpret_cast<const uint4*>(dy + static_cast<size_t>(row) * H + c * 8), dd);
+      unpack8(cz, zz);
+      unpack8(cd, dd);
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
         xh[k] = (zz[k] - mean) * rstd;
@@ -233,17 +247,23 @@ embed_ln_fwd_kernel(const int32_t* __restrict__ ids, const int32_t* __restrict__
   }
 }
 
-// de (bf16 grad of the LN output) -> LN backward -> scatter-add into the three tables
+// de (bf16 grad of the LN output) -> LN backward -> scatter-add into the three tables.
+// kSmemWord: the word-table gradient (V x E floats; 96 KB for the 188 x 128 table) is accumulated in shared memory per
+// CTA and flushed once, because a handful of rows (mask, separator) receive ~30 % of all tokens and would otherwise
+// serialise in the L2 atomic units.
+template <bool kSmemWord>
 __global__ void __launch_bounds__(WARPS * 32)
 embed_ln_bwd_kernel(const __nv_bfloat16* __restrict__ de, const int32_t* __restrict__ ids,
                     const int32_t* __restrict__ pos, int T, int E, const float* __restrict__ word,
                     const float* __restrict__ posemb, const float* __restrict__ type0, const float* __restrict__ w,
-                    const float* __restrict__ stats, int pad_id, float* __restrict__ dword, float* __restrict__ dpos,
-                    float* __restrict__ dtype0, float* __restrict__ dw_acc, float* __restrict__ db_acc) {
-  extern __shared__ float s_red[];  // [3][E]: dw, db, dtype0
+                    const float* __restrict__ stats, int pad_id, int V, float* __restrict__ dword,
+                    float* __restrict__ dpos, float* __restrict__ dtype0, float* __restrict__ dw_acc,
+                    float* __restrict__ db_acc) {
+  extern __shared__ float s_red[];  // [3][E]: dw, db, dtype0; then (kSmemWord) [V][E] word-table gradient
+  float* s_word = s_red + 3 * E;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int nchunk = E >> 2;
-  for (int i = threadIdx.x; i < 3 * E; i += blockDim.x) s_red[i] = 0.f;
+  for (int i = threadIdx.x; i < 3 * E + (kSmemWord ? V * E : 0); i += blockDim.x) s_red[i] = 0.f;
   __syncthreads();
   float ww[EMAXC][4], pdw[EMAXC][4], pdb[EMAXC][4], pdt[EMAXC][4];
 #pragma unroll
@@ -293,7 +313,10 @@ embed_ln_bwd_kernel(const __nv_bfloat16* __restrict__ de, const int32_t* __restr
         for (int k = 0; k < 4; ++k) {
           const float d = rstd * (g[i][k] - s1 - xh[i][k] * s2);
           pdt[i][k] += d;
-          if (id != pad_id) atomicAdd(dword + static_cast<size_t>(id) * E + c * 4 + k, d);  // padding_idx row gets no grad
+          if (id != pad_id) {  // padding_idx row gets no grad
+            if (kSmemWord) atomicAdd(s_word + id * E + c * 4 + k, d);
+            else atomicAdd(dword + static_cast<size_t>(id) * E + c * 4 + k, d);
+          }
           atomicAdd(dpos + static_cast<size_t>(ps) * E + c * 4 + k, d);
         }
       }
@@ -316,6 +339,12 @@ embed_ln_bwd_kernel(const __nv_bfloat16* __restrict__ de, const int32_t* __restr
     atomicAdd(dw_acc + i, s_red[i]);
     atomicAdd(db_acc + i, s_red[E + i]);
     atomicAdd(dtype0 + i, s_red[2 * E + i]);
+  }
+  if (kSmemWord) {
+    for (int i = threadIdx.x; i < V * E; i += blockDim.x) {
+      const float v = s_word[i];
+      if (v != 0.f) atomicAdd(dword + i, v);
+    }
   }
 }
 
@@ -367,16 +396,32 @@ extern "C" int plb_embed_ln_fwd(const int32_t* ids, const int32_t* pos, int T, i
   return check_launch("plb_embed_ln_fwd");
 }
 
-extern "C" int plb_embed_ln_bwd(const void* de, const int32_t* ids, const int32_t* pos, int T, int E, const float* word,
-                                const float* posemb, const float* type0, const float* ln_w, const float* stats,
-                                int pad_id, float* dword, float* dpos, float* dtype0, float* dln_w, float* dln_b,
-                                plb_stream_t stream) {
+extern "C" int plb_embed_ln_bwd(const void* de, const int32_t* ids, const int32_t* pos, int T, int E, int V,
+                                const float* word, const float* posemb, const float* type0, const float* ln_w,
+                                const float* stats, int pad_id, float* dword, float* dpos, float* dtype0, float* dln_w,
+                                float* dln_b, plb_stream_t stream) {
   PLB_REQUIRE(de && ids && pos && word && posemb && type0 && ln_w && stats && dword && dpos && dtype0 && dln_w && dln_b &&
                   T > 0,
               PLB_ERR_ARG, "embed_ln_bwd: bad arguments");
   PLB_REQUIRE(E % 4 == 0 && E >= 4 && E <= 4 * 32 * EMAXC, PLB_ERR_UNSUPPORTED, "embed_ln_bwd: E=%d unsupported", E);
-  embed_ln_bwd_kernel<<<row_grid(T, 4), WARPS * 32, 3 * E * sizeof(float), static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const __nv_bfloat16*>(de), ids, pos, T, E, word, posemb, type0, ln_w, stats, pad_id, dword, dpos,
-      dtype0, dln_w, dln_b);
+  PLB_REQUIRE(V > 0, PLB_ERR_ARG, "embed_ln_bwd: V must be the number of rows of the word table");
+  const size_t small = 3 * E * sizeof(float), big = small + static_cast<size_t>(V) * E * sizeof(float);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (big <= 200 * 1024) {
+    static bool configured = false;
+    if (!configured) {
+      cudaError_t e = cudaFuncSetAttribute(embed_ln_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+      PLB_REQUIRE(e == cudaSuccess, PLB_ERR_CUDA, "embed_ln_bwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+      configured = true;
+    }
+    const int need = (T + WARPS - 1) / WARPS;
+    embed_ln_bwd_kernel<true><<<need < sm_count() ? need : sm_count(), WARPS * 32, big, st>>>(
+        static_cast<const __nv_bfloat16*>(de), ids, pos, T, E, word, posemb, type0, ln_w, stats, pad_id, V, dword, dpos,
+        dtype0, dln_w, dln_b);
+  } else {
+    embed_ln_bwd_kernel<false><<<row_grid(T, 4), WARPS * 32, small, st>>>(
+        static_cast<const __nv_bfloat16*>(de), ids, pos, T, E, word, posemb, type0, ln_w, stats, pad_id, V, dword, dpos,
+        dtype0, dln_w, dln_b);
+  }
   return check_launch("plb_embed_ln_bwd");
 }

@@ -353,18 +353,18 @@ class Engine:
             self._gemm(GEMM_WGRAD, EPI_NONE, H, H, T, self.d_z, H, A["ctx"], H, self.g(att + "dense.weight"), H)
             self._gemm(GEMM_DGRAD, EPI_NONE, T, H, H, self.d_z, H, self.w(att + "dense.weight"), H, self.d_ctx, H)
             call("plb_attn_bwd_tc", ptr(A["qkv"]), 3 * H, ptr(b.seq_start), ptr(b.q_len), ptr(b.kv_len), b.B, nh, H // nh, b.L,
-                 self._cap_T, ptr(A["ctx"]), ptr(self.d_ctx), H, ptr(A["lse"]), ptr(self.delta), ptr(self.d_qkv), 3 * H, s)
-            call("plb_colsum", ptr(self.d_qkv), 3 * H, T, 3 * H, ptr(g_bqkv), s)
+                 self._cap_T, ptr(A["ctx"]), ptr(self.d_ctx), H, ptr(A["lse"]), ptr(self.delta), ptr(self.d_qkv), 3 * H,
+                 ptr(g_bqkv), s)  # also accumulates the QKV bias gradient (column sums of dqkv)
             self._gemm(GEMM_WGRAD, EPI_NONE, 3 * H, H, T, self.d_qkv, 3 * H, x_in, H, g_wqkv, H)
             self._gemm(GEMM_DGRAD, EPI_RESIDUAL, T, H, 3 * H, self.d_qkv, 3 * H, wqkv, H, dy, H, aux_in=self.d_z, ld_in=H)
-            self.launches += 7  # 2 ln_bwd, 2 colsum, attention bwd = 3 kernels (delta, dQ, dK/dV)
+            self.launches += 6  # 2 ln_bwd, 1 colsum, attention bwd = 3 kernels (delta, dQ, dK/dV)
 
         # ---- embedding side -----------------------------------------------------------------------
         mp = "encoder.encoder.embedding_hidden_mapping_in."
         call("plb_colsum", ptr(dy), H, T, H, ptr(self.g(mp + "bias")), s)
         self._gemm(GEMM_WGRAD, EPI_NONE, H, E, T, dy, H, self.e, E, self.g(mp + "weight"), E)
         self._gemm(GEMM_DGRAD, EPI_NONE, T, E, H, dy, H, self.w(mp + "weight"), E, self.d_e, E)
-        call("plb_embed_ln_bwd", ptr(self.d_e), ptr(b.ids), ptr(b.pos), T, E, ptr(self.p(_EMB + "word_embeddings.weight")),
+        call("plb_embed_ln_bwd", ptr(self.d_e), ptr(b.ids), ptr(b.pos), T, E, c.vocab_size, ptr(self.p(_EMB + "word_embeddings.weight")),
              ptr(self.p(_EMB + "position_embeddings.weight")), ptr(self.p(_EMB + "token_type_embeddings.weight")),
              ptr(self.p(_EMB + "LayerNorm.weight")), ptr(self.e_stats), c.pad_token_id,
              ptr(self.g(_EMB + "word_embeddings.weight")), ptr(self.g(_EMB + "position_embeddings.weight")),

@@ -22,6 +22,7 @@ def main():
     dqkv = torch.empty(T, 3 * H, device=dev, dtype=torch.bfloat16)
     lse = torch.empty(nh, T, device=dev)
     delta = torch.empty(nh, T, device=dev)
+    dbias = torch.zeros(3 * H, device=dev)
     S = torch.cuda.current_stream().cuda_stream
     fwd_flops = 4.0 * B * nh * L * L * 64
 
@@ -42,8 +43,9 @@ def main():
         timeit(lambda: call(n, ptr(qkv), 3 * H, ptr(seq_start), ptr(lens), ptr(lens), B, nh, 64, L, T, ptr(ctx), H, ptr(lse), S),
                fwd_flops, n)
     for n in [n for n in ("plb_attn_bwd", "plb_attn_bwd_tc") if hasattr(load(), n)]:
+        extra = (ptr(dbias),) if n.endswith("_tc") else ()
         timeit(lambda: call(n, ptr(qkv), 3 * H, ptr(seq_start), ptr(lens), ptr(lens), B, nh, 64, L, T, ptr(ctx), ptr(dctx), H,
-                            ptr(lse), ptr(delta), ptr(dqkv), 3 * H, S), 2.5 * fwd_flops, n)
+                            ptr(lse), ptr(delta), ptr(dqkv), 3 * H, *extra, S), 2.5 * fwd_flops, n)
 
 
 if __name__ == "__main__":

@@ -28,7 +28,7 @@ def main():
             call("plb_attn_fwd_tc", ptr(qkv), 3 * H, ptr(ss), ptr(lens), ptr(lens), B, nh, 64, L, T, ptr(ctx), H, ptr(lse), S)
             if hasattr(load(), "plb_attn_bwd_tc"):
                 call("plb_attn_bwd_tc", ptr(qkv), 3 * H, ptr(ss), ptr(lens), ptr(lens), B, nh, 64, L, T, ptr(ctx), ptr(dctx), H,
-                     ptr(lse), ptr(delta), ptr(dqkv), 3 * H, S)
+                     ptr(lse), ptr(delta), ptr(dqkv), 3 * H, 0, S)
     if "gemm" in which:
         T = 148 * 128 * 4
         for (op, epi, N, K) in ((0, 0, 2304, 768), (0, 0, 768, 128), (0, 1, 768, 768), (0, 2, 2048, 768), (1, 3, 2048, 768), (2, 0, 768, 0)):

@@ -180,7 +180,7 @@ def test_layernorm_constant_row_is_finite(dev):
 
 
 # ------------------------------------------------------------------------------------------ embeddings
-@pytest.mark.parametrize("T,E,V,P", [(2000, 128, 188, 512), (333, 32, 188, 64)])
+@pytest.mark.parametrize("T,E,V,P", [(2000, 128, 188, 512), (333, 32, 188, 64), (5000, 128, 600, 512)])
 def test_embed_ln_fwd_bwd(dev, T, E, V, P):
     ids = torch.randint(0, V, (T,), device=dev, dtype=torch.int32)
     ids[:5] = 0
@@ -198,7 +198,7 @@ def test_embed_ln_fwd_bwd(dev, T, E, V, P):
     de = torch.randn(T, E, device=dev).to(BF)
     ref.backward(de.float())
     g = [torch.zeros_like(t) for t in (word, pe, typ[0], w, b)]
-    call("plb_embed_ln_bwd", ptr(de), ptr(ids), ptr(pos), T, E, ptr(word), ptr(pe), ptr(typ), ptr(w), ptr(stats), 0,
+    call("plb_embed_ln_bwd", ptr(de), ptr(ids), ptr(pos), T, E, V, ptr(word), ptr(pe), ptr(typ), ptr(w), ptr(stats), 0,
          ptr(g[0]), ptr(g[1]), ptr(g[2]), ptr(g[3]), ptr(g[4]), S())
     wg = word.grad.clone()
     wg[0] = 0  # padding_idx row
@@ -244,8 +244,16 @@ def test_attention_fwd_bwd(dev, B, L, nh, lens, fwd, bwd):
     ref.backward(dctx.float())
     dqkv = torch.full((T, 3 * H), float("nan"), device=dev, dtype=BF)
     delta = torch.zeros(nh, T, device=dev)
-    call(bwd, ptr(qkv), 3 * H, ptr(seq_start), ptr(q_len), ptr(lens_t), B, nh, 64, L, T, ptr(ctx), ptr(dctx), H,
-         ptr(lse), ptr(delta), ptr(dqkv), 3 * H, S())
+    dbias = torch.ones(3 * H, device=dev)
+    if bwd == "plb_attn_bwd_tc":
+        call(bwd, ptr(qkv), 3 * H, ptr(seq_start), ptr(q_len), ptr(lens_t), B, nh, 64, L, T, ptr(ctx), ptr(dctx), H,
+             ptr(lse), ptr(delta), ptr(dqkv), 3 * H, ptr(dbias), S())
+        # fused bias gradient = column sums of the stored (rounded) dqkv, accumulated on top of the initial ones
+        want = dqkv.float().sum(0)
+        assert (dbias - 1 - want).abs().max() <= 1e-3 * want.abs().max() + 1e-4
+    else:
+        call(bwd, ptr(qkv), 3 * H, ptr(seq_start), ptr(q_len), ptr(lens_t), B, nh, 64, L, T, ptr(ctx), ptr(dctx), H,
+             ptr(lse), ptr(delta), ptr(dqkv), 3 * H, S())
     assert torch.isfinite(dqkv.float()).all()
     for name, sl in (("dq", slice(0, H)), ("dk", slice(H, 2 * H)), ("dv", slice(2 * H, 3 * H))):
         assert rel(dqkv[:, sl].float(), qf.grad[:, sl]) < 2e-2, name
