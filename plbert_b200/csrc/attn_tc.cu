@@ -40,7 +40,8 @@ struct FwdSmem {
   static constexpr int kBar = kP + 2 * 2 * TILE16K;
   // k_full[4], v_full[4], then per group: q_full, q_empty, s_full, s_free, p_ready, pv_done, o_free
   static constexpr int kNumBars = 2 * MAX_BOXES + 2 * 7;
-  static constexpr int kBytes = kBar + kNumBars * 8 + 16;
+  static constexpr int kTurn = kBar + kNumBars * 8 + 16;  // 9 words for the exponential-phase turn-taking
+  static constexpr int kBytes = kTurn + 48;
   static constexpr int kAlloc = kBytes;  // no slack: the dynamic window is 1024-byte aligned (checked at run time)
 };
 static_assert(FwdSmem::kAlloc <= 232448, "forward attention exceeds the 227 KB shared-memory limit");
@@ -80,6 +81,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const AttnTcParam
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tm_qkv);
+    *reinterpret_cast<volatile float*>(smem + FwdSmem::kTurn) = 0.f;
     for (int i = 0; i < 2 * MAX_BOXES; ++i) mbar_init(&bars[i], 1);
     for (int g = 0; g < 2; ++g) {
       uint64_t* gb = gbar + g * BARS_PER_GROUP;
@@ -200,6 +202,8 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const AttnTcParam
     const uint32_t sPg = smem_u32(smem + FwdSmem::kP + grp * 2 * TILE16K);
     const uint32_t sP_row = sPg + row * 128;
     uint32_t c = 0;  // chunk counter of this group (phase of s_full / s_free / p_ready / pv_done)
+    const uint32_t turn_zero = smem_u32(smem + FwdSmem::kTurn);  // one zero word, then one sink word per softmax warp
+    const uint32_t steps0 = ((n_tiles + 1) >> 1) * n_chunks, steps1 = (n_tiles >> 1) * n_chunks;  // chunks per group
     for (int t = grp; t < n_tiles; t += 2) {
       float m_used = -INFINITY, l_run = 0.f;
       for (int j = 0; j < n_chunks; ++j, ++c) {
@@ -254,8 +258,18 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const AttnTcParam
         // P = exp2(S*k - m) -> bf16, packed in registers FIRST: the exponentials then overlap the previous PV MMA,
         // which still reads the group's single P buffer; only the stores wait for it.
         float ls[2] = {0.f, 0.f};
-        const float mneg = -m_used;
+        float mneg = -m_used;
         uint4 pk[KC / 8];
+        // The two groups' warps of one quadrant share an SM sub-partition and its MUFU.  Take turns on the exponential
+        // phase (64-thread named barriers, one pair per quadrant) so that one warp's exponentials overlap the other
+        // warp's TMEM / barrier / store phase instead of both phases running in lock-step.
+        // ptxas schedules freely around bar.sync / bar.arrive unless data flows through them: the exponent offset is
+        // re-read after the barrier (a volatile zero from shared memory) and the row sums are stored before the arrive.
+        if (grp == 0 ? (c >= 1 && c - 1 < steps1) : true) {
+          float z;
+          asm volatile("bar.sync %1, 64;\n\tld.volatile.shared.f32 %0, [%2];" : "=f"(z) : "r"(3 + grp * 4 + quad), "r"(turn_zero) : "memory");
+          mneg += z;
+        }
 #pragma unroll
         for (int cc = 0; cc < KC / 8; ++cc) {  // sixteen 16-byte pieces = 128 keys (masked keys: exp2(-inf) = 0)
           float e[8];
@@ -265,6 +279,9 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const AttnTcParam
           pk[cc].x = pack_bf16x2(e[0], e[1]); pk[cc].y = pack_bf16x2(e[2], e[3]);
           pk[cc].z = pack_bf16x2(e[4], e[5]); pk[cc].w = pack_bf16x2(e[6], e[7]);
         }
+        if (grp == 0 ? (c < steps1) : (c + 1 < steps0))
+          asm volatile("st.volatile.shared.f32 [%0], %1;\n\tbar.arrive %2, 64;" ::"r"(turn_zero + 4 + (warp - 4) * 4), "f"(ls[0] + ls[1]),
+                       "r"(3 + (grp ^ 1) * 4 + quad) : "memory");
         if (c >= 1) mbar_wait(&gb[PV_DONE], (c - 1) & 1);  // the previous PV has finished reading the P buffer
 #pragma unroll
         for (int cc = 0; cc < KC / 8; ++cc) sts128(sP_row + (cc >> 3) * TILE16K + (((cc & 7) ^ (row & 7)) << 4), pk[cc]);
