@@ -28,8 +28,8 @@ constexpr int KC = 128;                     // keys per chunk = one TMA box of K
 constexpr int MAX_BOXES = 4;                // K / V arrive as 128-row TMA boxes: sequences up to 512 keys
 constexpr int TILE16K = 128 * 64 * 2;       // one [128 x 64] bf16 swizzled tile
 constexpr int NUM_THREADS = 384;
-constexpr int REGS_CONTROL = 48;            // setmaxnreg budgets: TMA / MMA warpgroup ...
-constexpr int REGS_SOFTMAX = 224;           // ... and the two softmax warpgroups (128*48 + 256*224 <= 64 K registers)
+constexpr int REGS_CONTROL = 56;            // setmaxnreg budgets: TMA / MMA warpgroup ...
+constexpr int REGS_SOFTMAX = 224;           // ... and the two softmax warpgroups (128*56 + 256*224 <= 64 K registers)
 constexpr float RESCALE_THRESHOLD = 8.0f;   // log2 units
 
 struct FwdSmem {
@@ -60,6 +60,24 @@ enum { Q_FULL = 0, Q_EMPTY, S_FULL, S_FREE, P_READY, PV_DONE, O_FREE, BARS_PER_G
 
 __device__ __forceinline__ void group_bar_sync(int grp) { asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory"); }
 
+// Optional timeline instrumentation (profiles/attn_trace.py builds a separate library with -DPLB_ATTN_TRACE): lane 0 of
+// every warp of CTA 0 appends (clock, warp, code, index) records.  Compiled out of the product library.
+#ifdef PLB_ATTN_TRACE
+constexpr unsigned TRACE_SLOTS = 512;  // records per warp; plain stores, no atomics, so the timeline stays undisturbed
+constexpr unsigned TRACE_CAP = 3 * 16 * TRACE_SLOTS;  // kernel id (0 fwd, 1 dQ, 2 dK/dV) x warp x slot
+__device__ unsigned long long g_trace[TRACE_CAP];
+#define PLB_TRACE_INIT(kid) unsigned trace_k = 0; const unsigned trace_w = (kid) * 16 + (threadIdx.x >> 5)
+#define PLB_TRACE(code, idx)                                                                                          \
+  do {                                                                                                                \
+    if (blockIdx.x == 0 && (threadIdx.x & 31) == 0 && trace_k < TRACE_SLOTS)                                          \
+      g_trace[trace_w * TRACE_SLOTS + trace_k++] = (static_cast<unsigned long long>(clock64()) << 24) |               \
+                                                   (trace_w << 16) | ((code) << 8) | ((idx) & 255);                   \
+  } while (0)
+#else
+#define PLB_TRACE_INIT(kid) do { } while (0)
+#define PLB_TRACE(code, idx) do { } while (0)
+#endif
+
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const AttnTcParams p, __nv_bfloat16* __restrict__ ctx,
                    int ld_ctx, float* __restrict__ lse2) {
@@ -72,6 +90,8 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const AttnTcParam
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + FwdSmem::kNumBars);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  PLB_TRACE_INIT(0);
+  PLB_TRACE(0, 0);
   const int b = blockIdx.x / p.heads, h = blockIdx.x % p.heads;
   const int row_base = p.seq_start[b], nq = p.q_len[b], nk = p.kv_len[b];
   const int H = p.heads * D;
@@ -106,7 +126,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const AttnTcParam
    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_CONTROL));
    if (warp == 0) {
     // ====================================== TMA producer ======================================
-    if (lane == 0) {
+    if (elect_one_sync()) {
       for (int g = 0; g < 2 && g < n_tiles; ++g) {
         uint64_t* gb = gbar + g * BARS_PER_GROUP;
         mbar_arrive_expect_tx(&gb[Q_FULL], TILE16K);
@@ -133,60 +153,61 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const AttnTcParam
       }
     }
     __syncwarp();
-  } else if (warp == 1) {
-    // ====================================== MMA issuer ======================================
-    if (lane == 0) {
-      constexpr uint32_t idesc_s = umma_idesc_bf16(128, KC, 0, 0);   // S = Q K^T : A K-major, B K-major
-      constexpr uint32_t idesc_o = umma_idesc_bf16(128, D, 0, 1);    // O = P V   : A K-major, B MN-major
-      const uint32_t sK = smem_u32(smem + FwdSmem::kK), sV = smem_u32(smem + FwdSmem::kV);
-      // Two op streams per group: S (at most one chunk ahead: one S buffer) and PV.
-      //   ks/js/cs : tile, chunk-in-tile and running count of the next S;  kp/jp/cp : same for the next PV
-      int ks[2] = {0, 0}, js[2] = {0, 0}, kp[2] = {0, 0}, jp[2] = {0, 0};
-      uint32_t cs[2] = {0, 0}, cp[2] = {0, 0};
-      const int tiles_of[2] = {(n_tiles + 1) >> 1, n_tiles >> 1};
-      while (kp[0] < tiles_of[0] || kp[1] < tiles_of[1]) {
+   } else if ((warp == 1 || warp == 2) && elect_one_sync()) {
+    // ====================================== MMA issuers: one thread per group ======================================
+    // A group's MMAs alternate deterministically — S of chunk c+1 becomes issuable when the group has pulled S_c out of
+    // TMEM, P V of chunk c when P_c is in shared memory — so the issuer blocks on exactly the barrier that is due next.
+    const int g = warp - 1;
+    const int my_tiles = g == 0 ? (n_tiles + 1) >> 1 : n_tiles >> 1;
+    constexpr uint32_t idesc_s = umma_idesc_bf16(128, KC, 0, 0);   // S = Q K^T : A K-major, B K-major
+    constexpr uint32_t idesc_o = umma_idesc_bf16(128, D, 0, 1);    // O = P V   : A K-major, B MN-major
+    uint64_t* gb = gbar + g * BARS_PER_GROUP;
+    const uint32_t tmem_sg = tmem_base + g * KC, tmem_og = tmem_base + 256 + g * D;
+    // descriptor bases; the start-address field counts 16-byte units, so advancing is a plain add
+    const uint64_t dQ = umma_smem_desc(smem_u32(smem + FwdSmem::kQ + g * TILE16K), 16, 1024);
+    const uint64_t dK = umma_smem_desc(smem_u32(smem + FwdSmem::kK), 16, 1024);
+    const uint64_t dV = umma_smem_desc(smem_u32(smem + FwdSmem::kV), TILE16K, 1024);
+    const uint64_t dP = umma_smem_desc(smem_u32(smem + FwdSmem::kP + g * 2 * TILE16K), 16, 1024);
+    const uint32_t total = my_tiles * n_chunks;
+    auto issue_s = [&](int k, int j, uint32_t cn) {  // S_j = Q K_j^T of the group's k-th tile
+      if (j == 0) mbar_wait(&gb[Q_FULL], k & 1);
+      if (k == 0) mbar_wait(&k_full[j], 0);
+      tc_fence_after();
+      const uint64_t kb = dK + static_cast<uint64_t>(j * (TILE16K >> 4));
 #pragma unroll
-        for (int g = 0; g < 2; ++g) {
-          uint64_t* gb = gbar + g * BARS_PER_GROUP;
-          // ---- O += P_j V_j ----
-          if (kp[g] < tiles_of[g] && mbar_test(&gb[P_READY], cp[g] & 1) &&
-              (jp[g] > 0 || mbar_test(&gb[O_FREE], (kp[g] & 1) ^ 1))) {
-            const int j = jp[g];
-            mbar_wait(&v_full[j], 0);
-            tc_fence_after();
-            const uint32_t sP = smem_u32(smem + FwdSmem::kP + g * 2 * TILE16K);
+      for (int kk = 0; kk < D / 16; ++kk) umma_bf16(tmem_sg, dQ + 2 * kk, kb + 2 * kk, idesc_s, kk > 0);
+      umma_commit(&gb[S_FULL]);
+      if (j == n_chunks - 1) umma_commit(&gb[Q_EMPTY]);
+      PLB_TRACE(1, cn);
+    };
+    if (total > 0) issue_s(0, 0, 0);
+    uint32_t c = 0;
+    for (int k = 0; k < my_tiles; ++k) {
+      for (int j = 0; j < n_chunks; ++j, ++c) {
+        const bool has_next = c + 1 < total;
+        const bool next_in_tile = j + 1 < n_chunks;
+        if (has_next && next_in_tile) {
+          mbar_wait(&gb[S_FREE], c & 1);
+          issue_s(k, j + 1, c + 1);
+        }
+        // ---- O += P_j V_j ----
+        mbar_wait(&gb[P_READY], c & 1);
+        if (j == 0) mbar_wait(&gb[O_FREE], (k & 1) ^ 1);
+        if (k == 0) mbar_wait(&v_full[j], 0);
+        tc_fence_after();
+        const uint64_t vb = dV + static_cast<uint64_t>(j * (TILE16K >> 4));
 #pragma unroll
-            for (int kk = 0; kk < KC / 16; ++kk)
-              umma_bf16(tmem_base + 256 + g * D, umma_smem_desc(sP + (kk >> 2) * TILE16K + (kk & 3) * 32, 16, 1024),
-                        umma_smem_desc(sV + j * TILE16K + kk * 2048, TILE16K, 1024), idesc_o, (j > 0 || kk > 0));
-            umma_commit(&gb[PV_DONE]);
-            ++cp[g];
-            if (++jp[g] == n_chunks) { jp[g] = 0; ++kp[g]; }
-          }
-          // ---- S_j = Q K_j^T as soon as the group has pulled the previous S out of TMEM ----
-          if (ks[g] < tiles_of[g] &&
-              (cs[g] == 0 || mbar_test(&gb[S_FREE], (cs[g] - 1) & 1)) &&
-              (js[g] > 0 || mbar_test(&gb[Q_FULL], ks[g] & 1))) {
-            const int j = js[g];
-            mbar_wait(&k_full[j], 0);
-            tc_fence_after();
-            const uint32_t sQ = smem_u32(smem + FwdSmem::kQ + g * TILE16K);
-#pragma unroll
-            for (int kk = 0; kk < D / 16; ++kk)
-              umma_bf16(tmem_base + g * KC, umma_smem_desc(sQ + kk * 32, 16, 1024),
-                        umma_smem_desc(sK + j * TILE16K + kk * 32, 16, 1024), idesc_s, kk > 0);
-            umma_commit(&gb[S_FULL]);
-            ++cs[g];
-            if (++js[g] == n_chunks) {
-              umma_commit(&gb[Q_EMPTY]);
-              js[g] = 0;
-              ++ks[g];
-            }
-          }
+        for (int kk = 0; kk < KC / 16; ++kk)
+          umma_bf16(tmem_og, dP + static_cast<uint64_t>((kk >> 2) * (TILE16K >> 4) + (kk & 3) * 2), vb + 128 * kk, idesc_o,
+                    (j > 0 || kk > 0));
+        umma_commit(&gb[PV_DONE]);
+        PLB_TRACE(2, c);
+        if (has_next && !next_in_tile) {  // next tile: its Q arrives only after this tile's last S MMA has run
+          mbar_wait(&gb[S_FREE], c & 1);
+          issue_s(k + 1, 0, c + 1);
         }
       }
     }
-    __syncwarp();
    }
   } else {
     asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS_SOFTMAX));
@@ -209,6 +230,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const AttnTcParam
       for (int j = 0; j < n_chunks; ++j, ++c) {
         mbar_wait(&gb[S_FULL], c & 1);
         tc_fence_after();
+        PLB_TRACE(10, c);
         // pull the 128 scores of this row out of TMEM and hand the S buffer straight back to the MMA warp, so that
         // S_{c+1} is computed while this group is busy with the exponentials of chunk c
         uint32_t sv[KC];
@@ -218,6 +240,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const AttnTcParam
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&gb[S_FREE]);
+        PLB_TRACE(11, c);
         const int valid = nk - j * KC;  // only the last chunk can hold keys >= kv_len -> -inf
         if (valid < KC) {
 #pragma unroll
@@ -259,6 +282,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const AttnTcParam
         // which still reads the group's single P buffer; only the stores wait for it.
         float ls[2] = {0.f, 0.f};
         float mneg = -m_used;
+        PLB_TRACE(12, c);
         uint4 pk[KC / 8];
         // The two groups' warps of one quadrant share an SM sub-partition and its MUFU.  Take turns on the exponential
         // phase (64-thread named barriers, one pair per quadrant) so that one warp's exponentials overlap the other
@@ -270,6 +294,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const AttnTcParam
           asm volatile("bar.sync %1, 64;\n\tld.volatile.shared.f32 %0, [%2];" : "=f"(z) : "r"(3 + grp * 4 + quad), "r"(turn_zero) : "memory");
           mneg += z;
         }
+        PLB_TRACE(13, c);
 #pragma unroll
         for (int cc = 0; cc < KC / 8; ++cc) {  // sixteen 16-byte pieces = 128 keys (masked keys: exp2(-inf) = 0)
           float e[8];
@@ -282,7 +307,9 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const AttnTcParam
         if (grp == 0 ? (c < steps1) : (c + 1 < steps0))
           asm volatile("st.volatile.shared.f32 [%0], %1;\n\tbar.arrive %2, 64;" ::"r"(turn_zero + 4 + (warp - 4) * 4), "f"(ls[0] + ls[1]),
                        "r"(3 + (grp ^ 1) * 4 + quad) : "memory");
+        PLB_TRACE(14, c);
         if (c >= 1) mbar_wait(&gb[PV_DONE], (c - 1) & 1);  // the previous PV has finished reading the P buffer
+        PLB_TRACE(15, c);
 #pragma unroll
         for (int cc = 0; cc < KC / 8; ++cc) sts128(sP_row + (cc >> 3) * TILE16K + (((cc & 7) ^ (row & 7)) << 4), pk[cc]);
         l_run += ls[0] + ls[1];
@@ -290,10 +317,12 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const AttnTcParam
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&gb[P_READY]);
+        PLB_TRACE(16, c);
       }
       // ---- epilogue of the tile: O / l -> bf16 -> staging (the group's P buffer) -> global; LSE ----
       mbar_wait(&gb[PV_DONE], (c - 1) & 1);  // all PV MMAs of the tile are complete: O final, P buffer dead
       tc_fence_after();
+      PLB_TRACE(20, t);
       const float inv = 1.f / l_run;
 #pragma unroll
       for (int q = 0; q < 2; ++q) {
@@ -327,10 +356,12 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const AttnTcParam
         }
       }
       group_bar_sync(grp);  // staging fully read before the next tile's P overwrites it
+      PLB_TRACE(21, t);
     }
   }
   tc_fence_before();
   __syncthreads();
+  PLB_TRACE(99, 0);
   if (warp == 1) tmem_dealloc(tmem_base, 512);
 }
 
@@ -450,6 +481,8 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_c
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + DqSmem::kNumBars);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  PLB_TRACE_INIT(1);
+  PLB_TRACE(0, 0);
   const int b = blockIdx.x / p.heads, h = blockIdx.x % p.heads;
   const int row_base = p.seq_start[b], nq = p.q_len[b], nk = p.kv_len[b];
   const int H = p.heads * D;
@@ -482,7 +515,7 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_c
 
   if (warp < 4) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_CONTROL));
-    if (warp == 0 && lane == 0) {
+    if (warp == 0 && elect_one_sync()) {
       // ====================================== TMA producer ======================================
       auto load_tile = [&](int g, int t) {
         uint64_t* gb = gbar + g * 7;
@@ -507,57 +540,63 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_c
         mbar_wait(&gbar[g * 7 + QDO_EMPTY], (k - 1) & 1);
         load_tile(g, t);
       }
-    } else if (warp == 1 && lane == 0) {
-      // ====================================== MMA issuer ======================================
+    } else if ((warp == 1 || warp == 2) && elect_one_sync()) {
+      // ====================================== MMA issuers: one thread per group ======================================
+      // A group's MMAs alternate deterministically — S/dP of chunk c+1 becomes issuable when the group has pulled chunk c
+      // out of TMEM (early in its softmax pass), dQ of chunk c when its dS is in shared memory (end of the pass) — so
+      // the issuer blocks on exactly the barrier that is due next; there is no polling loop.
+      const int g = warp - 1;
+      const int my_tiles = g == 0 ? (n_tiles + 1) >> 1 : n_tiles >> 1;
       constexpr uint32_t idesc_sd = umma_idesc_bf16(128, BC, 0, 0);  // S = Q K^T, dP = dO V^T : all K-major
       constexpr uint32_t idesc_dq = umma_idesc_bf16(128, D, 0, 1);   // dQ = dS K : A K-major, B MN-major
-      const uint32_t sK = smem_u32(smem + DqSmem::kK), sV = smem_u32(smem + DqSmem::kV);
-      int ks[2] = {0, 0}, js[2] = {0, 0}, kp[2] = {0, 0}, jp[2] = {0, 0};
-      uint32_t cs[2] = {0, 0}, cp[2] = {0, 0};
-      const int tiles_of[2] = {(n_tiles + 1) >> 1, n_tiles >> 1};
-      while (kp[0] < tiles_of[0] || kp[1] < tiles_of[1]) {
+      uint64_t* gb = gbar + g * 7;
+      const uint32_t tg = tmem_base + g * 192;
+      // descriptor bases; the start-address field counts 16-byte units, so advancing is a plain add
+      const uint64_t dQt = umma_smem_desc(smem_u32(smem + DqSmem::kQ + g * TILE16K), 16, 1024);
+      const uint64_t dDO = umma_smem_desc(smem_u32(smem + DqSmem::kDO + g * TILE16K), 16, 1024);
+      const uint64_t dDS = umma_smem_desc(smem_u32(smem + DqSmem::kDS + g * TILE16K), 16, 1024);
+      const uint64_t dKk = umma_smem_desc(smem_u32(smem + DqSmem::kK), 16, 1024);        // K-major view (S)
+      const uint64_t dVk = umma_smem_desc(smem_u32(smem + DqSmem::kV), 16, 1024);        // K-major view (dP)
+      const uint64_t dKm = umma_smem_desc(smem_u32(smem + DqSmem::kK), TILE16K, 1024);   // MN-major view (dQ)
+      const uint32_t total = my_tiles * n_chunks;
+      auto issue_sd = [&](int k, int j) {  // S_j = Q K_j^T and dP_j = dO V_j^T of the group's k-th tile
+        if (j == 0) mbar_wait(&gb[QDO_FULL], k & 1);
+        if (k == 0 && (j & 1) == 0) {
+          mbar_wait(&k_full[j >> 1], 0);
+          mbar_wait(&v_full[j >> 1], 0);
+        }
+        tc_fence_after();
+        const uint64_t kb = dKk + static_cast<uint64_t>(j * (CHUNK8K >> 4)), vb = dVk + static_cast<uint64_t>(j * (CHUNK8K >> 4));
 #pragma unroll
-        for (int g = 0; g < 2; ++g) {
-          uint64_t* gb = gbar + g * 7;
-          const uint32_t tg = tmem_base + g * 192;
-          // ---- dQ += dS_j K_j ----
-          if (kp[g] < tiles_of[g] && mbar_test(&gb[DS_READY], cp[g] & 1) &&
-              (jp[g] > 0 || mbar_test(&gb[DQ_FREE], (kp[g] & 1) ^ 1))) {
-            const int j = jp[g];
-            tc_fence_after();
-            const uint32_t sDS = smem_u32(smem + DqSmem::kDS + g * TILE16K);
+        for (int kk = 0; kk < D / 16; ++kk) umma_bf16(tg, dQt + 2 * kk, kb + 2 * kk, idesc_sd, kk > 0);
 #pragma unroll
-            for (int kk = 0; kk < BC / 16; ++kk)
-              umma_bf16(tg + 128, umma_smem_desc(sDS + kk * 32, 16, 1024),
-                        umma_smem_desc(sK + j * CHUNK8K + kk * 2048, TILE16K, 1024), idesc_dq, (j > 0 || kk > 0));
-            umma_commit(&gb[DQ_DONE]);
-            ++cp[g];
-            if (++jp[g] == n_chunks) { jp[g] = 0; ++kp[g]; }
+        for (int kk = 0; kk < D / 16; ++kk) umma_bf16(tg + 64, dDO + 2 * kk, vb + 2 * kk, idesc_sd, kk > 0);
+        umma_commit(&gb[SD_FULL]);
+        if (j == n_chunks - 1) umma_commit(&gb[QDO_EMPTY]);
+        PLB_TRACE(1, j);
+      };
+      if (total > 0) issue_sd(0, 0);
+      uint32_t c = 0;
+      for (int k = 0; k < my_tiles; ++k) {
+        for (int j = 0; j < n_chunks; ++j, ++c) {
+          const bool has_next = c + 1 < total;
+          const bool next_in_tile = j + 1 < n_chunks;
+          if (has_next && next_in_tile) {
+            mbar_wait(&gb[SD_FREE], c & 1);
+            issue_sd(k, j + 1);
           }
-          // ---- S_j = Q K_j^T and dP_j = dO V_j^T ----
-          if (ks[g] < tiles_of[g] && (cs[g] == 0 || mbar_test(&gb[SD_FREE], (cs[g] - 1) & 1)) &&
-              (js[g] > 0 || mbar_test(&gb[QDO_FULL], ks[g] & 1))) {
-            const int j = js[g];
-            mbar_wait(&k_full[j >> 1], 0);
-            mbar_wait(&v_full[j >> 1], 0);
-            tc_fence_after();
-            const uint32_t sQ = smem_u32(smem + DqSmem::kQ + g * TILE16K);
-            const uint32_t sDO = smem_u32(smem + DqSmem::kDO + g * TILE16K);
+          // ---- dQ += dS_j K_j ----
+          mbar_wait(&gb[DS_READY], c & 1);
+          if (j == 0) mbar_wait(&gb[DQ_FREE], (k & 1) ^ 1);
+          tc_fence_after();
+          const uint64_t kb = dKm + static_cast<uint64_t>(j * (CHUNK8K >> 4));
 #pragma unroll
-            for (int kk = 0; kk < D / 16; ++kk)
-              umma_bf16(tg, umma_smem_desc(sQ + kk * 32, 16, 1024),
-                        umma_smem_desc(sK + j * CHUNK8K + kk * 32, 16, 1024), idesc_sd, kk > 0);
-#pragma unroll
-            for (int kk = 0; kk < D / 16; ++kk)
-              umma_bf16(tg + 64, umma_smem_desc(sDO + kk * 32, 16, 1024),
-                        umma_smem_desc(sV + j * CHUNK8K + kk * 32, 16, 1024), idesc_sd, kk > 0);
-            umma_commit(&gb[SD_FULL]);
-            ++cs[g];
-            if (++js[g] == n_chunks) {
-              umma_commit(&gb[QDO_EMPTY]);
-              js[g] = 0;
-              ++ks[g];
-            }
+          for (int kk = 0; kk < BC / 16; ++kk) umma_bf16(tg + 128, dDS + 2 * kk, kb + 128 * kk, idesc_dq, (j > 0 || kk > 0));
+          umma_commit(&gb[DQ_DONE]);
+          PLB_TRACE(2, c);
+          if (has_next && !next_in_tile) {  // next tile: its Q / dO arrive only after this tile's last S / dP has run
+            mbar_wait(&gb[SD_FREE], c & 1);
+            issue_sd(k + 1, 0);
           }
         }
       }
@@ -585,6 +624,7 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_c
       for (int j = 0; j < n_chunks; ++j, ++c) {
         mbar_wait(&gb[SD_FULL], c & 1);
         tc_fence_after();
+        PLB_TRACE(10, c);
         uint32_t sv[BC], dv[BC];
         tmem_ld_32x32(tg, *reinterpret_cast<uint32_t(*)[32]>(&sv[0]));
         tmem_ld_32x32(tg + 32, *reinterpret_cast<uint32_t(*)[32]>(&sv[32]));
@@ -594,6 +634,7 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_c
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&gb[SD_FREE]);
+        PLB_TRACE(11, c);
         const int valid = nk - j * BC;  // keys >= kv_len are masked: P = 0
         uint4 pk[BC / 8];
 #pragma unroll
@@ -608,17 +649,21 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_c
           pk[cc].x = pack_bf16x2(e[0], e[1]); pk[cc].y = pack_bf16x2(e[2], e[3]);
           pk[cc].z = pack_bf16x2(e[4], e[5]); pk[cc].w = pack_bf16x2(e[6], e[7]);
         }
+        PLB_TRACE(14, c);
         if (c >= 1) mbar_wait(&gb[DQ_DONE], (c - 1) & 1);  // the dS buffer has been consumed by the previous dQ MMA
+        PLB_TRACE(15, c);
 #pragma unroll
         for (int cc = 0; cc < BC / 8; ++cc) sts128(sDS_row + ((cc ^ (row & 7)) << 4), pk[cc]);
         fence_proxy_async_smem();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&gb[DS_READY]);
+        PLB_TRACE(16, c);
       }
       // ---- tile epilogue: dQ * scale -> bf16 -> staging (dS buffer) -> global ----
       mbar_wait(&gb[DQ_DONE], (c - 1) & 1);
       tc_fence_after();
+      PLB_TRACE(20, t);
 #pragma unroll
       for (int q = 0; q < 2; ++q) {
         uint32_t o[32];
@@ -649,10 +694,12 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_c
       }
       if (dbias != nullptr) tile_colsum_atomic(sDS, min(QT, nq - t * QT), gtid, dbias + h * D);
       group_bar_sync(grp);
+      PLB_TRACE(21, t);
     }
   }
   tc_fence_before();
   __syncthreads();
+  PLB_TRACE(99, 0);
   if (warp == 1) tmem_dealloc(tmem_base, 512);
 }
 
@@ -665,8 +712,8 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_c
 struct DkvSmem {
   static constexpr int kGroup = 6 * TILE16K;                 // per group: K | V | ring (2 x (Q 8K + dO 8K)) | P^T | dS^T
   static constexpr int kK = 0, kV = TILE16K, kRing = 2 * TILE16K, kPT = 4 * TILE16K, kDST = 5 * TILE16K;
-  static constexpr int kStat = 2 * kGroup;                   // per group: float [2 slots][2 (lse, delta)][64]
-  static constexpr int kBar = kStat + 2 * 2 * 2 * 64 * 4;
+  static constexpr int kStat = 2 * kGroup;                   // float [2 (lse, delta)][512]: statistics of every query row
+  static constexpr int kBar = kStat + 2 * MAX_BOXES * 128 * 4;
   static constexpr int kBarsPerGroup = 11;
   static constexpr int kAlloc = kBar + 2 * kBarsPerGroup * 8 + 16;
 };
@@ -684,6 +731,8 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv128, const __gr
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(gbar + 2 * DkvSmem::kBarsPerGroup);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  PLB_TRACE_INIT(2);
+  PLB_TRACE(0, 0);
   const int b = blockIdx.x / p.heads, h = blockIdx.x % p.heads;
   const int row_base = p.seq_start[b], nq = p.q_len[b], nk = p.kv_len[b];
   const int H = p.heads * D;
@@ -705,6 +754,16 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv128, const __gr
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc(tmem_ptr_smem, 512);
+  {
+    // log-sum-exp and delta of every query row of the sequence, staged once: the threads own KEY rows here and need
+    // the statistics of all query COLUMNS (rows beyond the sequence: lse = +inf -> P = 0)
+    float* stat_all = reinterpret_cast<float*>(smem + DkvSmem::kStat);
+    const size_t base = static_cast<size_t>(h) * p.total_rows + row_base;
+    for (int q = threadIdx.x; q < MAX_BOXES * 128; q += NUM_THREADS) {
+      stat_all[q] = q < nq ? lse2[base + q] : INFINITY;
+      stat_all[MAX_BOXES * 128 + q] = q < nq ? delta[base + q] : 0.f;
+    }
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -713,90 +772,80 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv128, const __gr
 
   if (warp < 4) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_CONTROL));
-    if (warp == 0 && lane == 0) {
-      // ====================================== TMA producer (two independent streams) ======================================
-      int kl[2] = {0, 0}, jl[2] = {0, 0};
-      uint32_t lc[2] = {0, 0};
-      while (kl[0] < tiles_of[0] || kl[1] < tiles_of[1]) {
-#pragma unroll
-        for (int g = 0; g < 2; ++g) {
-          if (kl[g] >= tiles_of[g]) continue;
-          uint64_t* gb = gbar + g * DkvSmem::kBarsPerGroup;
-          uint8_t* gs = smem + g * DkvSmem::kGroup;
-          if (jl[g] == 0) {
-            // new key tile: K_t / V_t buffers are free once every S^T / dP^T MMA of the previous tile has run
-            if (kl[g] > 0 && !mbar_test(&gb[KV_EMPTY], (kl[g] - 1) & 1)) continue;
-            const int t = g + 2 * kl[g];
-            mbar_arrive_expect_tx(&gb[KV_FULL], 2 * TILE16K);
-            tma_load_2d(gs + DkvSmem::kK, &tm_qkv128, &gb[KV_FULL], H + h * D, row_base + t * 128);
-            tma_load_2d(gs + DkvSmem::kV, &tm_qkv128, &gb[KV_FULL], 2 * H + h * D, row_base + t * 128);
-          }
-          const int slot = lc[g] & 1;
-          if (lc[g] >= 2 && !mbar_test(&gb[RING_FREE0 + slot], ((lc[g] >> 1) - 1) & 1)) {
-            if (jl[g] == 0) jl[g] = -1;  // K/V already issued for this tile: do not issue them again
-            continue;
-          }
-          if (jl[g] < 0) jl[g] = 0;
+    // warps 0 / 3: TMA producers of group 0 / 1; warps 1 / 2: MMA issuers of group 0 / 1.  Every role blocks on the one
+    // barrier that is due next (the order of a group's operations is fixed), so there are no polling loops.
+    const int g = (warp == 0 || warp == 1) ? 0 : 1;
+    uint64_t* gb = gbar + g * DkvSmem::kBarsPerGroup;
+    if ((warp == 0 || warp == 3) && elect_one_sync()) {
+      // ====================================== TMA producer of group g ======================================
+      uint8_t* gs = smem + g * DkvSmem::kGroup;
+      uint32_t lc = 0;
+      for (int kl = 0; kl < tiles_of[g]; ++kl) {
+        const int t = g + 2 * kl;
+        // K_t / V_t buffers are free once every S^T / dP^T MMA of the previous tile has run
+        if (kl > 0) mbar_wait(&gb[KV_EMPTY], (kl - 1) & 1);
+        mbar_arrive_expect_tx(&gb[KV_FULL], 2 * TILE16K);
+        tma_load_2d(gs + DkvSmem::kK, &tm_qkv128, &gb[KV_FULL], H + h * D, row_base + t * 128);
+        tma_load_2d(gs + DkvSmem::kV, &tm_qkv128, &gb[KV_FULL], 2 * H + h * D, row_base + t * 128);
+        for (int jl = 0; jl < n_qc; ++jl, ++lc) {
+          const int slot = lc & 1;
+          if (lc >= 2) mbar_wait(&gb[RING_FREE0 + slot], ((lc >> 1) - 1) & 1);
           uint8_t* ring = gs + DkvSmem::kRing + slot * TILE16K;
           mbar_arrive_expect_tx(&gb[RING_FULL0 + slot], TILE16K);
-          tma_load_2d(ring, &tm_qkv64, &gb[RING_FULL0 + slot], h * D, row_base + jl[g] * BC);
-          tma_load_2d(ring + CHUNK8K, &tm_dctx64, &gb[RING_FULL0 + slot], h * D, row_base + jl[g] * BC);
-          ++lc[g];
-          if (++jl[g] == n_qc) { jl[g] = 0; ++kl[g]; }
+          tma_load_2d(ring, &tm_qkv64, &gb[RING_FULL0 + slot], h * D, row_base + jl * BC);
+          tma_load_2d(ring + CHUNK8K, &tm_dctx64, &gb[RING_FULL0 + slot], h * D, row_base + jl * BC);
         }
       }
-    } else if (warp == 1 && lane == 0) {
-      // ====================================== MMA issuer ======================================
+    } else if ((warp == 1 || warp == 2) && elect_one_sync()) {
+      // ====================================== MMA issuer of group g ======================================
       constexpr uint32_t idesc_st = umma_idesc_bf16(128, BC, 0, 0);  // S^T = K Q^T, dP^T = V dO^T : all K-major
       constexpr uint32_t idesc_acc = umma_idesc_bf16(128, D, 0, 1);  // dV = P^T dO, dK = dS^T Q : B MN-major
-      int ks[2] = {0, 0}, js[2] = {0, 0}, kp[2] = {0, 0}, jp[2] = {0, 0};
-      uint32_t cs[2] = {0, 0}, cp[2] = {0, 0};
-      while (kp[0] < tiles_of[0] || kp[1] < tiles_of[1]) {
+      const uint32_t gs = smem_u32(smem + g * DkvSmem::kGroup);
+      const uint32_t tg = tmem_base + g * 256;
+      // descriptor bases; the start-address field counts 16-byte units, so advancing is a plain add
+      const uint64_t dK = umma_smem_desc(gs + DkvSmem::kK, 16, 1024), dV = umma_smem_desc(gs + DkvSmem::kV, 16, 1024);
+      const uint64_t dPT = umma_smem_desc(gs + DkvSmem::kPT, 16, 1024), dDST = umma_smem_desc(gs + DkvSmem::kDST, 16, 1024);
+      const uint64_t dRingK = umma_smem_desc(gs + DkvSmem::kRing, 16, 1024);        // Q / dO chunk, K-major view
+      const uint64_t dRingM = umma_smem_desc(gs + DkvSmem::kRing, TILE16K, 1024);   // same bytes, MN-major view
+      const uint32_t total = tiles_of[g] * n_qc;
+      auto issue_st = [&](int k, int j, uint32_t cn) {  // S^T = K_t Q_c^T ; dP^T = V_t dO_c^T for running chunk count cn
+        if (j == 0) mbar_wait(&gb[KV_FULL], k & 1);
+        mbar_wait(&gb[RING_FULL0 + (cn & 1)], (cn >> 1) & 1);
+        tc_fence_after();
+        const uint64_t rq = dRingK + static_cast<uint64_t>((cn & 1) * (TILE16K >> 4)), rdo = rq + (CHUNK8K >> 4);
 #pragma unroll
-        for (int g = 0; g < 2; ++g) {
-          uint64_t* gb = gbar + g * DkvSmem::kBarsPerGroup;
-          const uint32_t gs = smem_u32(smem + g * DkvSmem::kGroup);
-          const uint32_t tg = tmem_base + g * 256;
-          // ---- dV += P^T dO_c ; dK += dS^T Q_c ----
-          if (kp[g] < tiles_of[g] && mbar_test(&gb[PDS_READY], cp[g] & 1) &&
-              (jp[g] > 0 || mbar_test(&gb[ACC_FREE], (kp[g] & 1) ^ 1))) {
-            const int slot = cp[g] & 1;
-            tc_fence_after();
-            const uint32_t ring = gs + DkvSmem::kRing + slot * TILE16K;
+        for (int kk = 0; kk < D / 16; ++kk) umma_bf16(tg, dK + 2 * kk, rq + 2 * kk, idesc_st, kk > 0);
 #pragma unroll
-            for (int kk = 0; kk < BC / 16; ++kk)
-              umma_bf16(tg + 192, umma_smem_desc(gs + DkvSmem::kPT + kk * 32, 16, 1024),
-                        umma_smem_desc(ring + CHUNK8K + kk * 2048, TILE16K, 1024), idesc_acc, (jp[g] > 0 || kk > 0));
-#pragma unroll
-            for (int kk = 0; kk < BC / 16; ++kk)
-              umma_bf16(tg + 128, umma_smem_desc(gs + DkvSmem::kDST + kk * 32, 16, 1024),
-                        umma_smem_desc(ring + kk * 2048, TILE16K, 1024), idesc_acc, (jp[g] > 0 || kk > 0));
-            umma_commit(&gb[DKV_DONE]);
-            umma_commit(&gb[RING_FREE0 + slot]);
-            ++cp[g];
-            if (++jp[g] == n_qc) { jp[g] = 0; ++kp[g]; }
+        for (int kk = 0; kk < D / 16; ++kk) umma_bf16(tg + 64, dV + 2 * kk, rdo + 2 * kk, idesc_st, kk > 0);
+        umma_commit(&gb[ST_FULL]);
+        if (j == n_qc - 1) umma_commit(&gb[KV_EMPTY]);
+        PLB_TRACE(1, cn);
+      };
+      if (total > 0) issue_st(0, 0, 0);
+      uint32_t c = 0;
+      for (int k = 0; k < tiles_of[g]; ++k) {
+        for (int j = 0; j < n_qc; ++j, ++c) {
+          const bool has_next = c + 1 < total;
+          const bool next_in_tile = j + 1 < n_qc;
+          if (has_next && next_in_tile) {
+            mbar_wait(&gb[ST_FREE], c & 1);
+            issue_st(k, j + 1, c + 1);
           }
-          // ---- S^T = K_t Q_c^T ; dP^T = V_t dO_c^T ----
-          if (ks[g] < tiles_of[g] && (cs[g] == 0 || mbar_test(&gb[ST_FREE], (cs[g] - 1) & 1)) &&
-              mbar_test(&gb[RING_FULL0 + (cs[g] & 1)], (cs[g] >> 1) & 1) &&
-              (js[g] > 0 || mbar_test(&gb[KV_FULL], ks[g] & 1))) {
-            tc_fence_after();
-            const uint32_t ring = gs + DkvSmem::kRing + (cs[g] & 1) * TILE16K;
+          // ---- dV += P^T dO_c ; dK += dS^T Q_c ----
+          mbar_wait(&gb[PDS_READY], c & 1);
+          if (j == 0) mbar_wait(&gb[ACC_FREE], (k & 1) ^ 1);
+          tc_fence_after();
+          const uint64_t rq = dRingM + static_cast<uint64_t>((c & 1) * (TILE16K >> 4)), rdo = rq + (CHUNK8K >> 4);
 #pragma unroll
-            for (int kk = 0; kk < D / 16; ++kk)
-              umma_bf16(tg, umma_smem_desc(gs + DkvSmem::kK + kk * 32, 16, 1024),
-                        umma_smem_desc(ring + kk * 32, 16, 1024), idesc_st, kk > 0);
+          for (int kk = 0; kk < BC / 16; ++kk) umma_bf16(tg + 192, dPT + 2 * kk, rdo + 128 * kk, idesc_acc, (j > 0 || kk > 0));
 #pragma unroll
-            for (int kk = 0; kk < D / 16; ++kk)
-              umma_bf16(tg + 64, umma_smem_desc(gs + DkvSmem::kV + kk * 32, 16, 1024),
-                        umma_smem_desc(ring + CHUNK8K + kk * 32, 16, 1024), idesc_st, kk > 0);
-            umma_commit(&gb[ST_FULL]);
-            ++cs[g];
-            if (++js[g] == n_qc) {
-              umma_commit(&gb[KV_EMPTY]);
-              js[g] = 0;
-              ++ks[g];
-            }
+          for (int kk = 0; kk < BC / 16; ++kk) umma_bf16(tg + 128, dDST + 2 * kk, rq + 128 * kk, idesc_acc, (j > 0 || kk > 0));
+          umma_commit(&gb[DKV_DONE]);
+          umma_commit(&gb[RING_FREE0 + (c & 1)]);
+          PLB_TRACE(2, c);
+          if (has_next && !next_in_tile) {  // next key tile: its K / V arrive only after this tile's last S^T / dP^T has run
+            mbar_wait(&gb[ST_FREE], c & 1);
+            issue_st(k + 1, 0, c + 1);
           }
         }
       }
@@ -814,10 +863,7 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv128, const __gr
     uint64_t* gb = gbar + grp * DkvSmem::kBarsPerGroup;
     const uint32_t gs = smem_u32(smem + grp * DkvSmem::kGroup);
     const uint32_t sPT_row = gs + DkvSmem::kPT + row * 128, sDST_row = gs + DkvSmem::kDST + row * 128;
-    float* stat = reinterpret_cast<float*>(smem + DkvSmem::kStat) + grp * 256;  // [2 slots][2][64]
-    const uint32_t stat_addr = smem_u32(stat);
-    const float* lse_seq = lse2 + static_cast<size_t>(h) * p.total_rows + row_base;
-    const float* dl_seq = delta + static_cast<size_t>(h) * p.total_rows + row_base;
+    const uint32_t stat_addr = smem_u32(smem + DkvSmem::kStat);  // float [2 (lse, delta)][512 query rows]
 
     // key rows in [128 * n_kt, nq): padded keys inside the allocated sequence -> their gradients are exactly zero
     for (int t = n_kt + grp; t * 128 < nq; t += 2) {
@@ -837,15 +883,10 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv128, const __gr
     for (int t = grp; t < n_kt; t += 2) {
       const bool key_valid = (t * 128 + row) < nk;
       for (int j = 0; j < n_qc; ++j, ++c) {
-        // stage lse / delta of this chunk's 64 query columns (rows beyond the sequence: lse = +inf -> P = 0)
-        if (gtid < 64) {
-          const int q = j * BC + gtid;
-          stat[(c & 1) * 128 + gtid] = q < nq ? lse_seq[q] : INFINITY;
-          stat[(c & 1) * 128 + 64 + gtid] = q < nq ? dl_seq[q] : 0.f;
-        }
-        group_bar_sync(grp);
+        PLB_TRACE(9, c);
         mbar_wait(&gb[ST_FULL], c & 1);
         tc_fence_after();
+        PLB_TRACE(10, c);
         uint32_t sv[BC], dv[BC];
         tmem_ld_32x32(tg, *reinterpret_cast<uint32_t(*)[32]>(&sv[0]));
         tmem_ld_32x32(tg + 32, *reinterpret_cast<uint32_t(*)[32]>(&sv[32]));
@@ -855,12 +896,13 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv128, const __gr
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&gb[ST_FREE]);
-        const uint32_t st = stat_addr + (c & 1) * 512;
+        PLB_TRACE(11, c);
+        const uint32_t st = stat_addr + j * (BC * 4);
         uint4 pkp[BC / 8], pkd[BC / 8];
 #pragma unroll
         for (int cc = 0; cc < BC / 8; ++cc) {
           const float4 l0 = lds128_ro(st + cc * 32), l1 = lds128_ro(st + cc * 32 + 16);
-          const float4 d0 = lds128_ro(st + 256 + cc * 32), d1 = lds128_ro(st + 256 + cc * 32 + 16);
+          const float4 d0 = lds128_ro(st + MAX_BOXES * 512 + cc * 32), d1 = lds128_ro(st + MAX_BOXES * 512 + cc * 32 + 16);
           const float ls[8] = {l0.x, l0.y, l0.z, l0.w, l1.x, l1.y, l1.z, l1.w};
           const float dl[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
           float pr[8], ds[8];
@@ -875,7 +917,9 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv128, const __gr
           pkd[cc].x = pack_bf16x2(ds[0], ds[1]); pkd[cc].y = pack_bf16x2(ds[2], ds[3]);
           pkd[cc].z = pack_bf16x2(ds[4], ds[5]); pkd[cc].w = pack_bf16x2(ds[6], ds[7]);
         }
+        PLB_TRACE(14, c);
         if (c >= 1) mbar_wait(&gb[DKV_DONE], (c - 1) & 1);  // P^T / dS^T buffers consumed by the previous dV / dK MMAs
+        PLB_TRACE(15, c);
 #pragma unroll
         for (int cc = 0; cc < BC / 8; ++cc) {
           sts128(sPT_row + ((cc ^ (row & 7)) << 4), pkp[cc]);
@@ -885,10 +929,12 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv128, const __gr
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&gb[PDS_READY]);
+        PLB_TRACE(16, c);
       }
       // ---- tile epilogue: dK * scale, dV -> bf16 -> staging (P^T / dS^T buffers) -> global ----
       mbar_wait(&gb[DKV_DONE], (c - 1) & 1);
       tc_fence_after();
+      PLB_TRACE(20, t);
 #pragma unroll
       for (int which = 0; which < 2; ++which) {  // 0: dK (cols 128..191), 1: dV (cols 192..255)
         const float mul = which == 0 ? p.scale : 1.f;
@@ -930,10 +976,12 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv128, const __gr
         tile_colsum_atomic(gs + DkvSmem::kDST, min(128, nk - t * 128), gtid, dbias + 2 * H + h * D);
       }
       group_bar_sync(grp);
+      PLB_TRACE(21, t);
     }
   }
   tc_fence_before();
   __syncthreads();
+  PLB_TRACE(99, 0);
   if (warp == 1) tmem_dealloc(tmem_base, 512);
 }
 
@@ -986,3 +1034,17 @@ extern "C" int plb_attn_bwd_tc(const void* qkv, int ld_qkv, const int32_t* seq_s
                                                                               dbias_qkv_accum);
   return check_launch("plb_attn_bwd_tc(dkv)");
 }
+
+#ifdef PLB_ATTN_TRACE
+// Trace build only: copies the record table (zero = unused slot) to the host and clears it.
+extern "C" int plb_attn_trace_dump(unsigned long long* host, int cap) {
+  if (cap < static_cast<int>(plb::TRACE_CAP)) return -1;
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(host, plb::g_trace, sizeof(plb::g_trace));
+  void* dev = nullptr;
+  cudaGetSymbolAddress(&dev, plb::g_trace);
+  cudaMemset(dev, 0, sizeof(plb::g_trace));
+  cudaDeviceSynchronize();
+  return static_cast<int>(plb::TRACE_CAP);
+}
+#endif

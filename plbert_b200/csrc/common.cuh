@@ -195,6 +195,13 @@ __device__ __forceinline__ void umma_commit_2cta(uint64_t* bar, uint16_t cta_mas
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 // D[tmem] (+)= A[smem desc] * B[smem desc]; bf16 x bf16 -> fp32. One thread issues for the CTA.
+// One lane of a converged warp (elect.sync): ptxas then knows the guarded region runs on a single thread.
+__device__ __forceinline__ bool elect_one_sync() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+
 __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
                                           uint32_t accumulate) {
   asm volatile(

@@ -1,0 +1,80 @@
+"""Timeline of one CTA of the tcgen05 attention kernels (clock64 stamps from lane 0 of every warp of CTA 0).
+
+`python profiles/attn_trace.py build` compiles plbert_b200/csrc/*.cu with -DPLB_ATTN_TRACE into
+profiles/_trace/libplbert_b200_trace.so (git-ignored; done in the CPU container, travels to the GPU box);
+`python profiles/attn_trace.py run [fwd]` launches the kernel at the BASELINE shape and prints the records of CTA 0.
+The product library never contains the instrumentation.
+"""
+import ctypes
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+OUT = os.path.join(ROOT, "profiles", "_trace")
+LIB = os.path.join(OUT, "libplbert_b200_trace.so")
+
+
+def build():
+    from plbert_b200.build import NVCC_FLAGS, _nvcc, _sources
+    os.makedirs(OUT, exist_ok=True)
+    cmd = [_nvcc(), *NVCC_FLAGS, "-DPLB_ATTN_TRACE", "-shared", "-o", LIB, *_sources(), "-lcuda"]
+    print(" ".join(cmd))
+    subprocess.run(cmd, check=True)
+
+
+def run(which="fwd"):
+    import torch
+    lib = ctypes.CDLL(LIB)
+    dev = torch.device("cuda:0")
+    B, L, nh = 192, 512, 12
+    H, T = nh * 64, B * L
+    P, I = ctypes.c_void_p, ctypes.c_int
+    qkv = torch.randn(T, 3 * H, device=dev).to(torch.bfloat16)
+    lens = torch.full((B,), L, device=dev, dtype=torch.int32)
+    qlens = torch.full((B,), int(os.environ.get("QLEN", L)), device=dev, dtype=torch.int32)  # QLEN=128: one softmax group only
+    seq_start = torch.arange(B, device=dev, dtype=torch.int32) * L
+    ctx = torch.empty(T, H, device=dev, dtype=torch.bfloat16)
+    dctx = torch.randn(T, H, device=dev).to(torch.bfloat16)
+    dqkv = torch.empty(T, 3 * H, device=dev, dtype=torch.bfloat16)
+    lse = torch.empty(nh, T, device=dev)
+    delta = torch.empty(nh, T, device=dev)
+    dbias = torch.zeros(3 * H, device=dev)
+    S = torch.cuda.current_stream().cuda_stream
+    lib.plb_attn_fwd_tc.argtypes = [P, I, P, P, P, I, I, I, I, I, P, I, P, P]
+    lib.plb_attn_bwd_tc.argtypes = [P, I, P, P, P, I, I, I, I, I, P, P, I, P, P, P, I, P, P]
+    lib.plb_attn_trace_dump.argtypes = [P, I]
+
+    def fwd():
+        rc = lib.plb_attn_fwd_tc(qkv.data_ptr(), 3 * H, seq_start.data_ptr(), qlens.data_ptr(), lens.data_ptr(), B, nh, 64, L, T,
+                                 ctx.data_ptr(), H, lse.data_ptr(), S)
+        assert rc == 0
+
+    def bwd():
+        rc = lib.plb_attn_bwd_tc(qkv.data_ptr(), 3 * H, seq_start.data_ptr(), lens.data_ptr(), lens.data_ptr(), B, nh, 64, L, T,
+                                 ctx.data_ptr(), dctx.data_ptr(), H, lse.data_ptr(), delta.data_ptr(), dqkv.data_ptr(), 3 * H,
+                                 dbias.data_ptr(), S)
+        assert rc == 0
+
+    cap = 3 * 16 * 512
+    buf = (ctypes.c_ulonglong * cap)()
+    lib.plb_attn_trace_dump(buf, cap)  # clears the table
+    fwd()
+    if which != "fwd":
+        bwd()
+    lib.plb_attn_trace_dump(buf, cap)  # warm-up records discarded
+    (fwd if which == "fwd" else bwd)()
+    n = lib.plb_attn_trace_dump(buf, cap)
+    kid = {"fwd": 0, "dq": 1, "dkv": 2}[which]
+    recs = sorted(((v >> 24), (v >> 16) & 15, (v >> 8) & 255, v & 255) for v in buf[:n] if v and ((v >> 20) & 15) == kid)
+    t0 = recs[0][0]
+    for clk, warp, code, idx in recs:
+        print(f"{clk - t0:8d} warp{warp:2d} code {code:3d} idx {idx}")
+
+
+if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "build":
+        build()
+    else:
+        run(sys.argv[2] if len(sys.argv) > 2 else "fwd")
