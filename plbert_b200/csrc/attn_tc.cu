@@ -60,6 +60,26 @@ enum { Q_FULL = 0, Q_EMPTY, S_FULL, S_FREE, P_READY, PV_DONE, O_FREE, BARS_PER_G
 
 __device__ __forceinline__ void group_bar_sync(int grp) { asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory"); }
 
+// Turn-taking on the exponential phase.  The two groups' warps of one TMEM lane quadrant share an SM sub-partition and
+// its MUFU; left alone the groups run in lock-step (both in their TMEM / barrier / store phase, then both fighting for
+// the MUFU, with their MMA bursts colliding too).  Each quadrant pair alternates through two 64-thread named barriers:
+// group 0 runs step c after group 1 finished step c-1, group 1 runs step c after group 0 finished step c.  ptxas
+// schedules freely around bar.sync / bar.arrive unless data flows through them, so acquire returns a volatile zero
+// from shared memory (add it to an input of the phase) and release stores a value derived from the phase's results.
+//   smem: one zero word at `turn_addr`, then one sink word per softmax warp.
+__device__ __forceinline__ float turn_acquire(int grp, int quad, uint32_t c, uint32_t steps1, uint32_t turn_addr) {
+  float z = 0.f;
+  if (grp == 0 ? (c >= 1 && c - 1 < steps1) : true)
+    asm volatile("bar.sync %1, 64;\n\tld.volatile.shared.f32 %0, [%2];" : "=f"(z) : "r"(3 + grp * 4 + quad), "r"(turn_addr) : "memory");
+  return z;
+}
+__device__ __forceinline__ void turn_release(int grp, int quad, uint32_t c, uint32_t steps0, uint32_t steps1, uint32_t turn_addr,
+                                             uint32_t result_bits) {
+  if (grp == 0 ? (c < steps1) : (c + 1 < steps0))
+    asm volatile("st.volatile.shared.b32 [%0], %1;\n\tbar.arrive %2, 64;" ::"r"(turn_addr + 4 + (grp * 4 + quad) * 4), "r"(result_bits),
+                 "r"(3 + (grp ^ 1) * 4 + quad) : "memory");
+}
+
 // Optional timeline instrumentation (profiles/attn_trace.py builds a separate library with -DPLB_ATTN_TRACE): lane 0 of
 // every warp of CTA 0 appends (clock, warp, code, index) records.  Compiled out of the product library.
 #ifdef PLB_ATTN_TRACE
@@ -284,16 +304,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const AttnTcParam
         float mneg = -m_used;
         PLB_TRACE(12, c);
         uint4 pk[KC / 8];
-        // The two groups' warps of one quadrant share an SM sub-partition and its MUFU.  Take turns on the exponential
-        // phase (64-thread named barriers, one pair per quadrant) so that one warp's exponentials overlap the other
-        // warp's TMEM / barrier / store phase instead of both phases running in lock-step.
-        // ptxas schedules freely around bar.sync / bar.arrive unless data flows through them: the exponent offset is
-        // re-read after the barrier (a volatile zero from shared memory) and the row sums are stored before the arrive.
-        if (grp == 0 ? (c >= 1 && c - 1 < steps1) : true) {
-          float z;
-          asm volatile("bar.sync %1, 64;\n\tld.volatile.shared.f32 %0, [%2];" : "=f"(z) : "r"(3 + grp * 4 + quad), "r"(turn_zero) : "memory");
-          mneg += z;
-        }
+        mneg += turn_acquire(grp, quad, c, steps1, turn_zero);
         PLB_TRACE(13, c);
 #pragma unroll
         for (int cc = 0; cc < KC / 8; ++cc) {  // sixteen 16-byte pieces = 128 keys (masked keys: exp2(-inf) = 0)
@@ -304,9 +315,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const AttnTcParam
           pk[cc].x = pack_bf16x2(e[0], e[1]); pk[cc].y = pack_bf16x2(e[2], e[3]);
           pk[cc].z = pack_bf16x2(e[4], e[5]); pk[cc].w = pack_bf16x2(e[6], e[7]);
         }
-        if (grp == 0 ? (c < steps1) : (c + 1 < steps0))
-          asm volatile("st.volatile.shared.f32 [%0], %1;\n\tbar.arrive %2, 64;" ::"r"(turn_zero + 4 + (warp - 4) * 4), "f"(ls[0] + ls[1]),
-                       "r"(3 + (grp ^ 1) * 4 + quad) : "memory");
+        turn_release(grp, quad, c, steps0, steps1, turn_zero, __float_as_uint(ls[0] + ls[1]));
         PLB_TRACE(14, c);
         if (c >= 1) mbar_wait(&gb[PV_DONE], (c - 1) & 1);  // the previous PV has finished reading the P buffer
         PLB_TRACE(15, c);
@@ -463,7 +472,8 @@ struct DqSmem {
   static constexpr int kDS = kDO + 2 * TILE16K;              // dS chunk [128 x 64] per group (also dQ staging)
   static constexpr int kBar = kDS + 2 * TILE16K;
   static constexpr int kNumBars = 2 * MAX_BOXES + 2 * 7;
-  static constexpr int kAlloc = kBar + kNumBars * 8 + 16;
+  static constexpr int kTurn = kBar + kNumBars * 8 + 16;     // 9 words for the exponential-phase turn-taking
+  static constexpr int kAlloc = kTurn + 48;
 };
 static_assert(DqSmem::kAlloc <= 232448, "dQ kernel exceeds the 227 KB shared-memory limit");
 enum { QDO_FULL = 0, QDO_EMPTY, SD_FULL, SD_FREE, DS_READY, DQ_DONE, DQ_FREE };
@@ -504,6 +514,7 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_c
       mbar_init(&gb[DQ_DONE], 1);
       mbar_init(&gb[DQ_FREE], 4);
     }
+    *reinterpret_cast<volatile float*>(smem + DqSmem::kTurn) = 0.f;
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc(tmem_ptr_smem, 512);
@@ -615,6 +626,8 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_c
     const uint32_t sDS = smem_u32(smem + DqSmem::kDS + grp * TILE16K);
     const uint32_t sDS_row = sDS + row * 128;
     uint32_t c = 0;
+    const uint32_t turn_addr = smem_u32(smem + DqSmem::kTurn);
+    const uint32_t steps0 = ((n_tiles + 1) >> 1) * n_chunks, steps1 = (n_tiles >> 1) * n_chunks;  // chunks per group
     for (int t = grp; t < n_tiles; t += 2) {
       const int qrow = t * QT + row;
       const size_t stat_idx = static_cast<size_t>(h) * p.total_rows + row_base + qrow;
@@ -635,20 +648,26 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_c
         __syncwarp();
         if (lane == 0) mbar_arrive(&gb[SD_FREE]);
         PLB_TRACE(11, c);
-        const int valid = nk - j * BC;  // keys >= kv_len are masked: P = 0
+        const int valid = nk - j * BC;  // keys >= kv_len are masked: P = exp2(-inf) = 0 (only the last chunk can have them)
+        if (valid < BC) {
+#pragma unroll
+          for (int i = 0; i < BC; ++i)
+            if (i >= valid) sv[i] = 0xff800000u;
+        }
         uint4 pk[BC / 8];
+        const float nlse = turn_acquire(grp, quad, c, steps1, turn_addr) - lse;
 #pragma unroll
         for (int cc = 0; cc < BC / 8; ++cc) {
           float e[8];
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
-            const float pr = ex2_fast(fmaf(__uint_as_float(sv[cc * 8 + i]), p.scale_log2, -lse));
-            const float ds = pr * (__uint_as_float(dv[cc * 8 + i]) - dlt);
-            e[i] = (cc * 8 + i < valid) ? ds : 0.f;
+            const float pr = ex2_fast(fmaf(__uint_as_float(sv[cc * 8 + i]), p.scale_log2, nlse));
+            e[i] = pr * (__uint_as_float(dv[cc * 8 + i]) - dlt);
           }
           pk[cc].x = pack_bf16x2(e[0], e[1]); pk[cc].y = pack_bf16x2(e[2], e[3]);
           pk[cc].z = pack_bf16x2(e[4], e[5]); pk[cc].w = pack_bf16x2(e[6], e[7]);
         }
+        turn_release(grp, quad, c, steps0, steps1, turn_addr, pk[1].y ^ pk[3].w ^ pk[5].x ^ pk[7].w);
         PLB_TRACE(14, c);
         if (c >= 1) mbar_wait(&gb[DQ_DONE], (c - 1) & 1);  // the dS buffer has been consumed by the previous dQ MMA
         PLB_TRACE(15, c);
@@ -715,7 +734,8 @@ struct DkvSmem {
   static constexpr int kStat = 2 * kGroup;                   // float [2 (lse, delta)][512]: statistics of every query row
   static constexpr int kBar = kStat + 2 * MAX_BOXES * 128 * 4;
   static constexpr int kBarsPerGroup = 11;
-  static constexpr int kAlloc = kBar + 2 * kBarsPerGroup * 8 + 16;
+  static constexpr int kTurn = kBar + 2 * kBarsPerGroup * 8 + 16;   // 9 words for the exponential-phase turn-taking
+  static constexpr int kAlloc = kTurn + 48;
 };
 static_assert(DkvSmem::kAlloc <= 232448, "dK/dV kernel exceeds the 227 KB shared-memory limit");
 enum { KV_FULL = 0, KV_EMPTY, RING_FULL0, RING_FULL1, RING_FREE0, RING_FREE1, ST_FULL, ST_FREE, PDS_READY, DKV_DONE, ACC_FREE };
@@ -751,6 +771,7 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv128, const __gr
       mbar_init(&gb[PDS_READY], 4);
       mbar_init(&gb[ACC_FREE], 4);
     }
+    *reinterpret_cast<volatile float*>(smem + DkvSmem::kTurn) = 0.f;
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc(tmem_ptr_smem, 512);
@@ -880,6 +901,8 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv128, const __gr
     }
 
     uint32_t c = 0;
+    const uint32_t turn_addr = smem_u32(smem + DkvSmem::kTurn);
+    const uint32_t steps0 = tiles_of[0] * n_qc, steps1 = tiles_of[1] * n_qc;  // chunks per group
     for (int t = grp; t < n_kt; t += 2) {
       const bool key_valid = (t * 128 + row) < nk;
       for (int j = 0; j < n_qc; ++j, ++c) {
@@ -896,9 +919,14 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv128, const __gr
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&gb[ST_FREE]);
+        if (!key_valid) {  // key rows >= kv_len (last tile only): P = exp2(-inf) = 0, hence dS = 0
+#pragma unroll
+          for (int i = 0; i < BC; ++i) sv[i] = 0xff800000u;
+        }
         PLB_TRACE(11, c);
         const uint32_t st = stat_addr + j * (BC * 4);
         uint4 pkp[BC / 8], pkd[BC / 8];
+        const float tz = turn_acquire(grp, quad, c, steps1, turn_addr);
 #pragma unroll
         for (int cc = 0; cc < BC / 8; ++cc) {
           const float4 l0 = lds128_ro(st + cc * 32), l1 = lds128_ro(st + cc * 32 + 16);
@@ -908,8 +936,7 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv128, const __gr
           float pr[8], ds[8];
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
-            const float e = ex2_fast(fmaf(__uint_as_float(sv[cc * 8 + i]), p.scale_log2, -ls[i]));
-            pr[i] = key_valid ? e : 0.f;
+            pr[i] = ex2_fast(fmaf(__uint_as_float(sv[cc * 8 + i]), p.scale_log2, tz - ls[i]));
             ds[i] = pr[i] * (__uint_as_float(dv[cc * 8 + i]) - dl[i]);
           }
           pkp[cc].x = pack_bf16x2(pr[0], pr[1]); pkp[cc].y = pack_bf16x2(pr[2], pr[3]);
@@ -917,6 +944,7 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv128, const __gr
           pkd[cc].x = pack_bf16x2(ds[0], ds[1]); pkd[cc].y = pack_bf16x2(ds[2], ds[3]);
           pkd[cc].z = pack_bf16x2(ds[4], ds[5]); pkd[cc].w = pack_bf16x2(ds[6], ds[7]);
         }
+        turn_release(grp, quad, c, steps0, steps1, turn_addr, pkd[1].y ^ pkd[3].w ^ pkd[5].x ^ pkd[7].w);
         PLB_TRACE(14, c);
         if (c >= 1) mbar_wait(&gb[DKV_DONE], (c - 1) & 1);  // P^T / dS^T buffers consumed by the previous dV / dK MMAs
         PLB_TRACE(15, c);
