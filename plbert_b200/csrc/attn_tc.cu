@@ -28,6 +28,9 @@ constexpr int KC = 128;                     // keys per chunk = one TMA box of K
 constexpr int MAX_BOXES = 4;                // K / V arrive as 128-row TMA boxes: sequences up to 512 keys
 constexpr int TILE16K = 128 * 64 * 2;       // one [128 x 64] bf16 swizzled tile
 constexpr int NUM_THREADS = 384;
+constexpr int BWD_THREADS = 640;            // backward kernels: control warpgroup + 2 groups x 8 warps (two column halves per row)
+constexpr int BWD_REGS_CONTROL = 56;        // setmaxnreg only moves registers inside the launch allocation (640 x 96 = 61440):
+constexpr int BWD_REGS_SOFTMAX = 104;       // 128*56 + 512*104 = 60416
 constexpr int REGS_CONTROL = 56;            // setmaxnreg budgets: TMA / MMA warpgroup ...
 constexpr int REGS_SOFTMAX = 224;           // ... and the two softmax warpgroups (128*56 + 256*224 <= 64 K registers)
 constexpr float RESCALE_THRESHOLD = 8.0f;   // log2 units
@@ -59,6 +62,7 @@ struct AttnTcParams {
 enum { Q_FULL = 0, Q_EMPTY, S_FULL, S_FREE, P_READY, PV_DONE, O_FREE, BARS_PER_GROUP };
 
 __device__ __forceinline__ void group_bar_sync(int grp) { asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory"); }
+__device__ __forceinline__ void group_bar_sync256(int grp) { asm volatile("bar.sync %0, 256;" ::"r"(1 + grp) : "memory"); }
 
 // Turn-taking on the exponential phase.  The two groups' warps of one TMEM lane quadrant share an SM sub-partition and
 // its MUFU; left alone the groups run in lock-step (both in their TMEM / barrier / store phase, then both fighting for
@@ -67,17 +71,20 @@ __device__ __forceinline__ void group_bar_sync(int grp) { asm volatile("bar.sync
 // schedules freely around bar.sync / bar.arrive unless data flows through them, so acquire returns a volatile zero
 // from shared memory (add it to an input of the phase) and release stores a value derived from the phase's results.
 //   smem: one zero word at `turn_addr`, then one sink word per softmax warp.
+//   kPair = threads of one quadrant pair (64: one warp per group and quadrant; 128: two warps — the column halves).
+template <int kPair = 64>
 __device__ __forceinline__ float turn_acquire(int grp, int quad, uint32_t c, uint32_t steps1, uint32_t turn_addr) {
   float z = 0.f;
   if (grp == 0 ? (c >= 1 && c - 1 < steps1) : true)
-    asm volatile("bar.sync %1, 64;\n\tld.volatile.shared.f32 %0, [%2];" : "=f"(z) : "r"(3 + grp * 4 + quad), "r"(turn_addr) : "memory");
+    asm volatile("bar.sync %1, %3;\n\tld.volatile.shared.f32 %0, [%2];" : "=f"(z) : "r"(3 + grp * 4 + quad), "r"(turn_addr), "n"(kPair) : "memory");
   return z;
 }
+template <int kPair = 64>
 __device__ __forceinline__ void turn_release(int grp, int quad, uint32_t c, uint32_t steps0, uint32_t steps1, uint32_t turn_addr,
                                              uint32_t result_bits) {
   if (grp == 0 ? (c < steps1) : (c + 1 < steps0))
-    asm volatile("st.volatile.shared.b32 [%0], %1;\n\tbar.arrive %2, 64;" ::"r"(turn_addr + 4 + (grp * 4 + quad) * 4), "r"(result_bits),
-                 "r"(3 + (grp ^ 1) * 4 + quad) : "memory");
+    asm volatile("st.volatile.shared.b32 [%0], %1;\n\tbar.arrive %2, %3;" ::"r"(turn_addr + 4 + ((threadIdx.x >> 5) - 4) * 4), "r"(result_bits),
+                 "r"(3 + (grp ^ 1) * 4 + quad), "n"(kPair) : "memory");
 }
 
 // Optional timeline instrumentation (profiles/attn_trace.py builds a separate library with -DPLB_ATTN_TRACE): lane 0 of
@@ -445,19 +452,20 @@ __global__ void __launch_bounds__(256) attn_delta_kernel(const __nv_bfloat16* __
 
 
 // Bias gradient of the QKV projection fused into the backward kernels: column sums of a staged [128 x 64] bf16 tile
-// (rows < n_rows only), added to dbias[col] with atomics.  One column PAIR per lane (32-bit loads), 32 rows per warp.
+// (rows < n_rows only), added to dbias[col] with atomics.  One column PAIR per lane (32-bit loads), kRowsPerWarp rows per warp.
 // The sums run over the ROUNDED values, i.e. exactly what the weight-gradient GEMM reads.
+template <int kRowsPerWarp = 32>
 __device__ __forceinline__ void tile_colsum_atomic(uint32_t tile_smem, int n_rows, int gtid, float* dbias_cols) {
   const int cp = gtid & 31, quarter = gtid >> 5;
   float a0 = 0.f, a1 = 0.f;
-  const int r_end = min(n_rows, quarter * 32 + 32);
-  for (int r = quarter * 32; r < r_end; ++r) {
+  const int r_end = min(n_rows, quarter * kRowsPerWarp + kRowsPerWarp);
+  for (int r = quarter * kRowsPerWarp; r < r_end; ++r) {
     uint32_t v;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(tile_smem + r * 128 + (((cp >> 2) ^ (r & 7)) << 4) + (cp & 3) * 4));
     a0 += bf16_lo(v);
     a1 += bf16_hi(v);
   }
-  if (n_rows > quarter * 32) {
+  if (n_rows > quarter * kRowsPerWarp) {
     atomicAdd(dbias_cols + 2 * cp, a0);
     atomicAdd(dbias_cols + 2 * cp + 1, a1);
   }
@@ -469,16 +477,16 @@ struct DqSmem {
   static constexpr int kV = kK + MAX_BOXES * TILE16K;        // V of the head, resident
   static constexpr int kQ = kV + MAX_BOXES * TILE16K;        // Q tile per group
   static constexpr int kDO = kQ + 2 * TILE16K;               // dO tile per group
-  static constexpr int kDS = kDO + 2 * TILE16K;              // dS chunk [128 x 64] per group (also dQ staging)
+  static constexpr int kDS = kDO + 2 * TILE16K;              // dQ staging [128 x 64] per group (dS itself lives in TMEM)
   static constexpr int kBar = kDS + 2 * TILE16K;
   static constexpr int kNumBars = 2 * MAX_BOXES + 2 * 7;
-  static constexpr int kTurn = kBar + kNumBars * 8 + 16;     // 9 words for the exponential-phase turn-taking
-  static constexpr int kAlloc = kTurn + 48;
+  static constexpr int kTurn = kBar + kNumBars * 8 + 16;     // 17 words for the exponential-phase turn-taking
+  static constexpr int kAlloc = kTurn + 80;
 };
 static_assert(DqSmem::kAlloc <= 232448, "dQ kernel exceeds the 227 KB shared-memory limit");
 enum { QDO_FULL = 0, QDO_EMPTY, SD_FULL, SD_FREE, DS_READY, DQ_DONE, DQ_FREE };
 
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+__global__ void __launch_bounds__(BWD_THREADS, 1)
 attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_dctx,
                       const AttnTcParams p, const float* __restrict__ lse2, const float* __restrict__ delta,
                       __nv_bfloat16* __restrict__ dqkv, int ld_dqkv, float* __restrict__ dbias) {
@@ -509,10 +517,10 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_c
       mbar_init(&gb[QDO_FULL], 1);
       mbar_init(&gb[QDO_EMPTY], 1);
       mbar_init(&gb[SD_FULL], 1);
-      mbar_init(&gb[SD_FREE], 4);
-      mbar_init(&gb[DS_READY], 4);
+      mbar_init(&gb[SD_FREE], 8);   // one arrive per softmax warp (8 per group)
+      mbar_init(&gb[DS_READY], 8);
       mbar_init(&gb[DQ_DONE], 1);
-      mbar_init(&gb[DQ_FREE], 4);
+      mbar_init(&gb[DQ_FREE], 8);
     }
     *reinterpret_cast<volatile float*>(smem + DqSmem::kTurn) = 0.f;
     fence_mbar_init();
@@ -522,10 +530,10 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_c
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
-  // TMEM columns per group g: S [g*192, +64), dP [g*192 + 64, +64), dQ [g*192 + 128, +64)
+  // TMEM columns per group g (stride 224): S [+0, +64), dP [+64, +64), dQ [+128, +64), dS as packed bf16 pairs [+192, +32)
 
   if (warp < 4) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_CONTROL));
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(BWD_REGS_CONTROL));
     if (warp == 0 && elect_one_sync()) {
       // ====================================== TMA producer ======================================
       auto load_tile = [&](int g, int t) {
@@ -561,11 +569,10 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_c
       constexpr uint32_t idesc_sd = umma_idesc_bf16(128, BC, 0, 0);  // S = Q K^T, dP = dO V^T : all K-major
       constexpr uint32_t idesc_dq = umma_idesc_bf16(128, D, 0, 1);   // dQ = dS K : A K-major, B MN-major
       uint64_t* gb = gbar + g * 7;
-      const uint32_t tg = tmem_base + g * 192;
+      const uint32_t tg = tmem_base + g * 224;
       // descriptor bases; the start-address field counts 16-byte units, so advancing is a plain add
       const uint64_t dQt = umma_smem_desc(smem_u32(smem + DqSmem::kQ + g * TILE16K), 16, 1024);
       const uint64_t dDO = umma_smem_desc(smem_u32(smem + DqSmem::kDO + g * TILE16K), 16, 1024);
-      const uint64_t dDS = umma_smem_desc(smem_u32(smem + DqSmem::kDS + g * TILE16K), 16, 1024);
       const uint64_t dKk = umma_smem_desc(smem_u32(smem + DqSmem::kK), 16, 1024);        // K-major view (S)
       const uint64_t dVk = umma_smem_desc(smem_u32(smem + DqSmem::kV), 16, 1024);        // K-major view (dP)
       const uint64_t dKm = umma_smem_desc(smem_u32(smem + DqSmem::kK), TILE16K, 1024);   // MN-major view (dQ)
@@ -602,7 +609,7 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_c
           tc_fence_after();
           const uint64_t kb = dKm + static_cast<uint64_t>(j * (CHUNK8K >> 4));
 #pragma unroll
-          for (int kk = 0; kk < BC / 16; ++kk) umma_bf16(tg + 128, dDS + 2 * kk, kb + 128 * kk, idesc_dq, (j > 0 || kk > 0));
+          for (int kk = 0; kk < BC / 16; ++kk) umma_bf16_tmem_a(tg + 128, tg + 192 + 8 * kk, kb + 128 * kk, idesc_dq, (j > 0 || kk > 0));
           umma_commit(&gb[DQ_DONE]);
           PLB_TRACE(2, c);
           if (has_next && !next_in_tile) {  // next tile: its Q / dO arrive only after this tile's last S / dP has run
@@ -614,14 +621,18 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_c
     }
     __syncwarp();
   } else {
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS_SOFTMAX));
-    // ====================================== dS producers + dQ epilogue (two groups) ======================================
-    const int grp = (warp - 4) >> 2;
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(BWD_REGS_SOFTMAX));
+    // ====================================== dS producers + dQ epilogue (two groups x eight warps) ======================================
+    // Two threads per query row (same TMEM lane quadrant, different warps), each owning 32 of the chunk's 64 key columns:
+    // there is no cross-column reduction in the backward pass, so the split is free and halves every per-chunk latency
+    // (TMEM load, exponentials, stores) on the group's critical path; four softmax warps per scheduler hide the rest.
+    const int grp = (warp - 4) >> 3;
+    const int half = ((warp - 4) >> 2) & 1;
     const int quad = warp & 3;
     const int row = quad * 32 + lane;
-    const int gtid = threadIdx.x - 128 - grp * 128;
+    const int gtid = threadIdx.x - 128 - grp * 256;  // 0..255 within the group
     const uint32_t lane_addr = static_cast<uint32_t>(quad * 32) << 16;
-    const uint32_t tg = tmem_base + lane_addr + grp * 192;
+    const uint32_t tg = tmem_base + lane_addr + grp * 224;
     uint64_t* gb = gbar + grp * 7;
     const uint32_t sDS = smem_u32(smem + DqSmem::kDS + grp * TILE16K);
     const uint32_t sDS_row = sDS + row * 128;
@@ -638,42 +649,41 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_c
         mbar_wait(&gb[SD_FULL], c & 1);
         tc_fence_after();
         PLB_TRACE(10, c);
-        uint32_t sv[BC], dv[BC];
-        tmem_ld_32x32(tg, *reinterpret_cast<uint32_t(*)[32]>(&sv[0]));
-        tmem_ld_32x32(tg + 32, *reinterpret_cast<uint32_t(*)[32]>(&sv[32]));
-        tmem_ld_32x32(tg + 64, *reinterpret_cast<uint32_t(*)[32]>(&dv[0]));
-        tmem_ld_32x32(tg + 96, *reinterpret_cast<uint32_t(*)[32]>(&dv[32]));
+        uint32_t sv[32], dv[32];
+        tmem_ld_32x32(tg + half * 32, sv);
+        tmem_ld_32x32(tg + 64 + half * 32, dv);
         tmem_ld_wait();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&gb[SD_FREE]);
         PLB_TRACE(11, c);
-        const int valid = nk - j * BC;  // keys >= kv_len are masked: P = exp2(-inf) = 0 (only the last chunk can have them)
-        if (valid < BC) {
+        const int valid = nk - j * BC - half * 32;  // keys >= kv_len are masked: P = exp2(-inf) = 0 (last chunk only)
+        if (valid < 32) {
 #pragma unroll
-          for (int i = 0; i < BC; ++i)
+          for (int i = 0; i < 32; ++i)
             if (i >= valid) sv[i] = 0xff800000u;
         }
-        uint4 pk[BC / 8];
-        const float nlse = turn_acquire(grp, quad, c, steps1, turn_addr) - lse;
+        uint32_t pk[16];
+        const float nlse = turn_acquire<128>(grp, quad, c, steps1, turn_addr) - lse;
 #pragma unroll
-        for (int cc = 0; cc < BC / 8; ++cc) {
+        for (int cc = 0; cc < 4; ++cc) {
           float e[8];
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             const float pr = ex2_fast(fmaf(__uint_as_float(sv[cc * 8 + i]), p.scale_log2, nlse));
             e[i] = pr * (__uint_as_float(dv[cc * 8 + i]) - dlt);
           }
-          pk[cc].x = pack_bf16x2(e[0], e[1]); pk[cc].y = pack_bf16x2(e[2], e[3]);
-          pk[cc].z = pack_bf16x2(e[4], e[5]); pk[cc].w = pack_bf16x2(e[6], e[7]);
+          pk[cc * 4 + 0] = pack_bf16x2(e[0], e[1]); pk[cc * 4 + 1] = pack_bf16x2(e[2], e[3]);
+          pk[cc * 4 + 2] = pack_bf16x2(e[4], e[5]); pk[cc * 4 + 3] = pack_bf16x2(e[6], e[7]);
         }
-        turn_release(grp, quad, c, steps0, steps1, turn_addr, pk[1].y ^ pk[3].w ^ pk[5].x ^ pk[7].w);
+        turn_release<128>(grp, quad, c, steps0, steps1, turn_addr, pk[1] ^ pk[7] ^ pk[8] ^ pk[15]);
         PLB_TRACE(14, c);
-        if (c >= 1) mbar_wait(&gb[DQ_DONE], (c - 1) & 1);  // the dS buffer has been consumed by the previous dQ MMA
+        if (c >= 1) mbar_wait(&gb[DQ_DONE], (c - 1) & 1);  // the previous dQ MMA has consumed the dS columns
         PLB_TRACE(15, c);
-#pragma unroll
-        for (int cc = 0; cc < BC / 8; ++cc) sts128(sDS_row + ((cc ^ (row & 7)) << 4), pk[cc]);
-        fence_proxy_async_smem();
+        // dS goes to tensor memory (the A operand of dQ += dS K is read from there): no shared-memory round trip
+        tc_fence_after();
+        tmem_st_32x16(tg + 192 + half * 16, pk);
+        tmem_st_wait();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&gb[DS_READY]);
@@ -683,10 +693,9 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_c
       mbar_wait(&gb[DQ_DONE], (c - 1) & 1);
       tc_fence_after();
       PLB_TRACE(20, t);
-#pragma unroll
-      for (int q = 0; q < 2; ++q) {
+      {
         uint32_t o[32];
-        tmem_ld_32x32(tg + 128 + q * 32, o);
+        tmem_ld_32x32(tg + 128 + half * 32, o);
         tmem_ld_wait();
 #pragma unroll
         for (int cc = 0; cc < 4; ++cc) {
@@ -695,24 +704,24 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_c
           v.y = pack_bf16x2(__uint_as_float(o[cc * 8 + 2]) * p.scale, __uint_as_float(o[cc * 8 + 3]) * p.scale);
           v.z = pack_bf16x2(__uint_as_float(o[cc * 8 + 4]) * p.scale, __uint_as_float(o[cc * 8 + 5]) * p.scale);
           v.w = pack_bf16x2(__uint_as_float(o[cc * 8 + 6]) * p.scale, __uint_as_float(o[cc * 8 + 7]) * p.scale);
-          sts128(sDS_row + (((q * 4 + cc) ^ (row & 7)) << 4), v);
+          sts128(sDS_row + (((half * 4 + cc) ^ (row & 7)) << 4), v);
         }
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&gb[DQ_FREE]);
-      group_bar_sync(grp);
+      group_bar_sync256(grp);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int idx = gtid + i * 128;
+      for (int i = 0; i < 4; ++i) {
+        const int idx = gtid + i * 256;
         const int r = idx >> 3, cc = idx & 7;
         if (t * QT + r < nq) {
           const uint4 v = lds128(sDS + r * 128 + ((cc ^ (r & 7)) << 4));
           *reinterpret_cast<uint4*>(dqkv + static_cast<size_t>(row_base + t * QT + r) * ld_dqkv + h * D + cc * 8) = v;
         }
       }
-      if (dbias != nullptr) tile_colsum_atomic(sDS, min(QT, nq - t * QT), gtid, dbias + h * D);
-      group_bar_sync(grp);
+      if (dbias != nullptr) tile_colsum_atomic<16>(sDS, min(QT, nq - t * QT), gtid, dbias + h * D);
+      group_bar_sync256(grp);
       PLB_TRACE(21, t);
     }
   }
@@ -1052,7 +1061,7 @@ extern "C" int plb_attn_bwd_tc(const void* qkv, int ld_qkv, const int32_t* seq_s
                                                ld_ctx, total_rows, heads, total_rows, delta);
   int rc = check_launch("plb_attn_bwd_tc(delta)");
   if (rc) return rc;
-  attn_bwd_dq_tc_kernel<<<B * heads, NUM_THREADS, DqSmem::kAlloc, stream>>>(tm_qkv128, tm_dctx128, p, lse2, delta,
+  attn_bwd_dq_tc_kernel<<<B * heads, BWD_THREADS, DqSmem::kAlloc, stream>>>(tm_qkv128, tm_dctx128, p, lse2, delta,
                                                                             static_cast<__nv_bfloat16*>(dqkv), ld_dqkv,
                                                                             dbias_qkv_accum);
   rc = check_launch("plb_attn_bwd_tc(dq)");
