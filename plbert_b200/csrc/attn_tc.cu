@@ -39,8 +39,8 @@ struct FwdSmem {
   static constexpr int kK = 0;
   static constexpr int kV = kK + MAX_BOXES * TILE16K;
   static constexpr int kQ = kV + MAX_BOXES * TILE16K;   // one Q tile per group
-  static constexpr int kP = kQ + 2 * TILE16K;           // one [128 x 128] P buffer (two 16 KB blocks) per group
-  static constexpr int kBar = kP + 2 * 2 * TILE16K;
+  static constexpr int kP = kQ + 2 * TILE16K;           // output staging [128 x 64] per group (P itself lives in TMEM)
+  static constexpr int kBar = kP + 2 * TILE16K;
   // k_full[4], v_full[4], then per group: q_full, q_empty, s_full, s_free, p_ready, pv_done, o_free
   static constexpr int kNumBars = 2 * MAX_BOXES + 2 * 7;
   static constexpr int kTurn = kBar + kNumBars * 8 + 16;  // 9 words for the exponential-phase turn-taking
@@ -147,7 +147,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const AttnTcParam
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
-  // TMEM columns: S of group g at [g*128, +128), O of group g at [256 + g*64, +64)
+  // TMEM columns per group g (stride 256): S [+0, +128), O [+128, +64), P as packed bf16 pairs [+192, +64)
 
   if (warp < 4) {
    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_CONTROL));
@@ -189,12 +189,11 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const AttnTcParam
     constexpr uint32_t idesc_s = umma_idesc_bf16(128, KC, 0, 0);   // S = Q K^T : A K-major, B K-major
     constexpr uint32_t idesc_o = umma_idesc_bf16(128, D, 0, 1);    // O = P V   : A K-major, B MN-major
     uint64_t* gb = gbar + g * BARS_PER_GROUP;
-    const uint32_t tmem_sg = tmem_base + g * KC, tmem_og = tmem_base + 256 + g * D;
+    const uint32_t tmem_sg = tmem_base + g * 256, tmem_og = tmem_sg + 128, tmem_pg = tmem_sg + 192;
     // descriptor bases; the start-address field counts 16-byte units, so advancing is a plain add
     const uint64_t dQ = umma_smem_desc(smem_u32(smem + FwdSmem::kQ + g * TILE16K), 16, 1024);
     const uint64_t dK = umma_smem_desc(smem_u32(smem + FwdSmem::kK), 16, 1024);
     const uint64_t dV = umma_smem_desc(smem_u32(smem + FwdSmem::kV), TILE16K, 1024);
-    const uint64_t dP = umma_smem_desc(smem_u32(smem + FwdSmem::kP + g * 2 * TILE16K), 16, 1024);
     const uint32_t total = my_tiles * n_chunks;
     auto issue_s = [&](int k, int j, uint32_t cn) {  // S_j = Q K_j^T of the group's k-th tile
       if (j == 0) mbar_wait(&gb[Q_FULL], k & 1);
@@ -225,8 +224,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const AttnTcParam
         const uint64_t vb = dV + static_cast<uint64_t>(j * (TILE16K >> 4));
 #pragma unroll
         for (int kk = 0; kk < KC / 16; ++kk)
-          umma_bf16(tmem_og, dP + static_cast<uint64_t>((kk >> 2) * (TILE16K >> 4) + (kk & 3) * 2), vb + 128 * kk, idesc_o,
-                    (j > 0 || kk > 0));
+          umma_bf16_tmem_a(tmem_og, tmem_pg + 8 * kk, vb + 128 * kk, idesc_o, (j > 0 || kk > 0));
         umma_commit(&gb[PV_DONE]);
         PLB_TRACE(2, c);
         if (has_next && !next_in_tile) {  // next tile: its Q arrives only after this tile's last S MMA has run
@@ -244,10 +242,10 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const AttnTcParam
     const int row = quad * 32 + lane;
     const int gtid = threadIdx.x - 128 - grp * 128;  // 0..127 within the group
     const uint32_t lane_addr = static_cast<uint32_t>(quad * 32) << 16;
-    const uint32_t tmem_s = tmem_base + lane_addr + grp * KC;
-    const uint32_t tmem_o = tmem_base + lane_addr + 256 + grp * D;
+    const uint32_t tmem_s = tmem_base + lane_addr + grp * 256;
+    const uint32_t tmem_o = tmem_s + 128, tmem_p = tmem_s + 192;
     uint64_t* gb = gbar + grp * BARS_PER_GROUP;
-    const uint32_t sPg = smem_u32(smem + FwdSmem::kP + grp * 2 * TILE16K);
+    const uint32_t sPg = smem_u32(smem + FwdSmem::kP + grp * TILE16K);  // output staging of the group
     const uint32_t sP_row = sPg + row * 128;
     uint32_t c = 0;  // chunk counter of this group (phase of s_full / s_free / p_ready / pv_done)
     const uint32_t turn_zero = smem_u32(smem + FwdSmem::kTurn);  // one zero word, then one sink word per softmax warp
@@ -310,7 +308,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const AttnTcParam
         float ls[2] = {0.f, 0.f};
         float mneg = -m_used;
         PLB_TRACE(12, c);
-        uint4 pk[KC / 8];
+        uint32_t pk[KC / 2];
         mneg += turn_acquire(grp, quad, c, steps1, turn_zero);
         PLB_TRACE(13, c);
 #pragma unroll
@@ -319,17 +317,19 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const AttnTcParam
 #pragma unroll
           for (int i = 0; i < 8; ++i) e[i] = ex2_fast(fmaf(__uint_as_float(sv[cc * 8 + i]), p.scale_log2, mneg));
           ls[cc & 1] += ((e[0] + e[1]) + (e[2] + e[3])) + ((e[4] + e[5]) + (e[6] + e[7]));
-          pk[cc].x = pack_bf16x2(e[0], e[1]); pk[cc].y = pack_bf16x2(e[2], e[3]);
-          pk[cc].z = pack_bf16x2(e[4], e[5]); pk[cc].w = pack_bf16x2(e[6], e[7]);
+          pk[cc * 4 + 0] = pack_bf16x2(e[0], e[1]); pk[cc * 4 + 1] = pack_bf16x2(e[2], e[3]);
+          pk[cc * 4 + 2] = pack_bf16x2(e[4], e[5]); pk[cc * 4 + 3] = pack_bf16x2(e[6], e[7]);
         }
         turn_release(grp, quad, c, steps0, steps1, turn_zero, __float_as_uint(ls[0] + ls[1]));
         PLB_TRACE(14, c);
-        if (c >= 1) mbar_wait(&gb[PV_DONE], (c - 1) & 1);  // the previous PV has finished reading the P buffer
+        if (c >= 1) mbar_wait(&gb[PV_DONE], (c - 1) & 1);  // the previous PV has finished reading the P columns
         PLB_TRACE(15, c);
-#pragma unroll
-        for (int cc = 0; cc < KC / 8; ++cc) sts128(sP_row + (cc >> 3) * TILE16K + (((cc & 7) ^ (row & 7)) << 4), pk[cc]);
+        // P goes to tensor memory (the A operand of O += P V is read from there): no shared-memory round trip
+        tc_fence_after();
+        tmem_st_32x32(tmem_p, *reinterpret_cast<uint32_t(*)[32]>(&pk[0]));
+        tmem_st_32x32(tmem_p + 32, *reinterpret_cast<uint32_t(*)[32]>(&pk[32]));
         l_run += ls[0] + ls[1];
-        fence_proxy_async_smem();
+        tmem_st_wait();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&gb[P_READY]);

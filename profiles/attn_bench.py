@@ -48,5 +48,23 @@ def main():
                             ptr(lse), ptr(delta), ptr(dqkv), 3 * H, *extra, S), 2.5 * fwd_flops, n)
 
 
+    # per-kernel durations of one backward call (CUPTI)
+    from torch.profiler import ProfilerActivity, profile
+    n = "plb_attn_bwd_tc"
+    with profile(activities=[ProfilerActivity.CUDA]) as prof:
+        for _ in range(5):
+            call("plb_attn_fwd_tc", ptr(qkv), 3 * H, ptr(seq_start), ptr(lens), ptr(lens), B, nh, 64, L, T, ptr(ctx), H, ptr(lse), S)
+            call(n, ptr(qkv), 3 * H, ptr(seq_start), ptr(lens), ptr(lens), B, nh, 64, L, T, ptr(ctx), ptr(dctx), H,
+                 ptr(lse), ptr(delta), ptr(dqkv), 3 * H, ptr(dbias), S)
+        torch.cuda.synchronize()
+    import collections
+    tot = collections.Counter()
+    for e in prof.events():
+        if e.device_type == torch.autograd.DeviceType.CUDA:
+            tot[e.name.split("(")[0][-40:]] += (e.time_range.end - e.time_range.start) / 5
+    for k, v in tot.most_common():
+        print(f"  {v:9.1f} us  {k}")
+
+
 if __name__ == "__main__":
     main()
