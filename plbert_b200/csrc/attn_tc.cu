@@ -743,13 +743,13 @@ struct DkvSmem {
   static constexpr int kStat = 2 * kGroup;                   // float [2 (lse, delta)][512]: statistics of every query row
   static constexpr int kBar = kStat + 2 * MAX_BOXES * 128 * 4;
   static constexpr int kBarsPerGroup = 11;
-  static constexpr int kTurn = kBar + 2 * kBarsPerGroup * 8 + 16;   // 9 words for the exponential-phase turn-taking
-  static constexpr int kAlloc = kTurn + 48;
+  static constexpr int kTurn = kBar + 2 * kBarsPerGroup * 8 + 16;   // 17 words for the exponential-phase turn-taking
+  static constexpr int kAlloc = kTurn + 80;
 };
 static_assert(DkvSmem::kAlloc <= 232448, "dK/dV kernel exceeds the 227 KB shared-memory limit");
 enum { KV_FULL = 0, KV_EMPTY, RING_FULL0, RING_FULL1, RING_FREE0, RING_FREE1, ST_FULL, ST_FREE, PDS_READY, DKV_DONE, ACC_FREE };
 
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+__global__ void __launch_bounds__(BWD_THREADS, 1)
 attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv128, const __grid_constant__ CUtensorMap tm_qkv64,
                        const __grid_constant__ CUtensorMap tm_dctx64, const AttnTcParams p,
                        const float* __restrict__ lse2, const float* __restrict__ delta,
@@ -776,9 +776,9 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv128, const __gr
     for (int g = 0; g < 2; ++g) {
       uint64_t* gb = gbar + g * DkvSmem::kBarsPerGroup;
       for (int i = 0; i < DkvSmem::kBarsPerGroup; ++i) mbar_init(&gb[i], 1);
-      mbar_init(&gb[ST_FREE], 4);
-      mbar_init(&gb[PDS_READY], 4);
-      mbar_init(&gb[ACC_FREE], 4);
+      mbar_init(&gb[ST_FREE], 8);   // one arrive per softmax warp (8 per group)
+      mbar_init(&gb[PDS_READY], 8);
+      mbar_init(&gb[ACC_FREE], 8);
     }
     *reinterpret_cast<volatile float*>(smem + DkvSmem::kTurn) = 0.f;
     fence_mbar_init();
@@ -789,7 +789,7 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv128, const __gr
     // the statistics of all query COLUMNS (rows beyond the sequence: lse = +inf -> P = 0)
     float* stat_all = reinterpret_cast<float*>(smem + DkvSmem::kStat);
     const size_t base = static_cast<size_t>(h) * p.total_rows + row_base;
-    for (int q = threadIdx.x; q < MAX_BOXES * 128; q += NUM_THREADS) {
+    for (int q = threadIdx.x; q < MAX_BOXES * 128; q += BWD_THREADS) {
       stat_all[q] = q < nq ? lse2[base + q] : INFINITY;
       stat_all[MAX_BOXES * 128 + q] = q < nq ? delta[base + q] : 0.f;
     }
@@ -801,7 +801,7 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv128, const __gr
   // TMEM columns per group g: S^T [g*256, +64), dP^T [+64, +64), dK [+128, +64), dV [+192, +64)
 
   if (warp < 4) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_CONTROL));
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(BWD_REGS_CONTROL));
     // warps 0 / 3: TMA producers of group 0 / 1; warps 1 / 2: MMA issuers of group 0 / 1.  Every role blocks on the one
     // barrier that is due next (the order of a group's operations is fixed), so there are no polling loops.
     const int g = (warp == 0 || warp == 1) ? 0 : 1;
@@ -882,12 +882,14 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv128, const __gr
     }
     __syncwarp();
   } else {
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS_SOFTMAX));
-    // ====================================== P^T / dS^T producers + dK/dV epilogue (two groups) ======================================
-    const int grp = (warp - 4) >> 2;
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(BWD_REGS_SOFTMAX));
+    // ====================================== P^T / dS^T producers + dK/dV epilogue (two groups x eight warps) ======================================
+    // Two threads per key row (same TMEM lane quadrant, different warps), each owning 32 of the chunk's 64 query columns.
+    const int grp = (warp - 4) >> 3;
+    const int half = ((warp - 4) >> 2) & 1;
     const int quad = warp & 3;
     const int row = quad * 32 + lane;
-    const int gtid = threadIdx.x - 128 - grp * 128;
+    const int gtid = threadIdx.x - 128 - grp * 256;  // 0..255 within the group
     const uint32_t lane_addr = static_cast<uint32_t>(quad * 32) << 16;
     const uint32_t tg = tmem_base + lane_addr + grp * 256;
     uint64_t* gb = gbar + grp * DkvSmem::kBarsPerGroup;
@@ -898,8 +900,8 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv128, const __gr
     // key rows in [128 * n_kt, nq): padded keys inside the allocated sequence -> their gradients are exactly zero
     for (int t = n_kt + grp; t * 128 < nq; t += 2) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int idx = gtid + i * 128;
+      for (int i = 0; i < 4; ++i) {
+        const int idx = gtid + i * 256;
         const int r = t * 128 + (idx >> 3), cc = idx & 7;
         if (r < nq) {
           __nv_bfloat16* dst = dqkv + static_cast<size_t>(row_base + r) * ld_dqkv + h * D + cc * 8;
@@ -919,25 +921,23 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv128, const __gr
         mbar_wait(&gb[ST_FULL], c & 1);
         tc_fence_after();
         PLB_TRACE(10, c);
-        uint32_t sv[BC], dv[BC];
-        tmem_ld_32x32(tg, *reinterpret_cast<uint32_t(*)[32]>(&sv[0]));
-        tmem_ld_32x32(tg + 32, *reinterpret_cast<uint32_t(*)[32]>(&sv[32]));
-        tmem_ld_32x32(tg + 64, *reinterpret_cast<uint32_t(*)[32]>(&dv[0]));
-        tmem_ld_32x32(tg + 96, *reinterpret_cast<uint32_t(*)[32]>(&dv[32]));
+        uint32_t sv[32], dv[32];
+        tmem_ld_32x32(tg + half * 32, sv);
+        tmem_ld_32x32(tg + 64 + half * 32, dv);
         tmem_ld_wait();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&gb[ST_FREE]);
         if (!key_valid) {  // key rows >= kv_len (last tile only): P = exp2(-inf) = 0, hence dS = 0
 #pragma unroll
-          for (int i = 0; i < BC; ++i) sv[i] = 0xff800000u;
+          for (int i = 0; i < 32; ++i) sv[i] = 0xff800000u;
         }
         PLB_TRACE(11, c);
-        const uint32_t st = stat_addr + j * (BC * 4);
-        uint4 pkp[BC / 8], pkd[BC / 8];
-        const float tz = turn_acquire(grp, quad, c, steps1, turn_addr);
+        const uint32_t st = stat_addr + (j * BC + half * 32) * 4;
+        uint4 pkp[4], pkd[4];
+        const float tz = turn_acquire<128>(grp, quad, c, steps1, turn_addr);
 #pragma unroll
-        for (int cc = 0; cc < BC / 8; ++cc) {
+        for (int cc = 0; cc < 4; ++cc) {
           const float4 l0 = lds128_ro(st + cc * 32), l1 = lds128_ro(st + cc * 32 + 16);
           const float4 d0 = lds128_ro(st + MAX_BOXES * 512 + cc * 32), d1 = lds128_ro(st + MAX_BOXES * 512 + cc * 32 + 16);
           const float ls[8] = {l0.x, l0.y, l0.z, l0.w, l1.x, l1.y, l1.z, l1.w};
@@ -953,14 +953,14 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv128, const __gr
           pkd[cc].x = pack_bf16x2(ds[0], ds[1]); pkd[cc].y = pack_bf16x2(ds[2], ds[3]);
           pkd[cc].z = pack_bf16x2(ds[4], ds[5]); pkd[cc].w = pack_bf16x2(ds[6], ds[7]);
         }
-        turn_release(grp, quad, c, steps0, steps1, turn_addr, pkd[1].y ^ pkd[3].w ^ pkd[5].x ^ pkd[7].w);
+        turn_release<128>(grp, quad, c, steps0, steps1, turn_addr, pkd[0].y ^ pkd[1].w ^ pkd[2].x ^ pkd[3].w);
         PLB_TRACE(14, c);
         if (c >= 1) mbar_wait(&gb[DKV_DONE], (c - 1) & 1);  // P^T / dS^T buffers consumed by the previous dV / dK MMAs
         PLB_TRACE(15, c);
 #pragma unroll
-        for (int cc = 0; cc < BC / 8; ++cc) {
-          sts128(sPT_row + ((cc ^ (row & 7)) << 4), pkp[cc]);
-          sts128(sDST_row + ((cc ^ (row & 7)) << 4), pkd[cc]);
+        for (int cc = 0; cc < 4; ++cc) {
+          sts128(sPT_row + (((half * 4 + cc) ^ (row & 7)) << 4), pkp[cc]);
+          sts128(sDST_row + (((half * 4 + cc) ^ (row & 7)) << 4), pkd[cc]);
         }
         fence_proxy_async_smem();
         tc_fence_before();
@@ -976,29 +976,26 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv128, const __gr
       for (int which = 0; which < 2; ++which) {  // 0: dK (cols 128..191), 1: dV (cols 192..255)
         const float mul = which == 0 ? p.scale : 1.f;
         const uint32_t dst_row = which == 0 ? sPT_row : sDST_row;
+        uint32_t o[32];
+        tmem_ld_32x32(tg + 128 + which * 64 + half * 32, o);
+        tmem_ld_wait();
 #pragma unroll
-        for (int q = 0; q < 2; ++q) {
-          uint32_t o[32];
-          tmem_ld_32x32(tg + 128 + which * 64 + q * 32, o);
-          tmem_ld_wait();
-#pragma unroll
-          for (int cc = 0; cc < 4; ++cc) {
-            uint4 v;
-            v.x = pack_bf16x2(__uint_as_float(o[cc * 8 + 0]) * mul, __uint_as_float(o[cc * 8 + 1]) * mul);
-            v.y = pack_bf16x2(__uint_as_float(o[cc * 8 + 2]) * mul, __uint_as_float(o[cc * 8 + 3]) * mul);
-            v.z = pack_bf16x2(__uint_as_float(o[cc * 8 + 4]) * mul, __uint_as_float(o[cc * 8 + 5]) * mul);
-            v.w = pack_bf16x2(__uint_as_float(o[cc * 8 + 6]) * mul, __uint_as_float(o[cc * 8 + 7]) * mul);
-            sts128(dst_row + (((q * 4 + cc) ^ (row & 7)) << 4), v);
-          }
+        for (int cc = 0; cc < 4; ++cc) {
+          uint4 v;
+          v.x = pack_bf16x2(__uint_as_float(o[cc * 8 + 0]) * mul, __uint_as_float(o[cc * 8 + 1]) * mul);
+          v.y = pack_bf16x2(__uint_as_float(o[cc * 8 + 2]) * mul, __uint_as_float(o[cc * 8 + 3]) * mul);
+          v.z = pack_bf16x2(__uint_as_float(o[cc * 8 + 4]) * mul, __uint_as_float(o[cc * 8 + 5]) * mul);
+          v.w = pack_bf16x2(__uint_as_float(o[cc * 8 + 6]) * mul, __uint_as_float(o[cc * 8 + 7]) * mul);
+          sts128(dst_row + (((half * 4 + cc) ^ (row & 7)) << 4), v);
         }
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&gb[ACC_FREE]);
-      group_bar_sync(grp);
+      group_bar_sync256(grp);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int idx = gtid + i * 128;
+      for (int i = 0; i < 4; ++i) {
+        const int idx = gtid + i * 256;
         const int r = idx >> 3, cc = idx & 7;
         const int key = t * 128 + r;
         if (key < nq) {  // rows in [nk, nq) were masked above: their accumulators are exact zeros
@@ -1009,10 +1006,10 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv128, const __gr
       }
       if (dbias != nullptr) {
         // (the key-bias gradient is mathematically zero; it is accumulated anyway so the tensor holds what autograd would)
-        tile_colsum_atomic(gs + DkvSmem::kPT, min(128, nk - t * 128), gtid, dbias + H + h * D);
-        tile_colsum_atomic(gs + DkvSmem::kDST, min(128, nk - t * 128), gtid, dbias + 2 * H + h * D);
+        tile_colsum_atomic<16>(gs + DkvSmem::kPT, min(128, nk - t * 128), gtid, dbias + H + h * D);
+        tile_colsum_atomic<16>(gs + DkvSmem::kDST, min(128, nk - t * 128), gtid, dbias + 2 * H + h * D);
       }
-      group_bar_sync(grp);
+      group_bar_sync256(grp);
       PLB_TRACE(21, t);
     }
   }
@@ -1066,7 +1063,7 @@ extern "C" int plb_attn_bwd_tc(const void* qkv, int ld_qkv, const int32_t* seq_s
                                                                             dbias_qkv_accum);
   rc = check_launch("plb_attn_bwd_tc(dq)");
   if (rc) return rc;
-  attn_bwd_dkv_tc_kernel<<<B * heads, NUM_THREADS, DkvSmem::kAlloc, stream>>>(tm_qkv128, tm_qkv64, tm_dctx64, p, lse2, delta,
+  attn_bwd_dkv_tc_kernel<<<B * heads, BWD_THREADS, DkvSmem::kAlloc, stream>>>(tm_qkv128, tm_qkv64, tm_dctx64, p, lse2, delta,
                                                                               static_cast<__nv_bfloat16*>(dqkv), ld_dqkv,
                                                                               dbias_qkv_accum);
   return check_launch("plb_attn_bwd_tc(dkv)");

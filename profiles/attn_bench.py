@@ -1,5 +1,6 @@
 """Times the attention kernels at the BASELINE shape (192 sequences x 512 rows x 12 heads x 64) through the C ABI."""
 import math
+import re
 import os
 import sys
 
@@ -61,7 +62,8 @@ def main():
     tot = collections.Counter()
     for e in prof.events():
         if e.device_type == torch.autograd.DeviceType.CUDA:
-            tot[e.name.split("(")[0][-40:]] += (e.time_range.end - e.time_range.start) / 5
+            m = re.search(r"attn_\w+", e.name)
+            tot[m.group(0) if m else e.name[:40]] += (e.time_range.end - e.time_range.start) / 5
     for k, v in tot.most_common():
         print(f"  {v:9.1f} us  {k}")
 
