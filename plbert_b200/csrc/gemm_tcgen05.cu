@@ -124,7 +124,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CU
 
   if (warp == 0) {
     // =========================== TMA producer ===========================
-    if (lane == 0) {
+    if (elect_one_sync()) {  // elect.sync (not lane == 0): ptxas then emits the TMA / MMA instructions without waterfall loops
       int stage = 0;
       uint32_t phase = 0;
       for (int u = unit0; u < p.num_units; u += unit_stride) {
@@ -176,7 +176,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CU
     __syncwarp();
   } else if (warp == 1) {
     // =========================== MMA issuer ===========================
-    if (lane == 0 && rank == 0) {
+    if (rank == 0 && elect_one_sync()) {
       constexpr uint32_t idesc = umma_idesc_bf16(BM * kCta, BN, kAMn ? 1 : 0, kBMn ? 1 : 0);
       int stage = 0;
       uint32_t phase = 0;
@@ -193,12 +193,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CU
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
           const uint32_t sb = sa + A_TILE_BYTES;
+          // descriptor of the stage once; the start-address field counts 16-byte units, so a K step is a plain add
+          const uint64_t da0 = kAMn ? umma_smem_desc(sa, MN_BOX_BYTES, 1024) : umma_smem_desc(sa, 16, 1024);
+          const uint64_t db0 = kBMn ? umma_smem_desc(sb, MN_BOX_BYTES, 1024) : umma_smem_desc(sb, 16, 1024);
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k) {
-            const uint64_t da = kAMn ? umma_smem_desc(sa + k * (UMMA_K * 128), MN_BOX_BYTES, 1024)
-                                     : umma_smem_desc(sa + k * (UMMA_K * 2), 16, 1024);
-            const uint64_t db = kBMn ? umma_smem_desc(sb + k * (UMMA_K * 128), MN_BOX_BYTES, 1024)
-                                     : umma_smem_desc(sb + k * (UMMA_K * 2), 16, 1024);
+            const uint64_t da = da0 + static_cast<uint64_t>(k * ((kAMn ? UMMA_K * 128 : UMMA_K * 2) >> 4));
+            const uint64_t db = db0 + static_cast<uint64_t>(k * ((kBMn ? UMMA_K * 128 : UMMA_K * 2) >> 4));
             if (kCta == 2) umma_bf16_2cta(tmem_d, da, db, idesc, (kb > k_begin || k > 0) ? 1u : 0u);
             else umma_bf16(tmem_d, da, db, idesc, (kb > k_begin || k > 0) ? 1u : 0u);
           }
