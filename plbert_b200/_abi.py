@@ -10,7 +10,8 @@ import os
 from ctypes import c_char_p, c_double, c_float, c_int, c_long, c_void_p
 
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(PKG_DIR, "libplbert_b200.so")
+# PLBERT_B200_LIB points at an alternative build of the same ABI (profiles/ uses it for instrumented / experimental variants)
+LIB_PATH = os.environ.get("PLBERT_B200_LIB") or os.path.join(PKG_DIR, "libplbert_b200.so")
 
 GEMM_FWD, GEMM_DGRAD, GEMM_WGRAD = 0, 1, 2
 EPI_NONE, EPI_RESIDUAL, EPI_GELU, EPI_GELU_BWD = 0, 1, 2, 3

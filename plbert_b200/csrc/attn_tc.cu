@@ -19,6 +19,8 @@
 // rescaled in TMEM by the row's own thread (tcgen05.ld/st).
 #include "common.cuh"
 
+#include <cstdlib>
+
 namespace plb {
 namespace {
 
@@ -72,9 +74,13 @@ __device__ __forceinline__ void group_bar_sync256(int grp) { asm volatile("bar.s
 // from shared memory (add it to an input of the phase) and release stores a value derived from the phase's results.
 //   smem: one zero word at `turn_addr`, then one sink word per softmax warp.
 //   kPair = threads of one quadrant pair (64: one warp per group and quadrant; 128: two warps — the column halves).
+#ifndef PLB_TURN_BWD
+#define PLB_TURN_BWD 1
+#endif
 template <int kPair = 64>
 __device__ __forceinline__ float turn_acquire(int grp, int quad, uint32_t c, uint32_t steps1, uint32_t turn_addr) {
   float z = 0.f;
+  if (kPair == 128 && !PLB_TURN_BWD) return z;
   if (grp == 0 ? (c >= 1 && c - 1 < steps1) : true)
     asm volatile("bar.sync %1, %3;\n\tld.volatile.shared.f32 %0, [%2];" : "=f"(z) : "r"(3 + grp * 4 + quad), "r"(turn_addr), "n"(kPair) : "memory");
   return z;
@@ -82,6 +88,7 @@ __device__ __forceinline__ float turn_acquire(int grp, int quad, uint32_t c, uin
 template <int kPair = 64>
 __device__ __forceinline__ void turn_release(int grp, int quad, uint32_t c, uint32_t steps0, uint32_t steps1, uint32_t turn_addr,
                                              uint32_t result_bits) {
+  if (kPair == 128 && !PLB_TURN_BWD) return;
   if (grp == 0 ? (c < steps1) : (c + 1 < steps0))
     asm volatile("st.volatile.shared.b32 [%0], %1;\n\tbar.arrive %2, %3;" ::"r"(turn_addr + 4 + ((threadIdx.x >> 5) - 4) * 4), "r"(result_bits),
                  "r"(3 + (grp ^ 1) * 4 + quad), "n"(kPair) : "memory");
@@ -1019,6 +1026,305 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv128, const __gr
   if (warp == 1) tmem_dealloc(tmem_base, 512);
 }
 
+
+// ------------------------------------------------------------------------------------------------ dK/dV kernel, second generation
+// One key tile at a time per CTA, shared by BOTH softmax groups: the 64-query chunks of the tile alternate between the
+// groups (chunk C -> group C & 1, TMEM slot C & 1), and every chunk's dV += P^T dO / dK += dS^T Q accumulates into the
+// single dK / dV accumulator pair.  That frees enough tensor memory to keep P^T and dS^T there as packed bf16 — the A
+// operand of the accumulating MMAs is read from TMEM, so the softmax threads never store to shared memory in the loop
+// (no fence.proxy.async, no swizzled stores) and those MMAs only fetch their 2 KB B operand.  Q and dO of the whole
+// sequence stay resident (loaded once instead of once per key tile), K_t / V_t are double-buffered and the buffer of a
+// finished tile doubles as the staging area of its epilogue.
+//   TMEM columns: slot s: S^T [s*192, +64), dP^T [+64, +64), P^T bf16 pairs [+128, +32), dS^T bf16 pairs [+160, +32);
+//                 dK [384, +64), dV [448, +64).
+//   Warps: 0 TMA, 1 MMA issuer of the S^T / dP^T stream, 2 MMA issuer of the accumulating stream, 3 idle,
+//          4..11 softmax group 0, 12..19 softmax group 1 (two threads per key row, 32 query columns each).
+struct Dkv2Smem {
+  static constexpr int kQ = 0;                                // Q of the sequence: 8 chunks of [64 x 64] (8 KB each)
+  static constexpr int kDO = kQ + MAX_BOXES * TILE16K;        // dO of the sequence, same layout
+  static constexpr int kKV = kDO + MAX_BOXES * TILE16K;       // 2 buffers x (K_t 16 KB | V_t 16 KB); epilogue staging of tile t
+  static constexpr int kStat = kKV + 2 * 2 * TILE16K;         // float [2 (lse, delta)][512]
+  static constexpr int kBar = kStat + 2 * MAX_BOXES * 128 * 4;
+  // qdo_full[8], kv_full[2], kv_free[2], st_full[2], st_free[2], pds_ready[2], pds_free[2], acc_full, acc_free
+  static constexpr int kNumBars = 2 * MAX_BOXES + 2 + 2 + 2 + 2 + 2 + 2 + 2;
+  static constexpr int kTurn = kBar + kNumBars * 8 + 16;      // 17 words for the exponential-phase turn-taking
+  static constexpr int kAlloc = kTurn + 80;
+};
+static_assert(Dkv2Smem::kAlloc <= 232448, "dK/dV kernel exceeds the 227 KB shared-memory limit");
+
+__global__ void __launch_bounds__(BWD_THREADS, 1)
+attn_bwd_dkv2_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv128, const __grid_constant__ CUtensorMap tm_qkv64,
+                        const __grid_constant__ CUtensorMap tm_dctx64, const AttnTcParams p,
+                        const float* __restrict__ lse2, const float* __restrict__ delta,
+                        __nv_bfloat16* __restrict__ dqkv, int ld_dqkv, float* __restrict__ dbias) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if (smem_u32(smem) & 1023u) __trap();
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Dkv2Smem::kBar);
+  constexpr int NQC = 2 * MAX_BOXES;  // at most 8 query chunks
+  uint64_t* qdo_full = bars;                 // [8]
+  uint64_t* kv_full = bars + NQC;            // [2]
+  uint64_t* kv_free = kv_full + 2;           // [2]
+  uint64_t* st_full = kv_free + 2;           // [2]
+  uint64_t* st_free = st_full + 2;           // [2]
+  uint64_t* pds_ready = st_free + 2;         // [2]
+  uint64_t* pds_free = pds_ready + 2;        // [2]
+  uint64_t* acc_full = pds_free + 2;
+  uint64_t* acc_free = acc_full + 1;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + Dkv2Smem::kNumBars);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  PLB_TRACE_INIT(2);
+  PLB_TRACE(0, 0);
+  const int b = blockIdx.x / p.heads, h = blockIdx.x % p.heads;
+  const int row_base = p.seq_start[b], nq = p.q_len[b], nk = p.kv_len[b];
+  const int H = p.heads * D;
+  const int n_qc = (nq + BC - 1) / BC;            // query chunks per key tile
+  const int n_kt = (nk + 127) / 128;              // key tiles that hold at least one valid key
+  const uint32_t total = static_cast<uint32_t>(n_kt) * n_qc;  // chunks of the CTA, numbered C = t * n_qc + j
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tm_qkv128);
+    tma_prefetch_desc(&tm_qkv64);
+    tma_prefetch_desc(&tm_dctx64);
+    for (int i = 0; i < NQC + 4; ++i) mbar_init(&bars[i], 1);   // qdo_full, kv_full, kv_free
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&st_full[s], 1);
+      mbar_init(&st_free[s], 8);      // one arrive per softmax warp of the group
+      mbar_init(&pds_ready[s], 8);
+      mbar_init(&pds_free[s], 1);
+    }
+    mbar_init(acc_full, 1);
+    mbar_init(acc_free, 16);          // every softmax warp reads a part of the accumulators
+    *reinterpret_cast<volatile float*>(smem + Dkv2Smem::kTurn) = 0.f;
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_ptr_smem, 512);
+  {
+    // log-sum-exp and delta of every query row of the sequence (rows beyond it: lse = +inf -> P = 0)
+    float* stat_all = reinterpret_cast<float*>(smem + Dkv2Smem::kStat);
+    const size_t base = static_cast<size_t>(h) * p.total_rows + row_base;
+    for (int q = threadIdx.x; q < MAX_BOXES * 128; q += BWD_THREADS) {
+      stat_all[q] = q < nq ? lse2[base + q] : INFINITY;
+      stat_all[MAX_BOXES * 128 + q] = q < nq ? delta[base + q] : 0.f;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp < 4) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(BWD_REGS_CONTROL));
+    if (warp == 0 && elect_one_sync()) {
+      // ====================================== TMA producer ======================================
+      auto load_kv = [&](int t) {
+        uint8_t* buf = smem + Dkv2Smem::kKV + (t & 1) * 2 * TILE16K;
+        mbar_arrive_expect_tx(&kv_full[t & 1], 2 * TILE16K);
+        tma_load_2d(buf, &tm_qkv128, &kv_full[t & 1], H + h * D, row_base + t * 128);
+        tma_load_2d(buf + TILE16K, &tm_qkv128, &kv_full[t & 1], 2 * H + h * D, row_base + t * 128);
+      };
+      auto load_qdo = [&](int j) {
+        mbar_arrive_expect_tx(&qdo_full[j], TILE16K);
+        tma_load_2d(smem + Dkv2Smem::kQ + j * CHUNK8K, &tm_qkv64, &qdo_full[j], h * D, row_base + j * BC);
+        tma_load_2d(smem + Dkv2Smem::kDO + j * CHUNK8K, &tm_dctx64, &qdo_full[j], h * D, row_base + j * BC);
+      };
+      if (total > 0) {
+        load_qdo(0);
+        load_kv(0);
+        for (int j = 1; j < n_qc; ++j) load_qdo(j);
+        if (n_kt > 1) load_kv(1);
+        for (int t = 2; t < n_kt; ++t) {
+          mbar_wait(&kv_free[t & 1], ((t >> 1) - 1) & 1);  // the epilogue of tile t-2 has left the buffer
+          load_kv(t);
+        }
+      }
+    } else if (warp == 1 && elect_one_sync()) {
+      // ====================================== MMA issuer: S^T = K_t Q_j^T, dP^T = V_t dO_j^T ======================================
+      constexpr uint32_t idesc_st = umma_idesc_bf16(128, BC, 0, 0);
+      const uint64_t dQk = umma_smem_desc(smem_u32(smem + Dkv2Smem::kQ), 16, 1024);
+      const uint64_t dDOk = umma_smem_desc(smem_u32(smem + Dkv2Smem::kDO), 16, 1024);
+      const uint64_t dKV = umma_smem_desc(smem_u32(smem + Dkv2Smem::kKV), 16, 1024);
+      uint32_t C = 0;
+      for (int t = 0; t < n_kt; ++t) {
+        for (int j = 0; j < n_qc; ++j, ++C) {
+          const uint32_t s = C & 1, u = C >> 1;
+          if (t == 0) mbar_wait(&qdo_full[j], 0);
+          if (j == 0) mbar_wait(&kv_full[t & 1], (t >> 1) & 1);
+          if (u >= 1) mbar_wait(&st_free[s], (u - 1) & 1);
+          tc_fence_after();
+          const uint64_t kb = dKV + static_cast<uint64_t>((t & 1) * ((2 * TILE16K) >> 4)), vb = kb + (TILE16K >> 4);
+          const uint64_t qb = dQk + static_cast<uint64_t>(j * (CHUNK8K >> 4)), dob = dDOk + static_cast<uint64_t>(j * (CHUNK8K >> 4));
+          const uint32_t ts = tmem_base + s * 192;
+#pragma unroll
+          for (int kk = 0; kk < D / 16; ++kk) umma_bf16(ts, kb + 2 * kk, qb + 2 * kk, idesc_st, kk > 0);
+#pragma unroll
+          for (int kk = 0; kk < D / 16; ++kk) umma_bf16(ts + 64, vb + 2 * kk, dob + 2 * kk, idesc_st, kk > 0);
+          umma_commit(&st_full[s]);
+          PLB_TRACE(1, C);
+        }
+      }
+    } else if (warp == 2 && elect_one_sync()) {
+      // ====================================== MMA issuer: dV += P^T dO_j, dK += dS^T Q_j (A operands in TMEM) ======================================
+      constexpr uint32_t idesc_acc = umma_idesc_bf16(128, D, 0, 1);  // B MN-major
+      const uint64_t dQm = umma_smem_desc(smem_u32(smem + Dkv2Smem::kQ), TILE16K, 1024);
+      const uint64_t dDOm = umma_smem_desc(smem_u32(smem + Dkv2Smem::kDO), TILE16K, 1024);
+      uint32_t C = 0;
+      for (int t = 0; t < n_kt; ++t) {
+        for (int j = 0; j < n_qc; ++j, ++C) {
+          const uint32_t s = C & 1, u = C >> 1;
+          mbar_wait(&pds_ready[s], u & 1);
+          if (j == 0 && t >= 1) mbar_wait(acc_free, (t - 1) & 1);  // the epilogue of the previous tile has read dK / dV
+          tc_fence_after();
+          const uint64_t qb = dQm + static_cast<uint64_t>(j * (CHUNK8K >> 4)), dob = dDOm + static_cast<uint64_t>(j * (CHUNK8K >> 4));
+          const uint32_t ts = tmem_base + s * 192;
+#pragma unroll
+          for (int kk = 0; kk < BC / 16; ++kk) umma_bf16_tmem_a(tmem_base + 448, ts + 128 + 8 * kk, dob + 128 * kk, idesc_acc, (j > 0 || kk > 0));
+#pragma unroll
+          for (int kk = 0; kk < BC / 16; ++kk) umma_bf16_tmem_a(tmem_base + 384, ts + 160 + 8 * kk, qb + 128 * kk, idesc_acc, (j > 0 || kk > 0));
+          umma_commit(&pds_free[s]);
+          if (j == n_qc - 1) umma_commit(acc_full);
+          PLB_TRACE(2, C);
+        }
+      }
+    }
+    __syncwarp();
+  } else {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(BWD_REGS_SOFTMAX));
+    // ====================================== P^T / dS^T producers + dK/dV epilogue ======================================
+    const int grp = (warp - 4) >> 3;
+    const int half = ((warp - 4) >> 2) & 1;
+    const int quad = warp & 3;
+    const int row = quad * 32 + lane;
+    const int stid = threadIdx.x - 128;  // 0..511 over both groups
+    const uint32_t lane_addr = static_cast<uint32_t>(quad * 32) << 16;
+    const uint32_t ts = tmem_base + lane_addr + grp * 192;
+    const uint32_t stat_addr = smem_u32(smem + Dkv2Smem::kStat);
+    const uint32_t turn_addr = smem_u32(smem + Dkv2Smem::kTurn);
+    const uint32_t steps0 = (total + 1) >> 1, steps1 = total >> 1;  // chunks per group
+
+    // key rows in [128 * n_kt, nq): padded keys inside the allocated sequence -> their gradients are exactly zero
+    for (int t = n_kt; t * 128 < nq; ++t) {
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const int idx = stid + i * 512;
+        const int r = t * 128 + (idx >> 3), cc = idx & 7;
+        if (r < nq) {
+          __nv_bfloat16* dst = dqkv + static_cast<size_t>(row_base + r) * ld_dqkv + h * D + cc * 8;
+          *reinterpret_cast<uint4*>(dst + H) = make_uint4(0, 0, 0, 0);
+          *reinterpret_cast<uint4*>(dst + 2 * H) = make_uint4(0, 0, 0, 0);
+        }
+      }
+    }
+
+    uint32_t c = 0;  // chunks this group has processed (its step counter; global chunk C = 2 c + grp)
+    for (int t = 0; t < n_kt; ++t) {
+      const bool key_valid = (t * 128 + row) < nk;
+      // this group's chunks of tile t: global C in [t * n_qc, (t + 1) * n_qc) with C & 1 == grp
+      const uint32_t C_end = static_cast<uint32_t>(t + 1) * n_qc;
+      for (uint32_t C = 2 * c + grp; C < C_end; C += 2, ++c) {
+        const int j = static_cast<int>(C - static_cast<uint32_t>(t) * n_qc);
+        mbar_wait(&st_full[grp], c & 1);
+        tc_fence_after();
+        PLB_TRACE(10, c);
+        uint32_t sv[32], dv[32];
+        tmem_ld_32x32(ts + half * 32, sv);
+        tmem_ld_32x32(ts + 64 + half * 32, dv);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&st_free[grp]);
+        if (!key_valid) {  // key rows >= kv_len (last tile only): P = exp2(-inf) = 0, hence dS = 0
+#pragma unroll
+          for (int i = 0; i < 32; ++i) sv[i] = 0xff800000u;
+        }
+        PLB_TRACE(11, c);
+        const uint32_t st = stat_addr + (j * BC + half * 32) * 4;
+        uint32_t pkp[16], pkd[16];
+        const float tz = turn_acquire<128>(grp, quad, c, steps1, turn_addr);
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc) {
+          const float4 l0 = lds128_ro(st + cc * 32), l1 = lds128_ro(st + cc * 32 + 16);
+          const float4 d0 = lds128_ro(st + MAX_BOXES * 512 + cc * 32), d1 = lds128_ro(st + MAX_BOXES * 512 + cc * 32 + 16);
+          const float ls[8] = {l0.x, l0.y, l0.z, l0.w, l1.x, l1.y, l1.z, l1.w};
+          const float dl[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
+          float pr[8], ds[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            pr[i] = ex2_fast(fmaf(__uint_as_float(sv[cc * 8 + i]), p.scale_log2, tz - ls[i]));
+            ds[i] = pr[i] * (__uint_as_float(dv[cc * 8 + i]) - dl[i]);
+          }
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            pkp[cc * 4 + i] = pack_bf16x2(pr[2 * i], pr[2 * i + 1]);
+            pkd[cc * 4 + i] = pack_bf16x2(ds[2 * i], ds[2 * i + 1]);
+          }
+        }
+        turn_release<128>(grp, quad, c, steps0, steps1, turn_addr, pkd[1] ^ pkd[7] ^ pkd[8] ^ pkd[15]);
+        PLB_TRACE(14, c);
+        if (c >= 1) mbar_wait(&pds_free[grp], (c - 1) & 1);  // the previous accumulating MMAs of this slot have read P^T / dS^T
+        PLB_TRACE(15, c);
+        tc_fence_after();
+        tmem_st_32x16(ts + 128 + half * 16, pkp);
+        tmem_st_32x16(ts + 160 + half * 16, pkd);
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&pds_ready[grp]);
+        PLB_TRACE(16, c);
+      }
+      // ---- tile epilogue (all 16 warps): group 0 drains dK * scale, group 1 drains dV -> bf16 -> staging -> global ----
+      uint8_t* stage = smem + Dkv2Smem::kKV + (t & 1) * 2 * TILE16K;  // K_t / V_t of this tile are dead by now
+      const uint32_t stage_mine = smem_u32(stage) + grp * TILE16K;    // dK staging | dV staging
+      mbar_wait(acc_full, t & 1);
+      tc_fence_after();
+      PLB_TRACE(20, t);
+      {
+        const float mul = grp == 0 ? p.scale : 1.f;
+        uint32_t o[32];
+        tmem_ld_32x32(tmem_base + lane_addr + 384 + grp * 64 + half * 32, o);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(acc_free);  // accumulators are in registers: the next tile may start accumulating
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc) {
+          uint4 v;
+          v.x = pack_bf16x2(__uint_as_float(o[cc * 8 + 0]) * mul, __uint_as_float(o[cc * 8 + 1]) * mul);
+          v.y = pack_bf16x2(__uint_as_float(o[cc * 8 + 2]) * mul, __uint_as_float(o[cc * 8 + 3]) * mul);
+          v.z = pack_bf16x2(__uint_as_float(o[cc * 8 + 4]) * mul, __uint_as_float(o[cc * 8 + 5]) * mul);
+          v.w = pack_bf16x2(__uint_as_float(o[cc * 8 + 6]) * mul, __uint_as_float(o[cc * 8 + 7]) * mul);
+          sts128(stage_mine + row * 128 + (((half * 4 + cc) ^ (row & 7)) << 4), v);
+        }
+      }
+      asm volatile("bar.sync 11, 512;" ::: "memory");  // both staging tiles complete
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const int idx = stid + i * 512;
+        const int r = idx >> 3, cc = idx & 7;
+        const int key = t * 128 + r;
+        if (key < nq) {  // rows in [nk, nq) were masked above: their accumulators are exact zeros
+          __nv_bfloat16* dst = dqkv + static_cast<size_t>(row_base + key) * ld_dqkv + h * D + cc * 8;
+          *reinterpret_cast<uint4*>(dst + H) = lds128(smem_u32(stage) + r * 128 + ((cc ^ (r & 7)) << 4));
+          *reinterpret_cast<uint4*>(dst + 2 * H) = lds128(smem_u32(stage) + TILE16K + r * 128 + ((cc ^ (r & 7)) << 4));
+        }
+      }
+      if (dbias != nullptr) {
+        // (the key-bias gradient is mathematically zero; it is accumulated anyway so the tensor holds what autograd would)
+        tile_colsum_atomic<8>(smem_u32(stage), min(128, nk - t * 128), stid, dbias + H + h * D);
+        tile_colsum_atomic<8>(smem_u32(stage) + TILE16K, min(128, nk - t * 128), stid, dbias + 2 * H + h * D);
+      }
+      fence_proxy_async_smem();  // generic reads / writes of the staging area are ordered before the TMA load that reuses it
+      asm volatile("bar.sync 11, 512;" ::: "memory");
+      if (stid == 0) mbar_arrive(&kv_free[t & 1]);
+      PLB_TRACE(21, t);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  PLB_TRACE(99, 0);
+  if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
 }  // namespace
 }  // namespace plb
 
@@ -1048,6 +1354,8 @@ extern "C" int plb_attn_bwd_tc(const void* qkv, int ld_qkv, const int32_t* seq_s
   if (!configured) {
     cudaError_t e1 = cudaFuncSetAttribute(attn_bwd_dq_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DqSmem::kAlloc);
     cudaError_t e2 = cudaFuncSetAttribute(attn_bwd_dkv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DkvSmem::kAlloc);
+    if (e2 == cudaSuccess)
+      e2 = cudaFuncSetAttribute(attn_bwd_dkv2_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Dkv2Smem::kAlloc);
     PLB_REQUIRE(e1 == cudaSuccess && e2 == cudaSuccess, PLB_ERR_CUDA, "attn_bwd_tc: cudaFuncSetAttribute failed");
     configured = true;
   }
@@ -1063,9 +1371,16 @@ extern "C" int plb_attn_bwd_tc(const void* qkv, int ld_qkv, const int32_t* seq_s
                                                                             dbias_qkv_accum);
   rc = check_launch("plb_attn_bwd_tc(dq)");
   if (rc) return rc;
+  static const bool dkv_gen1 = [] { const char* e = getenv("PLB_ATTN_DKV"); return e != nullptr && atoi(e) == 1; }();
+  if (dkv_gen1) {
   attn_bwd_dkv_tc_kernel<<<B * heads, BWD_THREADS, DkvSmem::kAlloc, stream>>>(tm_qkv128, tm_qkv64, tm_dctx64, p, lse2, delta,
                                                                               static_cast<__nv_bfloat16*>(dqkv), ld_dqkv,
                                                                               dbias_qkv_accum);
+  } else {
+    attn_bwd_dkv2_tc_kernel<<<B * heads, BWD_THREADS, Dkv2Smem::kAlloc, stream>>>(tm_qkv128, tm_qkv64, tm_dctx64, p, lse2, delta,
+                                                                              static_cast<__nv_bfloat16*>(dqkv), ld_dqkv,
+                                                                              dbias_qkv_accum);
+  }
   return check_launch("plb_attn_bwd_tc(dkv)");
 }
 
