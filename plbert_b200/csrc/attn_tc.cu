@@ -98,9 +98,9 @@ __device__ __forceinline__ void turn_release(int grp, int quad, uint32_t c, uint
 // every warp of CTA 0 appends (clock, warp, code, index) records.  Compiled out of the product library.
 #ifdef PLB_ATTN_TRACE
 constexpr unsigned TRACE_SLOTS = 512;  // records per warp; plain stores, no atomics, so the timeline stays undisturbed
-constexpr unsigned TRACE_CAP = 3 * 16 * TRACE_SLOTS;  // kernel id (0 fwd, 1 dQ, 2 dK/dV) x warp x slot
+constexpr unsigned TRACE_CAP = 3 * 32 * TRACE_SLOTS;  // kernel id (0 fwd, 1 dQ, 2 dK/dV) x warp x slot
 __device__ unsigned long long g_trace[TRACE_CAP];
-#define PLB_TRACE_INIT(kid) unsigned trace_k = 0; const unsigned trace_w = (kid) * 16 + (threadIdx.x >> 5)
+#define PLB_TRACE_INIT(kid) unsigned trace_k = 0; const unsigned trace_w = (kid) * 32 + (threadIdx.x >> 5)
 #define PLB_TRACE(code, idx)                                                                                          \
   do {                                                                                                                \
     if (blockIdx.x == 0 && (threadIdx.x & 31) == 0 && trace_k < TRACE_SLOTS)                                          \

@@ -57,7 +57,7 @@ def run(which="fwd"):
                                  dbias.data_ptr(), S)
         assert rc == 0
 
-    cap = 3 * 16 * 512
+    cap = 3 * 32 * 512
     buf = (ctypes.c_ulonglong * cap)()
     lib.plb_attn_trace_dump(buf, cap)  # clears the table
     fwd()
@@ -67,7 +67,7 @@ def run(which="fwd"):
     (fwd if which == "fwd" else bwd)()
     n = lib.plb_attn_trace_dump(buf, cap)
     kid = {"fwd": 0, "dq": 1, "dkv": 2}[which]
-    recs = sorted(((v >> 24), (v >> 16) & 15, (v >> 8) & 255, v & 255) for v in buf[:n] if v and ((v >> 20) & 15) == kid)
+    recs = sorted(((v >> 24), (v >> 16) & 31, (v >> 8) & 255, v & 255) for v in buf[:n] if v and ((v >> 21) & 7) == kid)
     t0 = recs[0][0]
     for clk, warp, code, idx in recs:
         print(f"{clk - t0:8d} warp{warp:2d} code {code:3d} idx {idx}")
