@@ -489,13 +489,26 @@ extern "C" int plb_gemm_bf16(int op, int epilogue, int M, int N, int K, const vo
   if (op == PLB_GEMM_WGRAD) {
     PLB_REQUIRE(epilogue == PLB_EPI_NONE && bias == nullptr, PLB_ERR_ARG, "gemm: WGRAD takes no epilogue/bias");
     PLB_REQUIRE(ldc >= N, PLB_ERR_ARG, "gemm: ldc < N");
-    // split K so that every SM gets about two units; each unit keeps at least 8 k-iterations
+    // Split K so that the units fill whole waves of the persistent grid: with P workers (CTAs or CTA pairs) the GEMM takes
+    // ceil(units / P) rounds of one unit each, a unit costing its k-iterations plus a fixed fill / epilogue overhead
+    // (~8 iterations).  Pick the split count that minimises rounds x unit cost; every unit keeps at least 8 k-iterations.
+    // (The old rule "about two units per SM" left the last round 20-30 % full for the four weight shapes of the layer.)
     const int tiles = p.m_tiles * p.n_tiles;
-    int splits = (2 * (sm_count() / ctas) + tiles - 1) / tiles;
+    const int workers = sm_count() / ctas;
     const int max_splits = p.k_iters / 8 > 0 ? p.k_iters / 8 : 1;
-    if (splits > max_splits) splits = max_splits;
-    if (splits < 1) splits = 1;
-    p.k_per_split = (p.k_iters + splits - 1) / splits;
+    long best_cost = -1;
+    int best_kps = p.k_iters;
+    for (int sp = 1; sp <= max_splits && sp <= 4 * workers; ++sp) {
+      const int kps = (p.k_iters + sp - 1) / sp;
+      const int eff_splits = (p.k_iters + kps - 1) / kps;
+      const long rounds = (static_cast<long>(tiles) * eff_splits + workers - 1) / workers;
+      const long cost = rounds * (kps + 8);
+      if (best_cost < 0 || cost < best_cost) {
+        best_cost = cost;
+        best_kps = kps;
+      }
+    }
+    p.k_per_split = best_kps;
     p.splits = (p.k_iters + p.k_per_split - 1) / p.k_per_split;
     p.num_units = tiles * p.splits;
     p.c_f32 = static_cast<float*>(C);
