@@ -5,16 +5,17 @@
 // (sequence, head): K and V of that head (<= 2 x 64 KB bf16) are TMA-loaded ONCE into 128-byte-swizzled shared memory
 // and stay resident while the CTA walks the query tiles, so K/V leave HBM exactly once per head.
 //
-// Warp roles (12 warps = 3 warpgroups): warp 0 = TMA producer, warp 1 = TMEM owner + single-thread MMA issuer (warps 2,3
-// idle; the warpgroup gives its registers away with setmaxnreg), warps 4..7 = softmax group 0, warps 8..11 = softmax
-// group 1 (each softmax thread keeps a whole 128-score row in registers).  The two groups work on DIFFERENT query tiles (tile t goes to group t & 1), so
-// while one group is in its MUFU-bound exp2 phase the other is in its latency-bound phase (TMEM load, row maximum,
-// barriers) and the tensor pipe serves whichever group is ready ("ping-pong").  Thread r of a group owns row r of its
-// tile = TMEM lane r.  Per 128-query tile and 128-key chunk c:
+// Warp roles (12 warps = 3 warpgroups): warp 0 = TMA producer, warps 1 / 2 = MMA issuer of softmax group 0 / 1 (one elected
+// thread each, blocking on the barrier that is due next; warp 3 idle; the warpgroup gives its registers away with
+// setmaxnreg), warps 4..7 = softmax group 0, warps 8..11 = softmax group 1 (each softmax thread keeps a whole 128-score
+// row in registers).  The two groups work on DIFFERENT query tiles (tile t goes to group t & 1) and take turns on the
+// MUFU-bound exp2 phase (turn_acquire / turn_release), so one group's exponentials overlap the other's latency-bound
+// phase (TMEM load, row maximum, barriers) and MMAs.  Thread r of a group owns row r of its tile = TMEM lane r.
+// Per 128-query tile and 128-key chunk c:
 //     S_c  = Q K_c^T                 tcgen05.mma  M128 N128 K64  -> TMEM (one S buffer per group)
 //     regs = tcgen05.ld(S_c)         the S buffer is released right here, so S_{c+1} is computed during the exp2 phase
-//     P_c  = exp2(S_c*k - m)         fp32 softmax, bf16 P_c -> swizzled smem (A operand, one buffer per group)
-//     O   += P_c V_c                 tcgen05.mma  M128 N64 K128  (V as MN-major B: no transpose anywhere)
+//     P_c  = exp2(S_c*k - m)         fp32 softmax, bf16 pairs -> TENSOR MEMORY (tcgen05.st), no shared-memory round trip
+//     O   += P_c V_c                 tcgen05.mma  M128 N64 K128, A = P_c from TMEM, B = V as MN-major smem (no transpose)
 // The running maximum uses the lazy-rescale rule (only when it grows by more than 2^8); the O accumulator is then
 // rescaled in TMEM by the row's own thread (tcgen05.ld/st).
 #include "common.cuh"
@@ -422,9 +423,11 @@ extern "C" int plb_attn_fwd_tc(const void* qkv, int ld_qkv, const int32_t* seq_s
 // =================================================================================================================
 // Backward.  dS = P o (dP - delta), dQ = scale dS K, dK = scale dS^T Q, dV = P^T dO  (SURVEY.md appendix A), with
 // P recomputed from the saved log-sum-exp.  Two kernels so that every accumulator has ONE owner and no atomics are
-// needed: the dQ kernel owns query tiles, the dK/dV kernel owns key tiles.  Both use the forward's structure: one CTA
-// per (sequence, head), three warpgroups (control / softmax group 0 / softmax group 1), tiles alternate between the
-// groups, the single MMA thread serves whichever group is ready, 64-wide chunks along the contracted sequence axis.
+// needed: the dQ kernel owns query tiles, the dK/dV kernel owns key tiles; one CTA per (sequence, head), 64-wide chunks
+// along the contracted sequence axis.  20 warps: a control warpgroup (TMA, elected MMA issuers that block on the barrier
+// due next) and two softmax groups of EIGHT warps — two threads per row, 32 columns each, because the backward pass has
+// no cross-column reduction — which take turns on the exp2 phase.  dS (dQ kernel) and P^T / dS^T (dK/dV kernel) are
+// written to tensor memory as packed bf16 and consumed as the TMEM A operand of the accumulating MMAs.
 // =================================================================================================================
 namespace plb {
 namespace {
@@ -739,295 +742,6 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_c
 }
 
 // ------------------------------------------------------------------------------------------------ dK/dV kernel
-// Group g owns key tiles t = g, g+2 (128 keys each): K_t, V_t are the A operands and stay in shared memory for the
-// tile; Q and dO stream through a per-group two-slot ring in 64-row chunks and are used twice from the same slot —
-// K-major as the B operand of S^T = K Q^T / dP^T = V dO^T and MN-major as the B operand of dV += P^T dO /
-// dK += dS^T Q.  Thread r of a group owns key row r (TMEM lane r): it needs the log-sum-exp and delta of all 64
-// query COLUMNS of the chunk, which the group stages in shared memory.
-struct DkvSmem {
-  static constexpr int kGroup = 6 * TILE16K;                 // per group: K | V | ring (2 x (Q 8K + dO 8K)) | P^T | dS^T
-  static constexpr int kK = 0, kV = TILE16K, kRing = 2 * TILE16K, kPT = 4 * TILE16K, kDST = 5 * TILE16K;
-  static constexpr int kStat = 2 * kGroup;                   // float [2 (lse, delta)][512]: statistics of every query row
-  static constexpr int kBar = kStat + 2 * MAX_BOXES * 128 * 4;
-  static constexpr int kBarsPerGroup = 11;
-  static constexpr int kTurn = kBar + 2 * kBarsPerGroup * 8 + 16;   // 17 words for the exponential-phase turn-taking
-  static constexpr int kAlloc = kTurn + 80;
-};
-static_assert(DkvSmem::kAlloc <= 232448, "dK/dV kernel exceeds the 227 KB shared-memory limit");
-enum { KV_FULL = 0, KV_EMPTY, RING_FULL0, RING_FULL1, RING_FREE0, RING_FREE1, ST_FULL, ST_FREE, PDS_READY, DKV_DONE, ACC_FREE };
-
-__global__ void __launch_bounds__(BWD_THREADS, 1)
-attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv128, const __grid_constant__ CUtensorMap tm_qkv64,
-                       const __grid_constant__ CUtensorMap tm_dctx64, const AttnTcParams p,
-                       const float* __restrict__ lse2, const float* __restrict__ delta,
-                       __nv_bfloat16* __restrict__ dqkv, int ld_dqkv, float* __restrict__ dbias) {
-  extern __shared__ __align__(1024) uint8_t smem[];
-  if (smem_u32(smem) & 1023u) __trap();
-  uint64_t* gbar = reinterpret_cast<uint64_t*>(smem + DkvSmem::kBar);  // [2][11]
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(gbar + 2 * DkvSmem::kBarsPerGroup);
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  PLB_TRACE_INIT(2);
-  PLB_TRACE(0, 0);
-  const int b = blockIdx.x / p.heads, h = blockIdx.x % p.heads;
-  const int row_base = p.seq_start[b], nq = p.q_len[b], nk = p.kv_len[b];
-  const int H = p.heads * D;
-  const int n_qc = (nq + BC - 1) / BC;            // query chunks streamed per key tile
-  const int n_kt = (nk + 127) / 128;              // key tiles that hold at least one valid key
-  const int tiles_of[2] = {(n_kt + 1) >> 1, n_kt >> 1};
-
-  if (threadIdx.x == 0) {
-    tma_prefetch_desc(&tm_qkv128);
-    tma_prefetch_desc(&tm_qkv64);
-    tma_prefetch_desc(&tm_dctx64);
-    for (int g = 0; g < 2; ++g) {
-      uint64_t* gb = gbar + g * DkvSmem::kBarsPerGroup;
-      for (int i = 0; i < DkvSmem::kBarsPerGroup; ++i) mbar_init(&gb[i], 1);
-      mbar_init(&gb[ST_FREE], 8);   // one arrive per softmax warp (8 per group)
-      mbar_init(&gb[PDS_READY], 8);
-      mbar_init(&gb[ACC_FREE], 8);
-    }
-    *reinterpret_cast<volatile float*>(smem + DkvSmem::kTurn) = 0.f;
-    fence_mbar_init();
-  }
-  if (warp == 1) tmem_alloc(tmem_ptr_smem, 512);
-  {
-    // log-sum-exp and delta of every query row of the sequence, staged once: the threads own KEY rows here and need
-    // the statistics of all query COLUMNS (rows beyond the sequence: lse = +inf -> P = 0)
-    float* stat_all = reinterpret_cast<float*>(smem + DkvSmem::kStat);
-    const size_t base = static_cast<size_t>(h) * p.total_rows + row_base;
-    for (int q = threadIdx.x; q < MAX_BOXES * 128; q += BWD_THREADS) {
-      stat_all[q] = q < nq ? lse2[base + q] : INFINITY;
-      stat_all[MAX_BOXES * 128 + q] = q < nq ? delta[base + q] : 0.f;
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_ptr_smem;
-  // TMEM columns per group g: S^T [g*256, +64), dP^T [+64, +64), dK [+128, +64), dV [+192, +64)
-
-  if (warp < 4) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(BWD_REGS_CONTROL));
-    // warps 0 / 3: TMA producers of group 0 / 1; warps 1 / 2: MMA issuers of group 0 / 1.  Every role blocks on the one
-    // barrier that is due next (the order of a group's operations is fixed), so there are no polling loops.
-    const int g = (warp == 0 || warp == 1) ? 0 : 1;
-    uint64_t* gb = gbar + g * DkvSmem::kBarsPerGroup;
-    if ((warp == 0 || warp == 3) && elect_one_sync()) {
-      // ====================================== TMA producer of group g ======================================
-      uint8_t* gs = smem + g * DkvSmem::kGroup;
-      uint32_t lc = 0;
-      for (int kl = 0; kl < tiles_of[g]; ++kl) {
-        const int t = g + 2 * kl;
-        // K_t / V_t buffers are free once every S^T / dP^T MMA of the previous tile has run
-        if (kl > 0) mbar_wait(&gb[KV_EMPTY], (kl - 1) & 1);
-        mbar_arrive_expect_tx(&gb[KV_FULL], 2 * TILE16K);
-        tma_load_2d(gs + DkvSmem::kK, &tm_qkv128, &gb[KV_FULL], H + h * D, row_base + t * 128);
-        tma_load_2d(gs + DkvSmem::kV, &tm_qkv128, &gb[KV_FULL], 2 * H + h * D, row_base + t * 128);
-        for (int jl = 0; jl < n_qc; ++jl, ++lc) {
-          const int slot = lc & 1;
-          if (lc >= 2) mbar_wait(&gb[RING_FREE0 + slot], ((lc >> 1) - 1) & 1);
-          uint8_t* ring = gs + DkvSmem::kRing + slot * TILE16K;
-          mbar_arrive_expect_tx(&gb[RING_FULL0 + slot], TILE16K);
-          tma_load_2d(ring, &tm_qkv64, &gb[RING_FULL0 + slot], h * D, row_base + jl * BC);
-          tma_load_2d(ring + CHUNK8K, &tm_dctx64, &gb[RING_FULL0 + slot], h * D, row_base + jl * BC);
-        }
-      }
-    } else if ((warp == 1 || warp == 2) && elect_one_sync()) {
-      // ====================================== MMA issuer of group g ======================================
-      constexpr uint32_t idesc_st = umma_idesc_bf16(128, BC, 0, 0);  // S^T = K Q^T, dP^T = V dO^T : all K-major
-      constexpr uint32_t idesc_acc = umma_idesc_bf16(128, D, 0, 1);  // dV = P^T dO, dK = dS^T Q : B MN-major
-      const uint32_t gs = smem_u32(smem + g * DkvSmem::kGroup);
-      const uint32_t tg = tmem_base + g * 256;
-      // descriptor bases; the start-address field counts 16-byte units, so advancing is a plain add
-      const uint64_t dK = umma_smem_desc(gs + DkvSmem::kK, 16, 1024), dV = umma_smem_desc(gs + DkvSmem::kV, 16, 1024);
-      const uint64_t dPT = umma_smem_desc(gs + DkvSmem::kPT, 16, 1024), dDST = umma_smem_desc(gs + DkvSmem::kDST, 16, 1024);
-      const uint64_t dRingK = umma_smem_desc(gs + DkvSmem::kRing, 16, 1024);        // Q / dO chunk, K-major view
-      const uint64_t dRingM = umma_smem_desc(gs + DkvSmem::kRing, TILE16K, 1024);   // same bytes, MN-major view
-      const uint32_t total = tiles_of[g] * n_qc;
-      auto issue_st = [&](int k, int j, uint32_t cn) {  // S^T = K_t Q_c^T ; dP^T = V_t dO_c^T for running chunk count cn
-        if (j == 0) mbar_wait(&gb[KV_FULL], k & 1);
-        mbar_wait(&gb[RING_FULL0 + (cn & 1)], (cn >> 1) & 1);
-        tc_fence_after();
-        const uint64_t rq = dRingK + static_cast<uint64_t>((cn & 1) * (TILE16K >> 4)), rdo = rq + (CHUNK8K >> 4);
-#pragma unroll
-        for (int kk = 0; kk < D / 16; ++kk) umma_bf16(tg, dK + 2 * kk, rq + 2 * kk, idesc_st, kk > 0);
-#pragma unroll
-        for (int kk = 0; kk < D / 16; ++kk) umma_bf16(tg + 64, dV + 2 * kk, rdo + 2 * kk, idesc_st, kk > 0);
-        umma_commit(&gb[ST_FULL]);
-        if (j == n_qc - 1) umma_commit(&gb[KV_EMPTY]);
-        PLB_TRACE(1, cn);
-      };
-      if (total > 0) issue_st(0, 0, 0);
-      uint32_t c = 0;
-      for (int k = 0; k < tiles_of[g]; ++k) {
-        for (int j = 0; j < n_qc; ++j, ++c) {
-          const bool has_next = c + 1 < total;
-          const bool next_in_tile = j + 1 < n_qc;
-          if (has_next && next_in_tile) {
-            mbar_wait(&gb[ST_FREE], c & 1);
-            issue_st(k, j + 1, c + 1);
-          }
-          // ---- dV += P^T dO_c ; dK += dS^T Q_c ----
-          mbar_wait(&gb[PDS_READY], c & 1);
-          if (j == 0) mbar_wait(&gb[ACC_FREE], (k & 1) ^ 1);
-          tc_fence_after();
-          const uint64_t rq = dRingM + static_cast<uint64_t>((c & 1) * (TILE16K >> 4)), rdo = rq + (CHUNK8K >> 4);
-#pragma unroll
-          for (int kk = 0; kk < BC / 16; ++kk) umma_bf16(tg + 192, dPT + 2 * kk, rdo + 128 * kk, idesc_acc, (j > 0 || kk > 0));
-#pragma unroll
-          for (int kk = 0; kk < BC / 16; ++kk) umma_bf16(tg + 128, dDST + 2 * kk, rq + 128 * kk, idesc_acc, (j > 0 || kk > 0));
-          umma_commit(&gb[DKV_DONE]);
-          umma_commit(&gb[RING_FREE0 + (c & 1)]);
-          PLB_TRACE(2, c);
-          if (has_next && !next_in_tile) {  // next key tile: its K / V arrive only after this tile's last S^T / dP^T has run
-            mbar_wait(&gb[ST_FREE], c & 1);
-            issue_st(k + 1, 0, c + 1);
-          }
-        }
-      }
-    }
-    __syncwarp();
-  } else {
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(BWD_REGS_SOFTMAX));
-    // ====================================== P^T / dS^T producers + dK/dV epilogue (two groups x eight warps) ======================================
-    // Two threads per key row (same TMEM lane quadrant, different warps), each owning 32 of the chunk's 64 query columns.
-    const int grp = (warp - 4) >> 3;
-    const int half = ((warp - 4) >> 2) & 1;
-    const int quad = warp & 3;
-    const int row = quad * 32 + lane;
-    const int gtid = threadIdx.x - 128 - grp * 256;  // 0..255 within the group
-    const uint32_t lane_addr = static_cast<uint32_t>(quad * 32) << 16;
-    const uint32_t tg = tmem_base + lane_addr + grp * 256;
-    uint64_t* gb = gbar + grp * DkvSmem::kBarsPerGroup;
-    const uint32_t gs = smem_u32(smem + grp * DkvSmem::kGroup);
-    const uint32_t sPT_row = gs + DkvSmem::kPT + row * 128, sDST_row = gs + DkvSmem::kDST + row * 128;
-    const uint32_t stat_addr = smem_u32(smem + DkvSmem::kStat);  // float [2 (lse, delta)][512 query rows]
-
-    // key rows in [128 * n_kt, nq): padded keys inside the allocated sequence -> their gradients are exactly zero
-    for (int t = n_kt + grp; t * 128 < nq; t += 2) {
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int idx = gtid + i * 256;
-        const int r = t * 128 + (idx >> 3), cc = idx & 7;
-        if (r < nq) {
-          __nv_bfloat16* dst = dqkv + static_cast<size_t>(row_base + r) * ld_dqkv + h * D + cc * 8;
-          *reinterpret_cast<uint4*>(dst + H) = make_uint4(0, 0, 0, 0);
-          *reinterpret_cast<uint4*>(dst + 2 * H) = make_uint4(0, 0, 0, 0);
-        }
-      }
-    }
-
-    uint32_t c = 0;
-    const uint32_t turn_addr = smem_u32(smem + DkvSmem::kTurn);
-    const uint32_t steps0 = tiles_of[0] * n_qc, steps1 = tiles_of[1] * n_qc;  // chunks per group
-    for (int t = grp; t < n_kt; t += 2) {
-      const bool key_valid = (t * 128 + row) < nk;
-      for (int j = 0; j < n_qc; ++j, ++c) {
-        PLB_TRACE(9, c);
-        mbar_wait(&gb[ST_FULL], c & 1);
-        tc_fence_after();
-        PLB_TRACE(10, c);
-        uint32_t sv[32], dv[32];
-        tmem_ld_32x32(tg + half * 32, sv);
-        tmem_ld_32x32(tg + 64 + half * 32, dv);
-        tmem_ld_wait();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&gb[ST_FREE]);
-        if (!key_valid) {  // key rows >= kv_len (last tile only): P = exp2(-inf) = 0, hence dS = 0
-#pragma unroll
-          for (int i = 0; i < 32; ++i) sv[i] = 0xff800000u;
-        }
-        PLB_TRACE(11, c);
-        const uint32_t st = stat_addr + (j * BC + half * 32) * 4;
-        uint4 pkp[4], pkd[4];
-        const float tz = turn_acquire<128>(grp, quad, c, steps1, turn_addr);
-#pragma unroll
-        for (int cc = 0; cc < 4; ++cc) {
-          const float4 l0 = lds128_ro(st + cc * 32), l1 = lds128_ro(st + cc * 32 + 16);
-          const float4 d0 = lds128_ro(st + MAX_BOXES * 512 + cc * 32), d1 = lds128_ro(st + MAX_BOXES * 512 + cc * 32 + 16);
-          const float ls[8] = {l0.x, l0.y, l0.z, l0.w, l1.x, l1.y, l1.z, l1.w};
-          const float dl[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
-          float pr[8], ds[8];
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            pr[i] = ex2_fast(fmaf(__uint_as_float(sv[cc * 8 + i]), p.scale_log2, tz - ls[i]));
-            ds[i] = pr[i] * (__uint_as_float(dv[cc * 8 + i]) - dl[i]);
-          }
-          pkp[cc].x = pack_bf16x2(pr[0], pr[1]); pkp[cc].y = pack_bf16x2(pr[2], pr[3]);
-          pkp[cc].z = pack_bf16x2(pr[4], pr[5]); pkp[cc].w = pack_bf16x2(pr[6], pr[7]);
-          pkd[cc].x = pack_bf16x2(ds[0], ds[1]); pkd[cc].y = pack_bf16x2(ds[2], ds[3]);
-          pkd[cc].z = pack_bf16x2(ds[4], ds[5]); pkd[cc].w = pack_bf16x2(ds[6], ds[7]);
-        }
-        turn_release<128>(grp, quad, c, steps0, steps1, turn_addr, pkd[0].y ^ pkd[1].w ^ pkd[2].x ^ pkd[3].w);
-        PLB_TRACE(14, c);
-        if (c >= 1) mbar_wait(&gb[DKV_DONE], (c - 1) & 1);  // P^T / dS^T buffers consumed by the previous dV / dK MMAs
-        PLB_TRACE(15, c);
-#pragma unroll
-        for (int cc = 0; cc < 4; ++cc) {
-          sts128(sPT_row + (((half * 4 + cc) ^ (row & 7)) << 4), pkp[cc]);
-          sts128(sDST_row + (((half * 4 + cc) ^ (row & 7)) << 4), pkd[cc]);
-        }
-        fence_proxy_async_smem();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&gb[PDS_READY]);
-        PLB_TRACE(16, c);
-      }
-      // ---- tile epilogue: dK * scale, dV -> bf16 -> staging (P^T / dS^T buffers) -> global ----
-      mbar_wait(&gb[DKV_DONE], (c - 1) & 1);
-      tc_fence_after();
-      PLB_TRACE(20, t);
-#pragma unroll
-      for (int which = 0; which < 2; ++which) {  // 0: dK (cols 128..191), 1: dV (cols 192..255)
-        const float mul = which == 0 ? p.scale : 1.f;
-        const uint32_t dst_row = which == 0 ? sPT_row : sDST_row;
-        uint32_t o[32];
-        tmem_ld_32x32(tg + 128 + which * 64 + half * 32, o);
-        tmem_ld_wait();
-#pragma unroll
-        for (int cc = 0; cc < 4; ++cc) {
-          uint4 v;
-          v.x = pack_bf16x2(__uint_as_float(o[cc * 8 + 0]) * mul, __uint_as_float(o[cc * 8 + 1]) * mul);
-          v.y = pack_bf16x2(__uint_as_float(o[cc * 8 + 2]) * mul, __uint_as_float(o[cc * 8 + 3]) * mul);
-          v.z = pack_bf16x2(__uint_as_float(o[cc * 8 + 4]) * mul, __uint_as_float(o[cc * 8 + 5]) * mul);
-          v.w = pack_bf16x2(__uint_as_float(o[cc * 8 + 6]) * mul, __uint_as_float(o[cc * 8 + 7]) * mul);
-          sts128(dst_row + (((half * 4 + cc) ^ (row & 7)) << 4), v);
-        }
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&gb[ACC_FREE]);
-      group_bar_sync256(grp);
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int idx = gtid + i * 256;
-        const int r = idx >> 3, cc = idx & 7;
-        const int key = t * 128 + r;
-        if (key < nq) {  // rows in [nk, nq) were masked above: their accumulators are exact zeros
-          __nv_bfloat16* dst = dqkv + static_cast<size_t>(row_base + key) * ld_dqkv + h * D + cc * 8;
-          *reinterpret_cast<uint4*>(dst + H) = lds128(gs + DkvSmem::kPT + r * 128 + ((cc ^ (r & 7)) << 4));
-          *reinterpret_cast<uint4*>(dst + 2 * H) = lds128(gs + DkvSmem::kDST + r * 128 + ((cc ^ (r & 7)) << 4));
-        }
-      }
-      if (dbias != nullptr) {
-        // (the key-bias gradient is mathematically zero; it is accumulated anyway so the tensor holds what autograd would)
-        tile_colsum_atomic<16>(gs + DkvSmem::kPT, min(128, nk - t * 128), gtid, dbias + H + h * D);
-        tile_colsum_atomic<16>(gs + DkvSmem::kDST, min(128, nk - t * 128), gtid, dbias + 2 * H + h * D);
-      }
-      group_bar_sync256(grp);
-      PLB_TRACE(21, t);
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  PLB_TRACE(99, 0);
-  if (warp == 1) tmem_dealloc(tmem_base, 512);
-}
-
-
-// ------------------------------------------------------------------------------------------------ dK/dV kernel, second generation
 // One key tile at a time per CTA, shared by BOTH softmax groups: the 64-query chunks of the tile alternate between the
 // groups (chunk C -> group C & 1, TMEM slot C & 1), and every chunk's dV += P^T dO / dK += dS^T Q accumulates into the
 // single dK / dV accumulator pair.  That frees enough tensor memory to keep P^T and dS^T there as packed bf16 — the A
@@ -1039,7 +753,7 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv128, const __gr
 //                 dK [384, +64), dV [448, +64).
 //   Warps: 0 TMA, 1 MMA issuer of the S^T / dP^T stream, 2 MMA issuer of the accumulating stream, 3 idle,
 //          4..11 softmax group 0, 12..19 softmax group 1 (two threads per key row, 32 query columns each).
-struct Dkv2Smem {
+struct DkvSmem {
   static constexpr int kQ = 0;                                // Q of the sequence: 8 chunks of [64 x 64] (8 KB each)
   static constexpr int kDO = kQ + MAX_BOXES * TILE16K;        // dO of the sequence, same layout
   static constexpr int kKV = kDO + MAX_BOXES * TILE16K;       // 2 buffers x (K_t 16 KB | V_t 16 KB); epilogue staging of tile t
@@ -1050,16 +764,16 @@ struct Dkv2Smem {
   static constexpr int kTurn = kBar + kNumBars * 8 + 16;      // 17 words for the exponential-phase turn-taking
   static constexpr int kAlloc = kTurn + 80;
 };
-static_assert(Dkv2Smem::kAlloc <= 232448, "dK/dV kernel exceeds the 227 KB shared-memory limit");
+static_assert(DkvSmem::kAlloc <= 232448, "dK/dV kernel exceeds the 227 KB shared-memory limit");
 
 __global__ void __launch_bounds__(BWD_THREADS, 1)
-attn_bwd_dkv2_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv128, const __grid_constant__ CUtensorMap tm_qkv64,
+attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv128, const __grid_constant__ CUtensorMap tm_qkv64,
                         const __grid_constant__ CUtensorMap tm_dctx64, const AttnTcParams p,
                         const float* __restrict__ lse2, const float* __restrict__ delta,
                         __nv_bfloat16* __restrict__ dqkv, int ld_dqkv, float* __restrict__ dbias) {
   extern __shared__ __align__(1024) uint8_t smem[];
   if (smem_u32(smem) & 1023u) __trap();
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Dkv2Smem::kBar);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + DkvSmem::kBar);
   constexpr int NQC = 2 * MAX_BOXES;  // at most 8 query chunks
   uint64_t* qdo_full = bars;                 // [8]
   uint64_t* kv_full = bars + NQC;            // [2]
@@ -1070,7 +784,7 @@ attn_bwd_dkv2_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv128, const __g
   uint64_t* pds_free = pds_ready + 2;        // [2]
   uint64_t* acc_full = pds_free + 2;
   uint64_t* acc_free = acc_full + 1;
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + Dkv2Smem::kNumBars);
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + DkvSmem::kNumBars);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   PLB_TRACE_INIT(2);
@@ -1095,13 +809,13 @@ attn_bwd_dkv2_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv128, const __g
     }
     mbar_init(acc_full, 1);
     mbar_init(acc_free, 16);          // every softmax warp reads a part of the accumulators
-    *reinterpret_cast<volatile float*>(smem + Dkv2Smem::kTurn) = 0.f;
+    *reinterpret_cast<volatile float*>(smem + DkvSmem::kTurn) = 0.f;
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc(tmem_ptr_smem, 512);
   {
     // log-sum-exp and delta of every query row of the sequence (rows beyond it: lse = +inf -> P = 0)
-    float* stat_all = reinterpret_cast<float*>(smem + Dkv2Smem::kStat);
+    float* stat_all = reinterpret_cast<float*>(smem + DkvSmem::kStat);
     const size_t base = static_cast<size_t>(h) * p.total_rows + row_base;
     for (int q = threadIdx.x; q < MAX_BOXES * 128; q += BWD_THREADS) {
       stat_all[q] = q < nq ? lse2[base + q] : INFINITY;
@@ -1118,15 +832,15 @@ attn_bwd_dkv2_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv128, const __g
     if (warp == 0 && elect_one_sync()) {
       // ====================================== TMA producer ======================================
       auto load_kv = [&](int t) {
-        uint8_t* buf = smem + Dkv2Smem::kKV + (t & 1) * 2 * TILE16K;
+        uint8_t* buf = smem + DkvSmem::kKV + (t & 1) * 2 * TILE16K;
         mbar_arrive_expect_tx(&kv_full[t & 1], 2 * TILE16K);
         tma_load_2d(buf, &tm_qkv128, &kv_full[t & 1], H + h * D, row_base + t * 128);
         tma_load_2d(buf + TILE16K, &tm_qkv128, &kv_full[t & 1], 2 * H + h * D, row_base + t * 128);
       };
       auto load_qdo = [&](int j) {
         mbar_arrive_expect_tx(&qdo_full[j], TILE16K);
-        tma_load_2d(smem + Dkv2Smem::kQ + j * CHUNK8K, &tm_qkv64, &qdo_full[j], h * D, row_base + j * BC);
-        tma_load_2d(smem + Dkv2Smem::kDO + j * CHUNK8K, &tm_dctx64, &qdo_full[j], h * D, row_base + j * BC);
+        tma_load_2d(smem + DkvSmem::kQ + j * CHUNK8K, &tm_qkv64, &qdo_full[j], h * D, row_base + j * BC);
+        tma_load_2d(smem + DkvSmem::kDO + j * CHUNK8K, &tm_dctx64, &qdo_full[j], h * D, row_base + j * BC);
       };
       if (total > 0) {
         load_qdo(0);
@@ -1141,9 +855,9 @@ attn_bwd_dkv2_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv128, const __g
     } else if (warp == 1 && elect_one_sync()) {
       // ====================================== MMA issuer: S^T = K_t Q_j^T, dP^T = V_t dO_j^T ======================================
       constexpr uint32_t idesc_st = umma_idesc_bf16(128, BC, 0, 0);
-      const uint64_t dQk = umma_smem_desc(smem_u32(smem + Dkv2Smem::kQ), 16, 1024);
-      const uint64_t dDOk = umma_smem_desc(smem_u32(smem + Dkv2Smem::kDO), 16, 1024);
-      const uint64_t dKV = umma_smem_desc(smem_u32(smem + Dkv2Smem::kKV), 16, 1024);
+      const uint64_t dQk = umma_smem_desc(smem_u32(smem + DkvSmem::kQ), 16, 1024);
+      const uint64_t dDOk = umma_smem_desc(smem_u32(smem + DkvSmem::kDO), 16, 1024);
+      const uint64_t dKV = umma_smem_desc(smem_u32(smem + DkvSmem::kKV), 16, 1024);
       uint32_t C = 0;
       for (int t = 0; t < n_kt; ++t) {
         for (int j = 0; j < n_qc; ++j, ++C) {
@@ -1166,8 +880,8 @@ attn_bwd_dkv2_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv128, const __g
     } else if (warp == 2 && elect_one_sync()) {
       // ====================================== MMA issuer: dV += P^T dO_j, dK += dS^T Q_j (A operands in TMEM) ======================================
       constexpr uint32_t idesc_acc = umma_idesc_bf16(128, D, 0, 1);  // B MN-major
-      const uint64_t dQm = umma_smem_desc(smem_u32(smem + Dkv2Smem::kQ), TILE16K, 1024);
-      const uint64_t dDOm = umma_smem_desc(smem_u32(smem + Dkv2Smem::kDO), TILE16K, 1024);
+      const uint64_t dQm = umma_smem_desc(smem_u32(smem + DkvSmem::kQ), TILE16K, 1024);
+      const uint64_t dDOm = umma_smem_desc(smem_u32(smem + DkvSmem::kDO), TILE16K, 1024);
       uint32_t C = 0;
       for (int t = 0; t < n_kt; ++t) {
         for (int j = 0; j < n_qc; ++j, ++C) {
@@ -1198,8 +912,8 @@ attn_bwd_dkv2_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv128, const __g
     const int stid = threadIdx.x - 128;  // 0..511 over both groups
     const uint32_t lane_addr = static_cast<uint32_t>(quad * 32) << 16;
     const uint32_t ts = tmem_base + lane_addr + grp * 192;
-    const uint32_t stat_addr = smem_u32(smem + Dkv2Smem::kStat);
-    const uint32_t turn_addr = smem_u32(smem + Dkv2Smem::kTurn);
+    const uint32_t stat_addr = smem_u32(smem + DkvSmem::kStat);
+    const uint32_t turn_addr = smem_u32(smem + DkvSmem::kTurn);
     const uint32_t steps0 = (total + 1) >> 1, steps1 = total >> 1;  // chunks per group
 
     // key rows in [128 * n_kt, nq): padded keys inside the allocated sequence -> their gradients are exactly zero
@@ -1273,7 +987,7 @@ attn_bwd_dkv2_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv128, const __g
         PLB_TRACE(16, c);
       }
       // ---- tile epilogue (all 16 warps): group 0 drains dK * scale, group 1 drains dV -> bf16 -> staging -> global ----
-      uint8_t* stage = smem + Dkv2Smem::kKV + (t & 1) * 2 * TILE16K;  // K_t / V_t of this tile are dead by now
+      uint8_t* stage = smem + DkvSmem::kKV + (t & 1) * 2 * TILE16K;  // K_t / V_t of this tile are dead by now
       const uint32_t stage_mine = smem_u32(stage) + grp * TILE16K;    // dK staging | dV staging
       mbar_wait(acc_full, t & 1);
       tc_fence_after();
@@ -1354,8 +1068,6 @@ extern "C" int plb_attn_bwd_tc(const void* qkv, int ld_qkv, const int32_t* seq_s
   if (!configured) {
     cudaError_t e1 = cudaFuncSetAttribute(attn_bwd_dq_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DqSmem::kAlloc);
     cudaError_t e2 = cudaFuncSetAttribute(attn_bwd_dkv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DkvSmem::kAlloc);
-    if (e2 == cudaSuccess)
-      e2 = cudaFuncSetAttribute(attn_bwd_dkv2_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Dkv2Smem::kAlloc);
     PLB_REQUIRE(e1 == cudaSuccess && e2 == cudaSuccess, PLB_ERR_CUDA, "attn_bwd_tc: cudaFuncSetAttribute failed");
     configured = true;
   }
@@ -1371,16 +1083,9 @@ extern "C" int plb_attn_bwd_tc(const void* qkv, int ld_qkv, const int32_t* seq_s
                                                                             dbias_qkv_accum);
   rc = check_launch("plb_attn_bwd_tc(dq)");
   if (rc) return rc;
-  static const bool dkv_gen1 = [] { const char* e = getenv("PLB_ATTN_DKV"); return e != nullptr && atoi(e) == 1; }();
-  if (dkv_gen1) {
   attn_bwd_dkv_tc_kernel<<<B * heads, BWD_THREADS, DkvSmem::kAlloc, stream>>>(tm_qkv128, tm_qkv64, tm_dctx64, p, lse2, delta,
                                                                               static_cast<__nv_bfloat16*>(dqkv), ld_dqkv,
                                                                               dbias_qkv_accum);
-  } else {
-    attn_bwd_dkv2_tc_kernel<<<B * heads, BWD_THREADS, Dkv2Smem::kAlloc, stream>>>(tm_qkv128, tm_qkv64, tm_dctx64, p, lse2, delta,
-                                                                              static_cast<__nv_bfloat16*>(dqkv), ld_dqkv,
-                                                                              dbias_qkv_accum);
-  }
   return check_launch("plb_attn_bwd_tc(dkv)");
 }
 
