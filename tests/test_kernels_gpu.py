@@ -220,7 +220,11 @@ def _attn_ref(qkv, B, L, nh, lens):
 
 
 @pytest.mark.parametrize("B,L,nh,lens", [(2, 64, 2, [64, 64]), (3, 200, 2, [200, 77, 1]), (2, 512, 12, [512, 300]),
-                                         (4, 130, 3, [130, 129, 65, 64])])
+                                         (4, 130, 3, [130, 129, 65, 64]),
+                                         # tile / chunk parities of the two-group schedules: 1, 2, 3 query tiles, odd chunk
+                                         # counts, fewer key tiles than query tiles, a single valid key
+                                         (2, 128, 1, [128, 5]), (2, 256, 2, [256, 130]), (3, 384, 2, [384, 100, 257]),
+                                         (4, 512, 2, [1, 128, 129, 511]), (3, 320, 1, [320, 64, 200]), (2, 448, 1, [448, 449 - 64])])
 @pytest.mark.parametrize("fwd,bwd", [("plb_attn_fwd", "plb_attn_bwd"), ("plb_attn_fwd_tc", "plb_attn_bwd_tc")])
 def test_attention_fwd_bwd(dev, B, L, nh, lens, fwd, bwd):
     H, T = nh * 64, B * L
@@ -259,6 +263,41 @@ def test_attention_fwd_bwd(dev, B, L, nh, lens, fwd, bwd):
         assert rel(dqkv[:, sl].float(), qf.grad[:, sl]) < 2e-2, name
     # masked keys: exactly zero gradient for K and V
     assert not dqkv[~valid][:, H:].any()
+
+
+@pytest.mark.parametrize("lens", [[512, 300, 1, 77], [65, 64, 130, 129, 128, 127], [200]])
+def test_attention_tc_packed_layout(dev, lens):
+    """Packed (cu_seqlens) layout through the same ABI: q_len == kv_len == the sequence length, sequences back to back.
+    Rows past a sequence's end belong to its neighbour and must be neither read as keys nor written."""
+    nh = 2
+    H, B = nh * 64, len(lens)
+    starts = [0]
+    for n in lens[:-1]:
+        starts.append(starts[-1] + n)
+    T = sum(lens)
+    qkv = torch.randn(T, 3 * H, device=dev).to(BF)
+    lens_t = torch.tensor(lens, device=dev, dtype=torch.int32)
+    seq_start = torch.tensor(starts, device=dev, dtype=torch.int32)
+    ctx = torch.full((T, H), float("nan"), device=dev, dtype=BF)
+    lse = torch.zeros(nh, T, device=dev)
+    call("plb_attn_fwd_tc", ptr(qkv), 3 * H, ptr(seq_start), ptr(lens_t), ptr(lens_t), B, nh, 64, max(lens), T, ptr(ctx), H,
+         ptr(lse), S())
+    qf = qkv.float().requires_grad_(True)
+    outs = []
+    for b0, n in zip(starts, lens):
+        q, k, v = [t.view(n, nh, 64).transpose(0, 1) for t in qf[b0:b0 + n].split(H, dim=1)]
+        outs.append((torch.softmax(q @ k.transpose(-1, -2) / 8.0, dim=-1) @ v).transpose(0, 1).reshape(n, H))
+    ref = torch.cat(outs)
+    assert torch.isfinite(ctx.float()).all() and rel(ctx.float(), ref) < 8e-3
+    dctx = torch.randn(T, H, device=dev).to(BF)
+    ref.backward(dctx.float())
+    dqkv = torch.full((T, 3 * H), float("nan"), device=dev, dtype=BF)
+    delta = torch.zeros(nh, T, device=dev)
+    call("plb_attn_bwd_tc", ptr(qkv), 3 * H, ptr(seq_start), ptr(lens_t), ptr(lens_t), B, nh, 64, max(lens), T, ptr(ctx),
+         ptr(dctx), H, ptr(lse), ptr(delta), ptr(dqkv), 3 * H, 0, S())
+    assert torch.isfinite(dqkv.float()).all()
+    for name, sl in (("dq", slice(0, H)), ("dk", slice(H, 2 * H)), ("dv", slice(2 * H, 3 * H))):
+        assert rel(dqkv[:, sl].float(), qf.grad[:, sl]) < 2e-2, name
 
 
 # ------------------------------------------------------------------------------------------ masked-row loss path
