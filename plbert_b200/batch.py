@@ -9,6 +9,7 @@ code cannot travel to the GPU box).
 """
 from __future__ import annotations
 
+import itertools
 from dataclasses import dataclass, field
 from typing import List, Optional, Sequence, Tuple
 
@@ -26,22 +27,23 @@ def flatten_masked_indices(input_lengths: Sequence[int], masked_indices: Sequenc
     """Row selection of R/train.py:123-129 as flat arrays: ``rows[k] = b * seq_stride + i`` in the reference's
     iteration order and ``weights[k] = 1 / (count * n_b)`` where ``count`` is the number of samples with at least
     one masked index.  int32 / float32, bit-exact index arithmetic."""
-    count = sum(1 for m in masked_indices if len(m) > 0)
-    rows: List[np.ndarray] = []
-    weights: List[np.ndarray] = []
-    for b, (length, idx) in enumerate(zip(input_lengths, masked_indices)):
-        n_b = len(idx)
-        if n_b == 0:
-            continue
-        a = np.asarray(idx, dtype=np.int64)
-        a = np.where(a < 0, a + int(length), a)
-        if a.min() < 0 or a.max() >= int(length):
-            raise IndexError(f"masked index out of range for sample {b} (length {length})")
-        rows.append(a + b * seq_stride)
-        weights.append(np.full(n_b, 1.0 / (count * n_b), dtype=np.float64))
-    if not rows:
+    # one pass over the python lists, everything else vectorised (the per-sample loop cost 2-5 ms per 192-sample batch)
+    B = len(masked_indices)
+    counts = np.fromiter((len(m) for m in masked_indices), dtype=np.int64, count=B)
+    total = int(counts.sum())
+    if total == 0:
         return np.zeros(0, dtype=np.int32), np.zeros(0, dtype=np.float32)
-    return np.concatenate(rows).astype(np.int32), np.concatenate(weights).astype(np.float32)
+    flat = np.fromiter(itertools.chain.from_iterable(masked_indices), dtype=np.int64, count=total)
+    sample = np.repeat(np.arange(B, dtype=np.int64), counts)            # owning sample of every masked index
+    length = np.asarray(input_lengths, dtype=np.int64)[sample]
+    flat = np.where(flat < 0, flat + length, flat)                      # python-style negative indices
+    bad = (flat < 0) | (flat >= length)
+    if bad.any():
+        b = int(sample[np.argmax(bad)])
+        raise IndexError(f"masked index out of range for sample {b} (length {int(input_lengths[b])})")
+    count = int(np.count_nonzero(counts))                               # samples with at least one masked index
+    weights = 1.0 / (count * counts[sample].astype(np.float64))
+    return (flat + sample * seq_stride).astype(np.int32), weights.astype(np.float32)
 
 
 @dataclass
