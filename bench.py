@@ -54,6 +54,17 @@ def measured_peaks():
     return dict(burst=1590.0, sustained=1400.0, hbm=6650.0, source="fallback (B200_PROFILING.md)")
 
 
+def gemm_dram_traffic(two_heads):
+    """Average DRAM bytes (read + write) per GEMM launch of one step, from the committed ncu capture of the same step
+    (profiles/r1e_gemm_dram_traffic*.json; `ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum`).  None if absent."""
+    path = os.path.join(ROOT, "profiles", "r1e_gemm_dram_traffic_multitask.json" if two_heads else "r1e_gemm_dram_traffic.json")
+    try:
+        with open(path) as f:
+            return json.load(f)["avg_dram_bytes_per_launch"]
+    except (OSError, KeyError, ValueError):
+        return None
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
 
@@ -253,7 +264,8 @@ def run_b200(args):
         pk = measured_peaks()
         achieved = fl / tt / 1e12
         roof = {"bound": "tensor", "kernel": "gemm_kernel (tcgen05/TMA; fwd+dgrad+wgrad, all epilogues)", "achieved": achieved,
-                "peak": pk["sustained"], "unit": "TFLOP/s", "frac": achieved / pk["sustained"], "traffic": None,
+                "peak": pk["sustained"], "unit": "TFLOP/s", "frac": achieved / pk["sustained"],
+                "traffic": gemm_dram_traffic(two_heads),
                 "launches_per_step": len(records), "avg_launch_us": tt / len(records) * 1e6,
                 "flops_per_launch": fl / len(records), "gemm_share_of_step": tt / (ms_total * 1e-3 / args.steps),
                 "peak_source": pk["source"] + ", sustained figure (kernel timed inside a long step); burst " + str(pk["burst"])}
