@@ -23,10 +23,11 @@ NUM_SYMBOLS = 188   # len(symbols), probe in SURVEY.md §0
 
 
 def flatten_masked_indices(input_lengths: Sequence[int], masked_indices: Sequence[Sequence[int]],
-                           seq_stride: int) -> Tuple[np.ndarray, np.ndarray]:
+                           seq_stride) -> Tuple[np.ndarray, np.ndarray]:
     """Row selection of R/train.py:123-129 as flat arrays: ``rows[k] = b * seq_stride + i`` in the reference's
     iteration order and ``weights[k] = 1 / (count * n_b)`` where ``count`` is the number of samples with at least
-    one masked index.  int32 / float32, bit-exact index arithmetic."""
+    one masked index.  int32 / float32, bit-exact index arithmetic.  ``seq_stride`` is the padded row length, or an
+    integer array with the first row of every sample (packed layout: ``rows[k] = seq_stride[b] + i``)."""
     # one pass over the python lists, everything else vectorised (the per-sample loop cost 2-5 ms per 192-sample batch)
     B = len(masked_indices)
     counts = np.fromiter((len(m) for m in masked_indices), dtype=np.int64, count=B)
@@ -43,12 +44,14 @@ def flatten_masked_indices(input_lengths: Sequence[int], masked_indices: Sequenc
         raise IndexError(f"masked index out of range for sample {b} (length {int(input_lengths[b])})")
     count = int(np.count_nonzero(counts))                               # samples with at least one masked index
     weights = 1.0 / (count * counts[sample].astype(np.float64))
-    return (flat + sample * seq_stride).astype(np.int32), weights.astype(np.float32)
+    base = sample * int(seq_stride) if np.isscalar(seq_stride) else np.asarray(seq_stride, dtype=np.int64)[sample]
+    return (flat + base).astype(np.int32), weights.astype(np.float32)
 
 
 @dataclass
 class DeviceBatch:
-    """One batch resident in HBM, in the padded [B, L] row layout (row = b * L + j)."""
+    """One batch resident in HBM: padded [B, L] row layout (row = b * L + j) or, with ``packed``, the sequences back to
+    back without padding rows (row = seq_start[b] + j, q_len == kv_len == the sequence length)."""
 
     B: int
     L: int
@@ -63,10 +66,12 @@ class DeviceBatch:
     M: int = 0
     num_valid_tokens: int = 0
     h2d_bytes: int = 0
+    packed: bool = False
+    n_rows: int = -1           # activation rows: B * L (padded) or sum of the lengths (packed)
 
     @property
     def T(self) -> int:
-        return self.B * self.L
+        return self.n_rows if self.n_rows >= 0 else self.B * self.L
 
 
 class BatchStager:
@@ -96,7 +101,10 @@ class BatchStager:
 
     def stage(self, masked_phonemes: torch.Tensor, input_lengths: Sequence[int],
               masked_indices: Optional[Sequence[Sequence[int]]] = None,
-              label_tensors: Sequence[torch.Tensor] = ()) -> DeviceBatch:
+              label_tensors: Sequence[torch.Tensor] = (), packed: bool = False) -> DeviceBatch:
+        """``packed``: drop the padding rows: the sequences are laid out back to back, so every
+        per-token kernel (GEMMs, LayerNorm, attention query tiles) only sees valid tokens.  The reference computes the
+        padded rows and never reads them (R/train.py:125), so the loss and every gradient are unchanged."""
         ids = masked_phonemes
         if ids.dim() != 2:
             raise ValueError("masked_phonemes must be [B, L]")
@@ -104,17 +112,35 @@ class BatchStager:
         lengths = np.asarray([int(x) for x in input_lengths], dtype=np.int32)
         if lengths.shape[0] != B or lengths.min() < 1 or lengths.max() > L:
             raise ValueError("input_lengths must hold one length in [1, L] per sample")
-        T = B * L
-        ids_np = ids.reshape(-1).to(torch.int32).numpy() if ids.device.type == "cpu" else None
+        if packed:
+            starts = np.zeros(B, dtype=np.int64)
+            np.cumsum(lengths[:-1], out=starts[1:])
+            T = int(lengths.sum())
+            sample = np.repeat(np.arange(B, dtype=np.int64), lengths)
+            pos_np = (np.arange(T, dtype=np.int64) - starts[sample]).astype(np.int32)
+            src = sample * L + pos_np                       # padded flat index of every packed row
+        else:
+            starts = np.arange(B, dtype=np.int64) * L
+            T = B * L
+            pos_np = np.tile(np.arange(L, dtype=np.int32), B)
+            src = None
+        on_host = ids.device.type == "cpu"
+        ids_np = None
+        if on_host:
+            ids_np = ids.reshape(-1).to(torch.int32).numpy()
+            if src is not None:
+                ids_np = ids_np[src]
         if masked_indices is not None:
-            rows, weights = flatten_masked_indices(lengths, masked_indices, L)
+            rows, weights = flatten_masked_indices(lengths, masked_indices, starts if packed else L)
+            label_rows = flatten_masked_indices(lengths, masked_indices, L)[0] if packed else rows  # labels are padded [B, L]
         else:
             rows, weights = np.zeros(0, np.int32), np.zeros(0, np.float32)
+            label_rows = rows
         M = rows.shape[0]
         labs = []
         for lt in label_tensors:
             flat = lt.reshape(-1)
-            labs.append(flat[torch.from_numpy(rows.astype(np.int64))].to(torch.int32).cpu().numpy() if M else
+            labs.append(flat[torch.from_numpy(label_rows.astype(np.int64))].to(torch.int32).cpu().numpy() if M else
                         np.zeros(0, np.int32))
         # layout (int32 words): ids[T] | pos[T] | seq_start[B] | q_len[B] | kv_len[B] | rows[M] | weights[M] | labels..
         n = 2 * T + 3 * B + 2 * M + len(labs) * M
@@ -124,9 +150,9 @@ class BatchStager:
         if ids_np is not None:
             host[o:o + T] = ids_np
         o += T
-        host[o:o + T] = np.tile(np.arange(L, dtype=np.int32), B); o += T
-        host[o:o + B] = np.arange(B, dtype=np.int32) * L; o += B
-        host[o:o + B] = L; o += B
+        host[o:o + T] = pos_np; o += T
+        host[o:o + B] = starts.astype(np.int32); o += B
+        host[o:o + B] = lengths if packed else L; o += B
         host[o:o + B] = lengths; o += B
         host[o:o + M] = rows; o += M
         host[o:o + M] = weights.view(np.int32); o += M
@@ -136,20 +162,24 @@ class BatchStager:
         if self._done[slot] is None:
             self._done[slot] = torch.cuda.Event()
         self._done[slot].record()
-        if ids_np is None:  # ids already on the device
-            dev[:T].copy_(ids.reshape(-1).to(torch.int32))
+        if not on_host:  # ids already on the device
+            flat_ids = ids.reshape(-1).to(torch.int32)
+            dev[:T].copy_(flat_ids if src is None else flat_ids[torch.from_numpy(src).to(ids.device)])
         o = 0
         def take(k):
             nonlocal o
             v = dev[o:o + k]; o += k
             return v
-        batch = DeviceBatch(B=B, L=L, ids=take(T), pos=take(T), seq_start=take(B), q_len=take(B), kv_len=take(B))
+        batch = DeviceBatch(B=B, L=int(lengths.max()) if packed else L, ids=take(T), pos=take(T), seq_start=take(B), q_len=take(B),
+                            kv_len=take(B))
         batch.rows = take(M)
         batch.weights = take(M).view(torch.float32)
         batch.labels = [take(M) for _ in labs]
         batch.M = M
         batch.num_valid_tokens = int(lengths.sum())
         batch.h2d_bytes = 4 * n
+        batch.packed = packed
+        batch.n_rows = T
         return batch
 
 

@@ -241,7 +241,7 @@ class Engine:
             A = self.acts[l if train else l % 2]
             self._gemm(GEMM_FWD, EPI_NONE, T, 3 * H, H, x, H, wqkv, H, A["qkv"], 3 * H, bias=bqkv)
             call("plb_attn_fwd_tc", ptr(A["qkv"]), 3 * H, ptr(b.seq_start), ptr(b.q_len), ptr(b.kv_len), b.B, nh, H // nh,
-                 b.L, self._cap_T, ptr(A["ctx"]), H, ptr(A["lse"]), s)
+                 b.L, T, ptr(A["ctx"]), H, ptr(A["lse"]), s)
             self.launches += 1
             self._gemm(GEMM_FWD, EPI_RESIDUAL, T, H, H, A["ctx"], H, self.w(att + "dense.weight"), H, A["z1"], H,
                        bias=self.p(att + "dense.bias"), aux_in=x, ld_in=H)
@@ -353,7 +353,7 @@ class Engine:
             self._gemm(GEMM_WGRAD, EPI_NONE, H, H, T, self.d_z, H, A["ctx"], H, self.g(att + "dense.weight"), H)
             self._gemm(GEMM_DGRAD, EPI_NONE, T, H, H, self.d_z, H, self.w(att + "dense.weight"), H, self.d_ctx, H)
             call("plb_attn_bwd_tc", ptr(A["qkv"]), 3 * H, ptr(b.seq_start), ptr(b.q_len), ptr(b.kv_len), b.B, nh, H // nh, b.L,
-                 self._cap_T, ptr(A["ctx"]), ptr(self.d_ctx), H, ptr(A["lse"]), ptr(self.delta), ptr(self.d_qkv), 3 * H,
+                 T, ptr(A["ctx"]), ptr(self.d_ctx), H, ptr(A["lse"]), ptr(self.delta), ptr(self.d_qkv), 3 * H,
                  ptr(g_bqkv), s)  # also accumulates the QKV bias gradient (column sums of dqkv)
             self._gemm(GEMM_WGRAD, EPI_NONE, 3 * H, H, T, self.d_qkv, 3 * H, x_in, H, g_wqkv, H)
             self._gemm(GEMM_DGRAD, EPI_RESIDUAL, T, H, 3 * H, self.d_qkv, 3 * H, wqkv, H, dy, H, aux_in=self.d_z, ld_in=H)

@@ -100,6 +100,8 @@ class _FullLogitsFn(torch.autograd.Function):
 class _FusedModel(nn.Module):
     _heads: List[str] = []
 
+    pack_sequences = True  # loss_and_backward lays variable-length batches out without padding rows (cu_seqlens style)
+
     def _init_fused(self):
         self._engine: Optional[Engine] = None
         self._stager: Optional[BatchStager] = None
@@ -205,7 +207,9 @@ class _FusedModel(nn.Module):
                 raise _abi.PlbError("MultiTaskModel.loss_and_backward needs the 5-tuple batch with token_ids")
             label_tensors.append(token_ids)
             heads.append("token_predictor")
-        db = self._stager.stage(masked, lengths, midx, label_tensors)
+        # drop the padding rows when there are any: same loss and gradients, fewer tokens to process
+        packed = self.pack_sequences and min(int(x) for x in lengths) < masked.shape[1]
+        db = self._stager.stage(masked, lengths, midx, label_tensors, packed=packed)
         self.last_batch = db
         loss = eng.loss_and_backward(db, heads)
         self._publish_grads()

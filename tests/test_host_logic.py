@@ -34,6 +34,9 @@ def test_flatten_edge_cases():
     assert rows.tolist() == [3, 8, 8] and np.allclose(w, [0.5, 0.25, 0.25])
     with pytest.raises(IndexError):
         B.flatten_masked_indices([4], [[4]], 8)
+    # packed layout: per-sample first rows instead of a common stride
+    rows, w = B.flatten_masked_indices([4, 3, 5], [[1, -1], [], [0]], np.array([0, 4, 7]))
+    assert rows.tolist() == [1, 3, 7] and np.allclose(w, [0.25, 0.25, 0.5])
 
 
 def test_synthetic_batch_contract_and_statistics():

@@ -150,6 +150,29 @@ def test_step_matches_oracle(dev, two_heads, varlen):
     assert all(set(v) == {"step", "exp_avg", "exp_avg_sq"} for v in sd["state"].values())
 
 
+def test_packed_layout_equals_padded_layout(dev):
+    """Variable-length batches run without their padding rows.  The reference computes the padded
+    rows and never reads them, so loss and gradients must not change; only the fp32 summation order of the weight
+    gradients (split-K over a different row count) may."""
+    from plbert_b200.batch import synthetic_collate_batch
+    cfgv = [188, 32, 128, 2, 256, 4, 128, 211]
+    batch = synthetic_collate_batch(6, 128, seed=21, variable_length=True, min_length=9, with_token_ids=True, num_tokens=211,
+                                    word_pred_prob=0.25)
+    out = {}
+    for packed in (False, True):
+        model = build_model(cfgv, True, dev, seed=5)
+        model.pack_sequences = packed
+        loss = model.loss_and_backward(batch)
+        assert model.last_batch.packed == packed
+        if packed:
+            assert model.last_batch.T == sum(batch[3]) < 6 * 128
+        out[packed] = (loss.item(), {n: p.grad.detach().float().clone() for n, p in model.named_parameters() if p.grad is not None})
+    assert abs(out[True][0] - out[False][0]) <= 1e-5 * abs(out[False][0])
+    for n, g in out[False][1].items():
+        ref = g.abs().max().item()
+        assert (out[True][1][n] - g).abs().max().item() <= 2e-3 * ref + 1e-7, n
+
+
 def test_reference_style_forward_backward(dev):
     """Unchanged reference call pattern (R/train.py:381-390, 355-357): full logits -> python loss loop -> backward."""
     import plbert_b200 as P
