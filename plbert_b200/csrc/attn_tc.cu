@@ -45,7 +45,7 @@ struct FwdSmem {
   static constexpr int kP = kQ + 2 * TILE16K;           // output staging [128 x 64] per group (P itself lives in TMEM)
   static constexpr int kBar = kP + 2 * TILE16K;
   // k_full[4], v_full[4], then per group: q_full, q_empty, s_full, s_free, p_ready, pv_done, o_free
-  static constexpr int kNumBars = 2 * MAX_BOXES + 2 * 7;
+  static constexpr int kNumBars = 2 * MAX_BOXES + 2 * 7 + MAX_BOXES;   // ... then kv_free[4]
   static constexpr int kTurn = kBar + kNumBars * 8 + 16;  // 9 words for the exponential-phase turn-taking
   static constexpr int kBytes = kTurn + 48;
   static constexpr int kAlloc = kBytes;  // no slack: the dynamic window is 1024-byte aligned (checked at run time)
@@ -86,6 +86,16 @@ __device__ __forceinline__ float turn_acquire(int grp, int quad, uint32_t c, uin
     asm volatile("bar.sync %1, %3;\n\tld.volatile.shared.f32 %0, [%2];" : "=f"(z) : "r"(3 + grp * 4 + quad), "r"(turn_addr), "n"(kPair) : "memory");
   return z;
 }
+// The same two halves with the decision made by the caller (persistent forward kernel: the alternation runs across items).
+__device__ __forceinline__ float turn_wait(int grp, int quad, uint32_t turn_addr) {
+  float z;
+  asm volatile("bar.sync %1, 64;\n\tld.volatile.shared.f32 %0, [%2];" : "=f"(z) : "r"(3 + grp * 4 + quad), "r"(turn_addr) : "memory");
+  return z;
+}
+__device__ __forceinline__ void turn_signal(int grp, int quad, uint32_t turn_addr, uint32_t result_bits) {
+  asm volatile("st.volatile.shared.b32 [%0], %1;\n\tbar.arrive %2, 64;" ::"r"(turn_addr + 4 + ((threadIdx.x >> 5) - 4) * 4), "r"(result_bits),
+               "r"(3 + (grp ^ 1) * 4 + quad) : "memory");
+}
 template <int kPair = 64>
 __device__ __forceinline__ void turn_release(int grp, int quad, uint32_t c, uint32_t steps0, uint32_t steps1, uint32_t turn_addr,
                                              uint32_t result_bits) {
@@ -113,26 +123,43 @@ __device__ unsigned long long g_trace[TRACE_CAP];
 #define PLB_TRACE(code, idx) do { } while (0)
 #endif
 
+// Work item of a persistent forward CTA: one (sequence, head).
+struct FwdItem {
+  int h, row_base, nq, nk, n_chunks, n_tiles;
+};
+__device__ __forceinline__ FwdItem fwd_item(const AttnTcParams& p, int item) {
+  FwdItem it;
+  const int b = item / p.heads;
+  it.h = item % p.heads;
+  it.row_base = p.seq_start[b];
+  it.nq = p.q_len[b];
+  it.nk = p.kv_len[b];
+  // (lengths are >= 1 by contract; the clamps only keep the roles' barrier bookkeeping consistent on bad input)
+  it.n_chunks = max(1, (it.nk + KC - 1) / KC);  // = K / V boxes of the item
+  it.n_tiles = max(1, (it.nq + QT - 1) / QT);
+  return it;
+}
+
+// PERSISTENT: the grid is one CTA per SM and every CTA walks the items blockIdx.x, blockIdx.x + gridDim.x, ...  All
+// barriers keep running across items, and K / V box j is refilled with the NEXT item's rows as soon as both groups'
+// last tiles of the current item have passed chunk j (kv_free[j]), so the load latency, the pipeline fill and the
+// epilogue of one item overlap the tail / head of its neighbours instead of idling the SM once per (sequence, head).
 __global__ void __launch_bounds__(NUM_THREADS, 1)
-attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const AttnTcParams p, __nv_bfloat16* __restrict__ ctx,
-                   int ld_ctx, float* __restrict__ lse2) {
+attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const AttnTcParams p, int n_items,
+                   __nv_bfloat16* __restrict__ ctx, int ld_ctx, float* __restrict__ lse2) {
   extern __shared__ __align__(1024) uint8_t smem[];
   if (smem_u32(smem) & 1023u) __trap();  // 128-byte swizzle needs 1024-byte aligned tiles
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + FwdSmem::kBar);
   uint64_t* k_full = bars;                      // [4]
   uint64_t* v_full = bars + MAX_BOXES;          // [4]
   uint64_t* gbar = bars + 2 * MAX_BOXES;        // [2][BARS_PER_GROUP]
+  uint64_t* kv_free = gbar + 2 * BARS_PER_GROUP;  // [4]: both groups are done with K_j / V_j of the current item
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + FwdSmem::kNumBars);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   PLB_TRACE_INIT(0);
   PLB_TRACE(0, 0);
-  const int b = blockIdx.x / p.heads, h = blockIdx.x % p.heads;
-  const int row_base = p.seq_start[b], nq = p.q_len[b], nk = p.kv_len[b];
   const int H = p.heads * D;
-  const int n_chunks = (nk + KC - 1) / KC;
-  const int n_boxes = n_chunks;
-  const int n_tiles = (nq + QT - 1) / QT;
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tm_qkv);
@@ -148,6 +175,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const AttnTcParam
       mbar_init(&gb[PV_DONE], 1);
       mbar_init(&gb[O_FREE], 4);
     }
+    for (int j = 0; j < MAX_BOXES; ++j) mbar_init(&kv_free[j], 2);  // one arrive per group's MMA issuer
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc(tmem_ptr_smem, 512);
@@ -162,84 +190,139 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const AttnTcParam
    if (warp == 0) {
     // ====================================== TMA producer ======================================
     if (elect_one_sync()) {
-      for (int g = 0; g < 2 && g < n_tiles; ++g) {
-        uint64_t* gb = gbar + g * BARS_PER_GROUP;
-        mbar_arrive_expect_tx(&gb[Q_FULL], TILE16K);
-        tma_load_2d(smem + FwdSmem::kQ + g * TILE16K, &tm_qkv, &gb[Q_FULL], h * D, row_base + g * QT);
-        if (g == 0) {  // first K box right behind the first Q tile so the first S MMA starts early
-          mbar_arrive_expect_tx(&k_full[0], TILE16K);
-          tma_load_2d(smem + FwdSmem::kK, &tm_qkv, &k_full[0], H + h * D, row_base);
+      uint32_t box_loads[MAX_BOXES] = {0, 0, 0, 0};  // how often box j has been filled so far
+      uint32_t q_loads[2] = {0, 0};                   // Q tiles handed to each group so far
+      FwdItem nxt = blockIdx.x < n_items ? fwd_item(p, blockIdx.x) : FwdItem{};
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const FwdItem it = nxt;
+        if (item + static_cast<int>(gridDim.x) < n_items) nxt = fwd_item(p, item + gridDim.x);
+        auto load_q = [&](int t) {
+          const int g = t & 1;
+          uint64_t* gb = gbar + g * BARS_PER_GROUP;
+          if (q_loads[g] >= 1) mbar_wait(&gb[Q_EMPTY], (q_loads[g] - 1) & 1);  // every S MMA of the group's previous tile has read Q
+          mbar_arrive_expect_tx(&gb[Q_FULL], TILE16K);
+          tma_load_2d(smem + FwdSmem::kQ + g * TILE16K, &tm_qkv, &gb[Q_FULL], it.h * D, it.row_base + t * QT);
+          ++q_loads[g];
+        };
+        auto wait_box = [&](int j) {  // both groups are done with the previous item's K_j / V_j
+          if (box_loads[j] >= 1) mbar_wait(&kv_free[j], (box_loads[j] - 1) & 1);
+          ++box_loads[j];
+        };
+        auto load_k = [&](int j) {
+          mbar_arrive_expect_tx(&k_full[j], TILE16K);
+          tma_load_2d(smem + FwdSmem::kK + j * TILE16K, &tm_qkv, &k_full[j], H + it.h * D, it.row_base + j * 128);
+        };
+        auto load_v = [&](int j) {
+          mbar_arrive_expect_tx(&v_full[j], TILE16K);
+          tma_load_2d(smem + FwdSmem::kV + j * TILE16K, &tm_qkv, &v_full[j], 2 * H + it.h * D, it.row_base + j * 128);
+        };
+        // first Q tile and first K box first so that the first S MMA starts early
+        load_q(0);
+        wait_box(0);
+        load_k(0);
+        if (it.n_tiles > 1) load_q(1);
+        load_v(0);
+        for (int j = 1; j < it.n_chunks; ++j) {
+          wait_box(j);
+          load_k(j);
+          load_v(j);
         }
-      }
-      mbar_arrive_expect_tx(&v_full[0], TILE16K);
-      tma_load_2d(smem + FwdSmem::kV, &tm_qkv, &v_full[0], 2 * H + h * D, row_base);
-      for (int j = 1; j < n_boxes; ++j) {
-        mbar_arrive_expect_tx(&k_full[j], TILE16K);
-        tma_load_2d(smem + FwdSmem::kK + j * TILE16K, &tm_qkv, &k_full[j], H + h * D, row_base + j * 128);
-        mbar_arrive_expect_tx(&v_full[j], TILE16K);
-        tma_load_2d(smem + FwdSmem::kV + j * TILE16K, &tm_qkv, &v_full[j], 2 * H + h * D, row_base + j * 128);
-      }
-      for (int t = 2; t < n_tiles; ++t) {
-        const int g = t & 1, k = t >> 1;  // k-th tile of group g
-        uint64_t* gb = gbar + g * BARS_PER_GROUP;
-        mbar_wait(&gb[Q_EMPTY], (k - 1) & 1);  // every S MMA of the group's previous tile has read Q
-        mbar_arrive_expect_tx(&gb[Q_FULL], TILE16K);
-        tma_load_2d(smem + FwdSmem::kQ + g * TILE16K, &tm_qkv, &gb[Q_FULL], h * D, row_base + t * QT);
+        for (int t = 2; t < it.n_tiles; ++t) load_q(t);
       }
     }
     __syncwarp();
    } else if ((warp == 1 || warp == 2) && elect_one_sync()) {
     // ====================================== MMA issuers: one thread per group ======================================
     // A group's MMAs alternate deterministically — S of chunk c+1 becomes issuable when the group has pulled S_c out of
-    // TMEM, P V of chunk c when P_c is in shared memory — so the issuer blocks on exactly the barrier that is due next.
+    // TMEM, P V of chunk c when P_c is in tensor memory — so the issuer blocks on exactly the barrier that is due next.
     const int g = warp - 1;
-    const int my_tiles = g == 0 ? (n_tiles + 1) >> 1 : n_tiles >> 1;
     constexpr uint32_t idesc_s = umma_idesc_bf16(128, KC, 0, 0);   // S = Q K^T : A K-major, B K-major
-    constexpr uint32_t idesc_o = umma_idesc_bf16(128, D, 0, 1);    // O = P V   : A K-major, B MN-major
+    constexpr uint32_t idesc_o = umma_idesc_bf16(128, D, 0, 1);    // O = P V   : A from TMEM, B MN-major
     uint64_t* gb = gbar + g * BARS_PER_GROUP;
     const uint32_t tmem_sg = tmem_base + g * 256, tmem_og = tmem_sg + 128, tmem_pg = tmem_sg + 192;
     // descriptor bases; the start-address field counts 16-byte units, so advancing is a plain add
     const uint64_t dQ = umma_smem_desc(smem_u32(smem + FwdSmem::kQ + g * TILE16K), 16, 1024);
     const uint64_t dK = umma_smem_desc(smem_u32(smem + FwdSmem::kK), 16, 1024);
     const uint64_t dV = umma_smem_desc(smem_u32(smem + FwdSmem::kV), TILE16K, 1024);
-    const uint32_t total = my_tiles * n_chunks;
-    auto issue_s = [&](int k, int j, uint32_t cn) {  // S_j = Q K_j^T of the group's k-th tile
-      if (j == 0) mbar_wait(&gb[Q_FULL], k & 1);
-      if (k == 0) mbar_wait(&k_full[j], 0);
+    uint32_t box_uses[MAX_BOXES] = {0, 0, 0, 0};  // items that have used box j so far (phase of k_full / v_full)
+    uint32_t kt = 0;                              // tiles of this group so far (phase of Q_FULL / O_FREE)
+    uint32_t c = 0;                               // chunks of this group so far (phase of S_FREE / P_READY)
+    // position of the NEXT S to issue (runs one chunk ahead of the PV stream, across tiles and items)
+    int s_item = blockIdx.x, s_k = 0, s_j = 0;
+    FwdItem s_it = s_item < n_items ? fwd_item(p, s_item) : FwdItem{};
+    uint32_t s_kt = 0;
+    uint32_t s_box_uses[MAX_BOXES] = {0, 0, 0, 0};
+    auto s_tiles = [&]() { return g == 0 ? (s_it.n_tiles + 1) >> 1 : s_it.n_tiles >> 1; };
+    auto s_skip_empty = [&]() {  // advance the S cursor past items in which this group has no tile
+      while (s_item < n_items && s_tiles() == 0) {
+        for (int j = 0; j < s_it.n_chunks; ++j) ++s_box_uses[j];
+        s_item += gridDim.x;
+        if (s_item < n_items) s_it = fwd_item(p, s_item);
+      }
+    };
+    auto issue_s = [&]() {  // S_j = Q K_j^T at the cursor, then advance the cursor
+      if (s_j == 0) mbar_wait(&gb[Q_FULL], s_kt & 1);
+      if (s_k == 0) mbar_wait(&k_full[s_j], s_box_uses[s_j] & 1);
       tc_fence_after();
-      const uint64_t kb = dK + static_cast<uint64_t>(j * (TILE16K >> 4));
+      const uint64_t kb = dK + static_cast<uint64_t>(s_j * (TILE16K >> 4));
 #pragma unroll
       for (int kk = 0; kk < D / 16; ++kk) umma_bf16(tmem_sg, dQ + 2 * kk, kb + 2 * kk, idesc_s, kk > 0);
       umma_commit(&gb[S_FULL]);
-      if (j == n_chunks - 1) umma_commit(&gb[Q_EMPTY]);
-      PLB_TRACE(1, cn);
-    };
-    if (total > 0) issue_s(0, 0, 0);
-    uint32_t c = 0;
-    for (int k = 0; k < my_tiles; ++k) {
-      for (int j = 0; j < n_chunks; ++j, ++c) {
-        const bool has_next = c + 1 < total;
-        const bool next_in_tile = j + 1 < n_chunks;
-        if (has_next && next_in_tile) {
-          mbar_wait(&gb[S_FREE], c & 1);
-          issue_s(k, j + 1, c + 1);
-        }
-        // ---- O += P_j V_j ----
-        mbar_wait(&gb[P_READY], c & 1);
-        if (j == 0) mbar_wait(&gb[O_FREE], (k & 1) ^ 1);
-        if (k == 0) mbar_wait(&v_full[j], 0);
-        tc_fence_after();
-        const uint64_t vb = dV + static_cast<uint64_t>(j * (TILE16K >> 4));
-#pragma unroll
-        for (int kk = 0; kk < KC / 16; ++kk)
-          umma_bf16_tmem_a(tmem_og, tmem_pg + 8 * kk, vb + 128 * kk, idesc_o, (j > 0 || kk > 0));
-        umma_commit(&gb[PV_DONE]);
-        PLB_TRACE(2, c);
-        if (has_next && !next_in_tile) {  // next tile: its Q arrives only after this tile's last S MMA has run
-          mbar_wait(&gb[S_FREE], c & 1);
-          issue_s(k + 1, 0, c + 1);
+      if (s_j == s_it.n_chunks - 1) umma_commit(&gb[Q_EMPTY]);
+      PLB_TRACE(1, s_j);
+      if (++s_j == s_it.n_chunks) {
+        s_j = 0;
+        ++s_kt;
+        if (++s_k == s_tiles()) {
+          s_k = 0;
+          for (int j = 0; j < s_it.n_chunks; ++j) ++s_box_uses[j];
+          s_item += gridDim.x;
+          if (s_item < n_items) s_it = fwd_item(p, s_item);
+          s_skip_empty();
         }
       }
+    };
+    s_skip_empty();
+    if (s_item < n_items) issue_s();
+    FwdItem nxt = blockIdx.x < n_items ? fwd_item(p, blockIdx.x) : FwdItem{};
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+      const FwdItem it = nxt;
+      if (item + static_cast<int>(gridDim.x) < n_items) nxt = fwd_item(p, item + gridDim.x);
+      const int my_tiles = g == 0 ? (it.n_tiles + 1) >> 1 : it.n_tiles >> 1;
+      if (my_tiles == 0) {
+        // this group has nothing to do in the item: release its share of the K / V boxes right away
+        for (int j = 0; j < it.n_chunks; ++j) {
+          mbar_arrive(&kv_free[j]);
+          ++box_uses[j];
+        }
+        continue;
+      }
+      for (int k = 0; k < my_tiles; ++k, ++kt) {
+        for (int j = 0; j < it.n_chunks; ++j, ++c) {
+          const bool next_in_tile = j + 1 < it.n_chunks;
+          if (next_in_tile) {
+            mbar_wait(&gb[S_FREE], c & 1);
+            issue_s();
+          }
+          // ---- O += P_j V_j ----
+          mbar_wait(&gb[P_READY], c & 1);
+          if (j == 0) mbar_wait(&gb[O_FREE], (kt & 1) ^ 1);
+          if (k == 0) mbar_wait(&v_full[j], box_uses[j] & 1);
+          tc_fence_after();
+          const uint64_t vb = dV + static_cast<uint64_t>(j * (TILE16K >> 4));
+#pragma unroll
+          for (int kk = 0; kk < KC / 16; ++kk)
+            umma_bf16_tmem_a(tmem_og, tmem_pg + 8 * kk, vb + 128 * kk, idesc_o, (j > 0 || kk > 0));
+          umma_commit(&gb[PV_DONE]);
+          if (k == my_tiles - 1) umma_commit(&kv_free[j]);  // this group's last use of K_j / V_j in the item
+          PLB_TRACE(2, c);
+          if (!next_in_tile && s_item < n_items) {  // next tile (possibly of the next item): its Q arrives after this tile's last S
+            mbar_wait(&gb[S_FREE], c & 1);
+            issue_s();
+          }
+        }
+      }
+      for (int j = 0; j < it.n_chunks; ++j) ++box_uses[j];
     }
    }
   } else {
@@ -255,12 +338,23 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const AttnTcParam
     uint64_t* gb = gbar + grp * BARS_PER_GROUP;
     const uint32_t sPg = smem_u32(smem + FwdSmem::kP + grp * TILE16K);  // output staging of the group
     const uint32_t sP_row = sPg + row * 128;
-    uint32_t c = 0;  // chunk counter of this group (phase of s_full / s_free / p_ready / pv_done)
+    uint32_t c = 0;  // chunk counter of this group over all items (phase of s_full / s_free / p_ready / pv_done)
     const uint32_t turn_zero = smem_u32(smem + FwdSmem::kTurn);  // one zero word, then one sink word per softmax warp
-    const uint32_t steps0 = ((n_tiles + 1) >> 1) * n_chunks, steps1 = (n_tiles >> 1) * n_chunks;  // chunks per group
-    for (int t = grp; t < n_tiles; t += 2) {
+    bool prev_even = false;  // the previous item gave both groups the same number of chunks (so group 1 ran last)
+    FwdItem nxt = blockIdx.x < n_items ? fwd_item(p, blockIdx.x) : FwdItem{};
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+     const FwdItem it = nxt;
+     const bool has_next_item = item + static_cast<int>(gridDim.x) < n_items;
+     if (has_next_item) nxt = fwd_item(p, item + gridDim.x);  // its three scalar loads are in flight during this item
+     const int h = it.h, row_base = it.row_base, nq = it.nq, nk = it.nk, n_chunks = it.n_chunks, n_tiles = it.n_tiles;
+     const uint32_t steps0 = ((n_tiles + 1) >> 1) * n_chunks, steps1 = (n_tiles >> 1) * n_chunks;  // chunks per group in this item
+     uint32_t ci = 0;  // chunk counter within the item
+     // Exponential phases alternate g0, g1, g0, g1, ... within an item (g0 has the extra ones of an odd tile) and the
+     // alternation continues across items: g0's first step waits for g1's last step of the previous item when that item
+     // ended on g1, which g1 signals only if a next item exists.
+     for (int t = grp; t < n_tiles; t += 2) {
       float m_used = -INFINITY, l_run = 0.f;
-      for (int j = 0; j < n_chunks; ++j, ++c) {
+      for (int j = 0; j < n_chunks; ++j, ++c, ++ci) {
         mbar_wait(&gb[S_FULL], c & 1);
         tc_fence_after();
         PLB_TRACE(10, c);
@@ -312,12 +406,12 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const AttnTcParam
           }
         }
         // P = exp2(S*k - m) -> bf16, packed in registers FIRST: the exponentials then overlap the previous PV MMA,
-        // which still reads the group's single P buffer; only the stores wait for it.
+        // which still reads the group's P columns; only the TMEM stores wait for it.
         float ls[2] = {0.f, 0.f};
         float mneg = -m_used;
         PLB_TRACE(12, c);
         uint32_t pk[KC / 2];
-        mneg += turn_acquire(grp, quad, c, steps1, turn_zero);
+        if (grp == 0 ? (ci >= 1 ? ci - 1 < steps1 : prev_even) : true) mneg += turn_wait(grp, quad, turn_zero);
         PLB_TRACE(13, c);
 #pragma unroll
         for (int cc = 0; cc < KC / 8; ++cc) {  // sixteen 16-byte pieces = 128 keys (masked keys: exp2(-inf) = 0)
@@ -328,7 +422,8 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const AttnTcParam
           pk[cc * 4 + 0] = pack_bf16x2(e[0], e[1]); pk[cc * 4 + 1] = pack_bf16x2(e[2], e[3]);
           pk[cc * 4 + 2] = pack_bf16x2(e[4], e[5]); pk[cc * 4 + 3] = pack_bf16x2(e[6], e[7]);
         }
-        turn_release(grp, quad, c, steps0, steps1, turn_zero, __float_as_uint(ls[0] + ls[1]));
+        if (grp == 0 ? (ci < steps1) : (ci + 1 < steps0 || (steps1 == steps0 && has_next_item)))
+          turn_signal(grp, quad, turn_zero, __float_as_uint(ls[0] + ls[1]));
         PLB_TRACE(14, c);
         if (c >= 1) mbar_wait(&gb[PV_DONE], (c - 1) & 1);  // the previous PV has finished reading the P columns
         PLB_TRACE(15, c);
@@ -343,8 +438,8 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const AttnTcParam
         if (lane == 0) mbar_arrive(&gb[P_READY]);
         PLB_TRACE(16, c);
       }
-      // ---- epilogue of the tile: O / l -> bf16 -> staging (the group's P buffer) -> global; LSE ----
-      mbar_wait(&gb[PV_DONE], (c - 1) & 1);  // all PV MMAs of the tile are complete: O final, P buffer dead
+      // ---- epilogue of the tile: O / l -> bf16 -> staging -> global; LSE ----
+      mbar_wait(&gb[PV_DONE], (c - 1) & 1);  // all PV MMAs of the tile are complete: O final
       tc_fence_after();
       PLB_TRACE(20, t);
       const float inv = 1.f / l_run;
@@ -379,8 +474,10 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const AttnTcParam
           *reinterpret_cast<uint4*>(ctx + static_cast<size_t>(row_base + t * QT + r) * ld_ctx + h * D + cc * 8) = v;
         }
       }
-      group_bar_sync(grp);  // staging fully read before the next tile's P overwrites it
+      group_bar_sync(grp);  // staging fully read before the next tile overwrites it
       PLB_TRACE(21, t);
+     }
+     prev_even = steps1 == steps0;
     }
   }
   tc_fence_before();
@@ -415,8 +512,9 @@ extern "C" int plb_attn_fwd_tc(const void* qkv, int ld_qkv, const int32_t* seq_s
   }
   AttnTcParams p{seq_start, q_len, kv_len, heads, total_rows, 1.4426950408889634f / sqrtf((float)head_dim),
                  1.f / sqrtf((float)head_dim)};
-  attn_fwd_tc_kernel<<<B * heads, NUM_THREADS, FwdSmem::kAlloc, static_cast<cudaStream_t>(stream)>>>(
-      tm, p, static_cast<__nv_bfloat16*>(ctx), ld_ctx, lse2);
+  const int n_items = B * heads, sms = sm_count();
+  attn_fwd_tc_kernel<<<n_items < sms ? n_items : sms, NUM_THREADS, FwdSmem::kAlloc, static_cast<cudaStream_t>(stream)>>>(
+      tm, p, n_items, static_cast<__nv_bfloat16*>(ctx), ld_ctx, lse2);
   return check_launch("plb_attn_fwd_tc");
 }
 
