@@ -38,14 +38,15 @@ constexpr int REGS_CONTROL = 56;            // setmaxnreg budgets: TMA / MMA war
 constexpr int REGS_SOFTMAX = 224;           // ... and the two softmax warpgroups (128*56 + 256*224 <= 64 K registers)
 constexpr float RESCALE_THRESHOLD = 8.0f;   // log2 units
 
+constexpr int BARS_PER_GROUP_FWD = 9;  // q_full[2], q_empty[2], s_full, s_free, p_ready, pv_done, o_free
 struct FwdSmem {
   static constexpr int kK = 0;
   static constexpr int kV = kK + MAX_BOXES * TILE16K;
-  static constexpr int kQ = kV + MAX_BOXES * TILE16K;   // one Q tile per group
-  static constexpr int kP = kQ + 2 * TILE16K;           // output staging [128 x 64] per group (P itself lives in TMEM)
+  static constexpr int kQ = kV + MAX_BOXES * TILE16K;   // two Q tiles per group (the next tile is prefetched)
+  static constexpr int kP = kQ + 4 * TILE16K;           // output staging [128 x 64] per group (P itself lives in TMEM)
   static constexpr int kBar = kP + 2 * TILE16K;
   // k_full[4], v_full[4], then per group: q_full, q_empty, s_full, s_free, p_ready, pv_done, o_free
-  static constexpr int kNumBars = 2 * MAX_BOXES + 2 * 7 + MAX_BOXES;   // ... then kv_free[4]
+  static constexpr int kNumBars = 2 * MAX_BOXES + 2 * BARS_PER_GROUP_FWD + MAX_BOXES;   // ... then kv_free[4]
   static constexpr int kTurn = kBar + kNumBars * 8 + 16;  // 9 words for the exponential-phase turn-taking
   static constexpr int kBytes = kTurn + 48;
   static constexpr int kAlloc = kBytes;  // no slack: the dynamic window is 1024-byte aligned (checked at run time)
@@ -62,7 +63,8 @@ struct AttnTcParams {
   float scale;       // 1 / sqrt(d)
 };
 
-enum { Q_FULL = 0, Q_EMPTY, S_FULL, S_FREE, P_READY, PV_DONE, O_FREE, BARS_PER_GROUP };
+enum { Q_FULL = 0, Q_FULL1, Q_EMPTY, Q_EMPTY1, S_FULL, S_FREE, P_READY, PV_DONE, O_FREE, BARS_PER_GROUP };  // Q: two slots per group
+static_assert(BARS_PER_GROUP == BARS_PER_GROUP_FWD, "barrier layout");
 
 __device__ __forceinline__ void group_bar_sync(int grp) { asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory"); }
 __device__ __forceinline__ void group_bar_sync256(int grp) { asm volatile("bar.sync %0, 256;" ::"r"(1 + grp) : "memory"); }
@@ -167,8 +169,10 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const AttnTcParam
     for (int i = 0; i < 2 * MAX_BOXES; ++i) mbar_init(&bars[i], 1);
     for (int g = 0; g < 2; ++g) {
       uint64_t* gb = gbar + g * BARS_PER_GROUP;
-      mbar_init(&gb[Q_FULL], 1);
-      mbar_init(&gb[Q_EMPTY], 1);
+      for (int sl = 0; sl < 2; ++sl) {
+        mbar_init(&gb[Q_FULL + sl], 1);
+        mbar_init(&gb[Q_EMPTY + sl], 1);
+      }
       mbar_init(&gb[S_FULL], 1);
       mbar_init(&gb[S_FREE], 4);    // one arrive per softmax warp
       mbar_init(&gb[P_READY], 4);
@@ -199,9 +203,10 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const AttnTcParam
         auto load_q = [&](int t) {
           const int g = t & 1;
           uint64_t* gb = gbar + g * BARS_PER_GROUP;
-          if (q_loads[g] >= 1) mbar_wait(&gb[Q_EMPTY], (q_loads[g] - 1) & 1);  // every S MMA of the group's previous tile has read Q
-          mbar_arrive_expect_tx(&gb[Q_FULL], TILE16K);
-          tma_load_2d(smem + FwdSmem::kQ + g * TILE16K, &tm_qkv, &gb[Q_FULL], it.h * D, it.row_base + t * QT);
+          const uint32_t n = q_loads[g], sl = n & 1;  // two Q slots per group: the tile after the current one is prefetched
+          if (n >= 2) mbar_wait(&gb[Q_EMPTY + sl], ((n >> 1) - 1) & 1);  // every S MMA of the slot's previous tile has read Q
+          mbar_arrive_expect_tx(&gb[Q_FULL + sl], TILE16K);
+          tma_load_2d(smem + FwdSmem::kQ + (g * 2 + sl) * TILE16K, &tm_qkv, &gb[Q_FULL + sl], it.h * D, it.row_base + t * QT);
           ++q_loads[g];
         };
         auto wait_box = [&](int j) {  // both groups are done with the previous item's K_j / V_j
@@ -241,7 +246,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const AttnTcParam
     uint64_t* gb = gbar + g * BARS_PER_GROUP;
     const uint32_t tmem_sg = tmem_base + g * 256, tmem_og = tmem_sg + 128, tmem_pg = tmem_sg + 192;
     // descriptor bases; the start-address field counts 16-byte units, so advancing is a plain add
-    const uint64_t dQ = umma_smem_desc(smem_u32(smem + FwdSmem::kQ + g * TILE16K), 16, 1024);
+    const uint64_t dQ = umma_smem_desc(smem_u32(smem + FwdSmem::kQ + g * 2 * TILE16K), 16, 1024);  // slot 0; slot 1 is 16 KB further
     const uint64_t dK = umma_smem_desc(smem_u32(smem + FwdSmem::kK), 16, 1024);
     const uint64_t dV = umma_smem_desc(smem_u32(smem + FwdSmem::kV), TILE16K, 1024);
     uint32_t box_uses[MAX_BOXES] = {0, 0, 0, 0};  // items that have used box j so far (phase of k_full / v_full)
@@ -261,14 +266,15 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const AttnTcParam
       }
     };
     auto issue_s = [&]() {  // S_j = Q K_j^T at the cursor, then advance the cursor
-      if (s_j == 0) mbar_wait(&gb[Q_FULL], s_kt & 1);
+      const uint32_t sl = s_kt & 1;
+      if (s_j == 0) mbar_wait(&gb[Q_FULL + sl], (s_kt >> 1) & 1);
       if (s_k == 0) mbar_wait(&k_full[s_j], s_box_uses[s_j] & 1);
       tc_fence_after();
-      const uint64_t kb = dK + static_cast<uint64_t>(s_j * (TILE16K >> 4));
+      const uint64_t kb = dK + static_cast<uint64_t>(s_j * (TILE16K >> 4)), qb = dQ + static_cast<uint64_t>(sl * (TILE16K >> 4));
 #pragma unroll
-      for (int kk = 0; kk < D / 16; ++kk) umma_bf16(tmem_sg, dQ + 2 * kk, kb + 2 * kk, idesc_s, kk > 0);
+      for (int kk = 0; kk < D / 16; ++kk) umma_bf16(tmem_sg, qb + 2 * kk, kb + 2 * kk, idesc_s, kk > 0);
       umma_commit(&gb[S_FULL]);
-      if (s_j == s_it.n_chunks - 1) umma_commit(&gb[Q_EMPTY]);
+      if (s_j == s_it.n_chunks - 1) umma_commit(&gb[Q_EMPTY + sl]);
       PLB_TRACE(1, s_j);
       if (++s_j == s_it.n_chunks) {
         s_j = 0;
