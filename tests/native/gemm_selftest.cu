@@ -197,6 +197,11 @@ int main(int argc, char** argv) {
     perf_case("wgrad o", PLB_GEMM_WGRAD, PLB_EPI_NONE, 768, 768, T);
     perf_case("wgrad ffn1", PLB_GEMM_WGRAD, PLB_EPI_NONE, 2048, 768, T);
     perf_case("wgrad ffn2", PLB_GEMM_WGRAD, PLB_EPI_NONE, 768, 2048, T);
+    // the 64 k token head on the masked rows of one batch (M = 11421 rows)
+    const int Mr = 11421, Vt = 64000;
+    perf_case("fwd token head (bias)", PLB_GEMM_FWD, PLB_EPI_NONE, Mr, Vt, 768);
+    perf_case("dgrad token head", PLB_GEMM_DGRAD, PLB_EPI_NONE, Mr, 768, Vt);
+    perf_case("wgrad token head", PLB_GEMM_WGRAD, PLB_EPI_NONE, Vt, 768, Mr);
   }
   return g_fail ? 1 : 0;
 }
