@@ -7,7 +7,8 @@ One "step" = forward + masked-row loss (both heads) + backward + gradient all-re
 of BASELINE.json configs[1]: ALBERT-base from R/configs/config.yml (hidden 768, 12 shared layers, 12 heads, FFN 2048,
 vocab 188), bf16, 192 x 512 synthetic phoneme tokens per GPU with the reference's whole-word 15 % masking.
 ``value`` counts valid phoneme tokens per second over all ranks with the batch already resident in HBM; ``e2e`` is
-the same step through the public API from host (pinned) buffers including the loss read-back.
+the same step through the public API (``BatchFeeder.step`` + ``FusedAdamW.step`` + ``loss.item()``) from host buffers:
+every step flattens its collate tuple, copies it pinned -> device and reads the loss back.
 ``--impl reference`` times the CPU port of the reference step (oracle/reference_port.py) on the host cores.
 """
 from __future__ import annotations
@@ -223,8 +224,14 @@ def run_b200(args):
     value = total_tokens / (ms_total * 1e-3)
 
     # ---- end to end through the public API: host batch -> pinned -> H2D -> step -> loss D2H ---------------
+    # BatchFeeder = the input pipeline of the public API: step i runs on the batch staged during step i-1 and stages
+    # batch i+1 (host flatten -> pinned buffer -> H2D) while the GPU works; every step still uploads its own batch.
+    import itertools
+    from plbert_b200.batch import BatchFeeder
+    feed = BatchFeeder(model, (host_batches[i % n_batches] for i in itertools.count()))
+
     def api_step(i):
-        loss = model.loss_and_backward(host_batches[i % n_batches])
+        loss = feed.step()
         opt.step()
         return loss.item()
 

@@ -4,13 +4,15 @@ Public surface (mirrors the reference, Fadi987/PL-BERT):
   MultiTaskModel, PhonemeOnlyModel   drop-ins for R/model.py
   FusedAdamW                         drop-in for torch.optim.AdamW as used at R/train.py:272
   train.process_batch / length_to_mask / save_checkpoint / load_checkpoint / find_latest_checkpoint
+  BatchFeeder                        look-ahead input staging (host flatten + pinned H2D of batch i+1 under step i)
   ddp.GradientSynchronizer           bucketed NCCL gradient all-reduce overlapped with backward
 The compute lives in libplbert_b200.so (hand-written CUDA, C ABI in include/plbert_b200.h); importing this
 package does not need a GPU, computing with it does — there is no CPU fallback.
 """
 from . import _abi
 from ._abi import PlbError
+from .batch import BatchFeeder
 from .model import MultiTaskModel, PhonemeOnlyModel, normalize_state_dict_keys
 from .optim import FusedAdamW
 
-__all__ = ["MultiTaskModel", "PhonemeOnlyModel", "FusedAdamW", "PlbError", "normalize_state_dict_keys", "_abi"]
+__all__ = ["MultiTaskModel", "PhonemeOnlyModel", "FusedAdamW", "BatchFeeder", "PlbError", "normalize_state_dict_keys", "_abi"]

@@ -68,6 +68,7 @@ class DeviceBatch:
     h2d_bytes: int = 0
     packed: bool = False
     n_rows: int = -1           # activation rows: B * L (padded) or sum of the lengths (packed)
+    heads: List[str] = field(default_factory=list)   # head of every entry of ``labels`` (set by model.stage_batch)
 
     @property
     def T(self) -> int:
@@ -181,6 +182,49 @@ class BatchStager:
         batch.packed = packed
         batch.n_rows = T
         return batch
+
+
+class BatchFeeder:
+    """Input pipeline off the critical path: keeps one batch staged ahead of the step that runs.
+
+    The reference pulls a batch, builds masks on the CPU and copies with blocking pageable transfers before every step
+    (R/train.py:350-353, 383-386; ``num_workers=0`` at :253), so the GPU idles while the host prepares inputs.  Here
+    ``step()`` enqueues the kernels of step i on the batch that was staged during step i-1, then flattens / pins /
+    uploads batch i+1 while the GPU is busy, and only then hands the loss back — by the time the caller reads it
+    (``loss.item()``) the next batch is already resident::
+
+        feed = BatchFeeder(model, loader)
+        while not feed.exhausted:
+            loss = feed.step(); optimizer.step(); print(loss.item())
+
+    Every batch still takes its own pinned-memory H2D copy; nothing is cached."""
+
+    def __init__(self, model, batches):
+        self.model = model
+        self._it = iter(batches)
+        self._staged: Optional[DeviceBatch] = None
+        self._advance()
+
+    def _advance(self) -> None:
+        try:
+            host = next(self._it)
+        except StopIteration:
+            self._staged = None
+            return
+        self._staged = self.model.stage_batch(host)
+
+    @property
+    def exhausted(self) -> bool:
+        return self._staged is None
+
+    def step(self) -> torch.Tensor:
+        """forward + loss + backward on the staged batch (R/train.py:353-356), then stage the next one."""
+        if self._staged is None:
+            raise StopIteration("BatchFeeder: the batch iterable is exhausted")
+        cur = self._staged
+        loss = self.model.loss_and_backward(cur)
+        self._advance()
+        return loss
 
 
 def synthetic_collate_batch(batch_size: int, max_seq_length: int = 512, seed: int = 1234, *,

@@ -30,8 +30,19 @@ constexpr int B_TILE_BYTES = BN * BK * 2;       // 32 KB (one CTA) or 16 KB per 
 constexpr int EPI_COLS = 64;                    // columns per epilogue chunk (128 B of bf16)
 constexpr int EPI_BUF_BYTES = BM * EPI_COLS * 2;  // 16 KB
 constexpr int MN_BOX_BYTES = 64 * 64 * 2;       // one MN-major TMA box: 64 K-rows x 64 elements
-constexpr int NUM_THREADS = 192;
-constexpr int EPI_THREADS = 128;
+// Epilogue warps: EPI_GROUPS groups of four warps (one per TMEM lane quadrant).  With two groups the warps that share a
+// quadrant (and an SM sub-partition scheduler) split every 64-column chunk into 32-column halves, so tcgen05.ld / LDS /
+// MUFU latencies of one warp hide behind the other (the single-group epilogue left the scheduler idle 61 % of the cycles,
+// profiles/r1e_gemm_ncu_full_details.txt).  -DPLB_EPI_GROUPS=1 rebuilds the single-group kernel for A/B runs.
+#ifndef PLB_EPI_GROUPS
+#define PLB_EPI_GROUPS 2
+#endif
+constexpr int EPI_GROUPS = PLB_EPI_GROUPS;
+static_assert(EPI_GROUPS == 1 || EPI_GROUPS == 2, "one or two epilogue warp groups");
+constexpr int EPI_THREADS = 128 * EPI_GROUPS;
+constexpr int NUM_THREADS = 64 + EPI_THREADS;
+constexpr int GRP_COLS = EPI_COLS / EPI_GROUPS;   // columns of a chunk one thread handles
+constexpr int GRP_PIECES = GRP_COLS / 8;          // 16-byte pieces of a staged row one thread handles
 constexpr int TMEM_COLS = 512;
 
 enum Epi : int { kNone = 0, kResidual = 1, kGelu = 2, kGeluBwd = 3, kAtomicF32 = 4 };
@@ -109,7 +120,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CU
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
-      mbar_init(&tmem_empty[i], 4 * kCta);  // one arrive per epilogue warp of every CTA of the pair
+      mbar_init(&tmem_empty[i], 4 * EPI_GROUPS * kCta);  // one arrive per epilogue warp of every CTA of the pair
     }
     for (int i = 0; i < kBufs; ++i) mbar_init(&epi_in[i], 1);
     fence_mbar_init();
@@ -213,8 +224,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CU
     }
     __syncwarp();
   } else {
-    // =========================== epilogue (warps 2..5) ===========================
+    // =========================== epilogue (warps 2..) ===========================
     const int quad = warp & 3;             // TMEM lane quadrant this warp may read
+    const int grp = (warp - 2) >> 2;       // which column half of every chunk this warp handles (0 with one group)
     const int row = quad * 32 + lane;      // accumulator row owned by this thread
     const bool leader = (threadIdx.x == 64);
     uint8_t* epi_smem = smem + L::kEpiOff;
@@ -277,7 +289,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CU
       if (kEpi == kAtomicF32) {
         const int m = m0 + row;
 #pragma unroll 1
-        for (int c = 0; c < BN / 32; ++c) {
+        for (int c = grp; c < BN / 32; c += EPI_GROUPS) {
           if (n0 + c * 32 >= p.N) break;
           uint32_t v[32];
           tmem_ld_32x32(taddr + c * 32, v);
@@ -310,16 +322,18 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CU
           const uint32_t my_row = smem_u32(buf) + row * 128;
 
           uint32_t v0[32], v1[32];
-          tmem_ld_32x32(taddr + c * EPI_COLS, v0);
-          tmem_ld_32x32(taddr + c * EPI_COLS + 32, v1);
+          tmem_ld_32x32(taddr + c * EPI_COLS + grp * GRP_COLS, v0);
+          if constexpr (EPI_GROUPS == 1) tmem_ld_32x32(taddr + c * EPI_COLS + 32, v1);
           if (kHasAuxIn) mbar_wait(&epi_in[slot], (seq / kSlots) & 1);
           tmem_ld_wait();
 
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {  // eight 16-byte pieces of this thread's 128-byte row
+          for (int jl = 0; jl < GRP_PIECES; ++jl) {  // this thread's 16-byte pieces of its 128-byte staged row
+            const int j = grp * GRP_PIECES + jl;
             float f[8];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(j < 4 ? v0[j * 8 + i] : v1[(j - 4) * 8 + i]);
+            for (int i = 0; i < 8; ++i)
+              f[i] = __uint_as_float((EPI_GROUPS == 2 || jl < 4) ? v0[(jl & 3) * 8 + i] : v1[(jl & 3) * 8 + i]);
             if (p.bias != nullptr) {
               const float4 b0 = lds128_ro(s_bias_addr + (c * EPI_COLS + j * 8) * 4);
               const float4 b1 = lds128_ro(s_bias_addr + (c * EPI_COLS + j * 8 + 4) * 4);

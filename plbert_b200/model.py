@@ -186,20 +186,17 @@ class _FusedModel(nn.Module):
         return hidden.view(batch.B, batch.L, -1).clone()  # the workspace is reused by the next call
 
     # ------------------------------------------------------------------ fused training step
-    def loss_and_backward(self, batch: Sequence) -> torch.Tensor:
-        """R/train.py:381-390 ``process_batch`` + ``loss.backward()`` in one call.
-
-        ``batch`` is the collate tuple: ``(phoneme_labels, masked_phonemes, input_lengths, masked_indices)`` or, with
-        token ids, ``(token_ids, phoneme_labels, masked_phonemes, input_lengths, masked_indices)``.  Returns the loss
-        (mean over non-empty samples of the per-sample mean CE over masked rows; heads summed) as a device scalar and
-        leaves the gradients in ``p.grad``."""
+    def stage_batch(self, batch: Sequence) -> DeviceBatch:
+        """Host half of ``loss_and_backward``: flatten the collate tuple into the integer arrays the kernels read, fill one
+        pinned buffer and enqueue its H2D copy (asynchronous).  Calling it for batch i+1 right after the kernels of step i
+        have been enqueued hides the host work behind the GPU (``plbert_b200.batch.BatchFeeder`` does exactly that)."""
         if len(batch) == 5:
             token_ids, labels, masked, lengths, midx = batch
         else:
             labels, masked, lengths, midx = batch
             token_ids = None
         device = next(self.parameters()).device
-        eng = self._ensure_engine(device)
+        self._ensure_engine(device)
         label_tensors = [labels]
         heads = ["phoneme_predictor"]
         if "token_predictor" in self._heads:
@@ -210,8 +207,22 @@ class _FusedModel(nn.Module):
         # drop the padding rows when there are any: same loss and gradients, fewer tokens to process
         packed = self.pack_sequences and min(int(x) for x in lengths) < masked.shape[1]
         db = self._stager.stage(masked, lengths, midx, label_tensors, packed=packed)
+        db.heads = heads
+        return db
+
+    def loss_and_backward(self, batch) -> torch.Tensor:
+        """R/train.py:381-390 ``process_batch`` + ``loss.backward()`` in one call.
+
+        ``batch`` is the collate tuple: ``(phoneme_labels, masked_phonemes, input_lengths, masked_indices)`` or, with
+        token ids, ``(token_ids, phoneme_labels, masked_phonemes, input_lengths, masked_indices)`` — or a ``DeviceBatch``
+        already staged by ``stage_batch``.  Returns the loss (mean over non-empty samples of the per-sample mean CE over
+        masked rows; heads summed) as a device scalar and leaves the gradients in ``p.grad``."""
+        db = batch if isinstance(batch, DeviceBatch) else self.stage_batch(batch)
+        if not db.heads:
+            raise _abi.PlbError("loss_and_backward needs a batch staged with labels (stage_batch)")
+        eng = self._ensure_engine(db.ids.device)
         self.last_batch = db
-        loss = eng.loss_and_backward(db, heads)
+        loss = eng.loss_and_backward(db, db.heads)
         self._publish_grads()
         return loss
 

@@ -173,6 +173,44 @@ def test_packed_layout_equals_padded_layout(dev):
         assert (out[True][1][n] - g).abs().max().item() <= 2e-3 * ref + 1e-7, n
 
 
+def test_batch_feeder_matches_direct_calls(dev):
+    """The look-ahead input pipeline stages batch i+1 while step i runs; it must feed every step the
+    same integers as staging each batch right before its own step: the first loss is bit-identical (same weights, and the
+    forward pass is deterministic), later ones differ only through the fp32 atomic summation order of the gradients."""
+    import plbert_b200 as P
+    from plbert_b200.batch import BatchFeeder, synthetic_collate_batch
+    cfgv = [188, 32, 128, 2, 256, 2, 128, 211]
+    batches = [synthetic_collate_batch(4, 128, seed=30 + i, variable_length=(i == 1), min_length=9, with_token_ids=True,
+                                       num_tokens=211, word_pred_prob=0.25) for i in range(3)]
+    out = []
+    for fed in (False, True):
+        model = build_model(cfgv, True, dev, seed=6)
+        build_ref = {n: p.detach().clone() for n, p in model.named_parameters()}
+        opt = P.FusedAdamW(model.parameters(), lr=7e-5)
+        losses = []
+        if fed:
+            feed = BatchFeeder(model, batches)
+            while not feed.exhausted:
+                loss = feed.step()
+                opt.step()
+                losses.append(loss.item())
+            with pytest.raises(StopIteration):
+                feed.step()
+        else:
+            for b in batches:
+                loss = model.loss_and_backward(b)
+                opt.step()
+                losses.append(loss.item())
+        out.append((losses, {n: p.detach().clone() for n, p in model.named_parameters()}))
+    assert out[0][0][0] == out[1][0][0]
+    assert np.allclose(out[0][0], out[1][0], rtol=1e-4, atol=0)
+    for n, p in out[0][1].items():
+        assert (p - out[1][1][n]).abs().max().item() <= 3 * 7e-5, n   # three AdamW steps move an element by <= 3 lr
+        if "pooler" in n or "key.bias" in n:   # never updated / true gradient identically zero
+            continue
+        assert cosine((p - build_ref[n]).cpu().numpy(), (out[1][1][n] - build_ref[n]).cpu().numpy()) > 0.9, n
+
+
 def test_reference_style_forward_backward(dev):
     """Unchanged reference call pattern (R/train.py:381-390, 355-357): full logits -> python loss loop -> backward."""
     import plbert_b200 as P
