@@ -334,6 +334,64 @@ __device__ __forceinline__ float gelu_new_grad(float u) {
   return 0.5f * (1.0f + t) + 0.5f * u * (1.0f - t * t) * c * (1.0f + 0.134145f * u2);
 }
 
+// ---- packed fp32 pairs (Blackwell FFMA2 / FMUL2 / FADD2: one issue slot for two lanes of work) -------------------
+// The GEMM epilogues are issue-bound (one or two warps per scheduler), so the element-wise math runs on register pairs.
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 f2_pack(float lo, float hi) {
+  f32x2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void f2_unpack(f32x2 v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ f32x2 f2_splat(float x) { return f2_pack(x, x); }
+__device__ __forceinline__ f32x2 f2_fma(f32x2 a, f32x2 b, f32x2 c) {
+  f32x2 d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ f32x2 f2_mul(f32x2 a, f32x2 b) {
+  f32x2 d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ f32x2 f2_add(f32x2 a, f32x2 b) {
+  f32x2 d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ f32x2 f2_from_bf16x2(uint32_t w) { return f2_pack(bf16_lo(w), bf16_hi(w)); }
+__device__ __forceinline__ uint32_t f2_to_bf16x2(f32x2 v) {
+  float lo, hi;
+  f2_unpack(v, lo, hi);
+  return pack_bf16x2(lo, hi);
+}
+__device__ __forceinline__ f32x2 f2_tanh(f32x2 v) {
+  float lo, hi;
+  f2_unpack(v, lo, hi);
+  return f2_pack(tanh_fast(lo), tanh_fast(hi));
+}
+// gelu_new on a pair: 0.5 u (1 + tanh(c u (1 + k u^2)))  — 5 packed ops + 2 MUFU
+__device__ __forceinline__ f32x2 gelu_new_fwd_x2(f32x2 u) {
+  const float c = 0.7978845608028654f, k = 0.044715f;
+  const f32x2 u2 = f2_mul(u, u);
+  const f32x2 t = f2_tanh(f2_mul(u, f2_fma(u2, f2_splat(c * k), f2_splat(c))));
+  const f32x2 hu = f2_mul(u, f2_splat(0.5f));
+  return f2_fma(hu, t, hu);
+}
+// d gelu_new / du on a pair: r + w (1 - t^2) with r = 0.5 (1 + t), w = u (0.5 c + 1.5 c k u^2), evaluated as
+// t^2 (-w) + (r - (-w))  — 9 packed ops + 2 MUFU (the scalar form compiled to 14 FP instructions per element)
+__device__ __forceinline__ f32x2 gelu_new_grad_x2(f32x2 u) {
+  const float c = 0.7978845608028654f, k = 0.044715f;
+  const f32x2 u2 = f2_mul(u, u);
+  const f32x2 t = f2_tanh(f2_mul(u, f2_fma(u2, f2_splat(c * k), f2_splat(c))));
+  const f32x2 nw = f2_mul(u, f2_fma(u2, f2_splat(-1.5f * c * k), f2_splat(-0.5f * c)));
+  const f32x2 r = f2_fma(t, f2_splat(0.5f), f2_splat(0.5f));
+  const f32x2 base = f2_fma(nw, f2_splat(-1.0f), r);
+  return f2_fma(f2_mul(t, t), nw, base);
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -330,15 +330,19 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CU
 #pragma unroll
           for (int jl = 0; jl < GRP_PIECES; ++jl) {  // this thread's 16-byte pieces of its 128-byte staged row
             const int j = grp * GRP_PIECES + jl;
-            float f[8];
+            // four fp32 pairs (FFMA2-class packed math: the epilogue is issue-bound)
+            f32x2 f[4];
 #pragma unroll
-            for (int i = 0; i < 8; ++i)
-              f[i] = __uint_as_float((EPI_GROUPS == 2 || jl < 4) ? v0[(jl & 3) * 8 + i] : v1[(jl & 3) * 8 + i]);
+            for (int i = 0; i < 4; ++i) {
+              const int e = (jl & 3) * 8 + 2 * i;
+              f[i] = (EPI_GROUPS == 2 || jl < 4) ? f2_pack(__uint_as_float(v0[e]), __uint_as_float(v0[e + 1]))
+                                                 : f2_pack(__uint_as_float(v1[e]), __uint_as_float(v1[e + 1]));
+            }
             if (p.bias != nullptr) {
               const float4 b0 = lds128_ro(s_bias_addr + (c * EPI_COLS + j * 8) * 4);
               const float4 b1 = lds128_ro(s_bias_addr + (c * EPI_COLS + j * 8 + 4) * 4);
-              f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
-              f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
+              f[0] = f2_add(f[0], f2_pack(b0.x, b0.y)); f[1] = f2_add(f[1], f2_pack(b0.z, b0.w));
+              f[2] = f2_add(f[2], f2_pack(b1.x, b1.y)); f[3] = f2_add(f[3], f2_pack(b1.z, b1.w));
             }
             const uint32_t piece = my_row + ((j ^ (row & 7)) << 4);
             if (kHasAuxIn) {
@@ -346,33 +350,25 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CU
               const uint32_t aw[4] = {a.x, a.y, a.z, a.w};
 #pragma unroll
               for (int i = 0; i < 4; ++i) {
-                const float lo = bf16_lo(aw[i]), hi = bf16_hi(aw[i]);
-                if (kEpi == kResidual) {
-                  f[2 * i] += lo;
-                  f[2 * i + 1] += hi;
-                } else {  // kGeluBwd: acc * gelu'(u)
-                  f[2 * i] *= gelu_new_grad(lo);
-                  f[2 * i + 1] *= gelu_new_grad(hi);
-                }
+                const f32x2 x = f2_from_bf16x2(aw[i]);
+                if (kEpi == kResidual) f[i] = f2_add(f[i], x);
+                else f[i] = f2_mul(f[i], gelu_new_grad_x2(x));  // kGeluBwd: acc * gelu'(u)
               }
             }
             if (kDual) {
               // pre-activation u goes to the second buffer of the pair, gelu(u) to the first
               uint4 pu;
-              pu.x = pack_bf16x2(f[0], f[1]); pu.y = pack_bf16x2(f[2], f[3]);
-              pu.z = pack_bf16x2(f[4], f[5]); pu.w = pack_bf16x2(f[6], f[7]);
+              pu.x = f2_to_bf16x2(f[0]); pu.y = f2_to_bf16x2(f[1]);
+              pu.z = f2_to_bf16x2(f[2]); pu.w = f2_to_bf16x2(f[3]);
               sts128(my_row + EPI_BUF_BYTES + ((j ^ (row & 7)) << 4), pu);
               // gelu is evaluated on the bf16-rounded u so that forward and backward see the same value
               const uint32_t uw[4] = {pu.x, pu.y, pu.z, pu.w};
 #pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                f[2 * i] = gelu_new_fwd(bf16_lo(uw[i]));
-                f[2 * i + 1] = gelu_new_fwd(bf16_hi(uw[i]));
-              }
+              for (int i = 0; i < 4; ++i) f[i] = gelu_new_fwd_x2(f2_from_bf16x2(uw[i]));
             }
             uint4 o;
-            o.x = pack_bf16x2(f[0], f[1]); o.y = pack_bf16x2(f[2], f[3]);
-            o.z = pack_bf16x2(f[4], f[5]); o.w = pack_bf16x2(f[6], f[7]);
+            o.x = f2_to_bf16x2(f[0]); o.y = f2_to_bf16x2(f[1]);
+            o.z = f2_to_bf16x2(f[2]); o.w = f2_to_bf16x2(f[3]);
             sts128(piece, o);
           }
           fence_proxy_async_smem();
