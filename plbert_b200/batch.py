@@ -203,6 +203,7 @@ class BatchFeeder:
         self.model = model
         self._it = iter(batches)
         self._staged: Optional[DeviceBatch] = None
+        self._stager = model.new_stager()   # own slots: validation / inference calls in between must not recycle them
         self._advance()
 
     def _advance(self) -> None:
@@ -211,7 +212,7 @@ class BatchFeeder:
         except StopIteration:
             self._staged = None
             return
-        self._staged = self.model.stage_batch(host)
+        self._staged = self.model.stage_batch(host, stager=self._stager)
 
     @property
     def exhausted(self) -> bool:

@@ -192,14 +192,22 @@ class Engine:
                 self.d_e = mk(E)
                 self.delta = torch.empty((c.num_attention_heads, cap), dtype=torch.float32, device=dev)
             self._cap_T = cap
-        if train and M > self._cap_M:
-            cap = max(int(M * 1.25) + 64, self._cap_M)
-            vmax = max(c.num_phonemes, c.num_tokens or 0)
-            self.h_rows = torch.empty((cap, H), dtype=bf, device=dev)
-            self.dh_rows = torch.empty((cap, H), dtype=bf, device=dev)
-            self.logits = torch.empty(cap * ((vmax + 7) // 8 * 8), dtype=bf, device=dev)
-            self.row_loss = torch.empty(cap, dtype=torch.float32, device=dev)
-            self._cap_M = cap
+        if train:
+            self._ensure_row_workspace(M)
+
+    def _ensure_row_workspace(self, M: int) -> None:
+        """Buffers of the masked-row head path: gathered hidden rows, their gradient, logits, per-row loss."""
+        if M <= self._cap_M:
+            return
+        c = self.cfg
+        H, dev, bf = c.hidden_size, self.device, torch.bfloat16
+        cap = max(int(M * 1.25) + 64, self._cap_M)
+        vmax = max(c.num_phonemes, c.num_tokens or 0)
+        self.h_rows = torch.empty((cap, H), dtype=bf, device=dev)
+        self.dh_rows = torch.empty((cap, H), dtype=bf, device=dev)
+        self.logits = torch.empty(cap * ((vmax + 7) // 8 * 8), dtype=bf, device=dev)
+        self.row_loss = torch.empty(cap, dtype=torch.float32, device=dev)
+        self._cap_M = cap
 
     # ------------------------------------------------------------------ kernels
     def _gemm(self, op, epi, M, N, K, A, lda, B, ldb, C, ldc, bias=None, aux_in=None, ld_in=0, aux_out=None, ld_out=0):
@@ -310,6 +318,30 @@ class Engine:
         self.launches += 1
         self.encoder_backward(b)
         return self.loss_buf[0]
+
+    def loss_only(self, b: DeviceBatch, heads: List[str]) -> torch.Tensor:
+        """Forward + masked-row CE without the backward pass (validation, R/train.py:288-305 under ``no_grad``).
+        Uses the two-set activation ping-pong of the inference forward; leaves gradients and optimizer state alone."""
+        c = self.cfg
+        H, M = c.hidden_size, b.M
+        s = _stream()
+        hidden = self.forward(b, train=False)
+        if M == 0:
+            self.loss_buf.zero_()
+            return self.loss_buf[0].clone()
+        self._ensure_row_workspace(M)
+        call("plb_gather_rows", ptr(hidden), H, ptr(b.rows), M, H, ptr(self.h_rows), H, s)
+        self.launches += 1
+        for i, head in enumerate(heads):
+            V = self.layout.shapes[head + ".weight"][0]
+            ldv = (V + 7) // 8 * 8
+            logits = self.logits[:M * ldv].view(M, ldv)
+            self._gemm(GEMM_FWD, EPI_NONE, M, V, H, self.h_rows, H, self.w(head + ".weight"), H, logits, ldv,
+                       bias=self.p(head + ".bias"))
+            call("plb_masked_ce", ptr(logits), ldv, M, V, ptr(b.labels[i]), ptr(b.weights), ptr(self.row_loss),
+                 ptr(self.loss_buf), 1 if i > 0 else 0, s)
+            self.launches += 1
+        return self.loss_buf[0].clone()
 
     def begin_backward(self) -> None:
         """Gradients accumulate in place (12 applications of the shared layer), so the arena must start at zero."""

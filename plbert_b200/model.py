@@ -97,6 +97,43 @@ class _FullLogitsFn(torch.autograd.Function):
         return (None, None, None, None) + tuple(grads)
 
 
+class _EncoderGraph:
+    """One captured encoder forward for a fixed [B, L] shape (padded layout).  Inputs live in static device buffers
+    (ids, positions, lengths) that every call overwrites with device-side copies; the graph reads the engine's bf16
+    weight shadow in place, so weight updates only need the usual shadow refresh before the replay."""
+
+    def __init__(self, model: "_FusedModel", B: int, L: int):
+        eng: Engine = model._engine
+        dev = eng.device
+        self.model, self.B, self.L = model, B, L
+        i32 = dict(dtype=torch.int32, device=dev)
+        self.ids = torch.zeros(B * L, **i32)
+        self.kv_len = torch.full((B,), L, **i32)
+        self.batch = DeviceBatch(B=B, L=L, ids=self.ids, pos=torch.arange(L, **i32).repeat(B),
+                                 seq_start=torch.arange(B, **i32) * L, q_len=torch.full((B,), L, **i32), kv_len=self.kv_len,
+                                 num_valid_tokens=B * L, n_rows=B * L)
+        with torch.no_grad():
+            eng.forward(self.batch, train=False)          # warm-up: allocates the workspace, configures the kernels
+            torch.cuda.synchronize(dev)
+            # the graph holds raw pointers into these buffers: keep them alive even if the engine regrows its workspace
+            self._keep = (eng.e, eng.e_stats, eng.x0, list(eng.acts[:2]))
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph):
+                self.out = eng.forward(self.batch, train=False)
+
+    def __call__(self, phonemes: torch.Tensor, attention_mask: Optional[torch.Tensor]) -> torch.Tensor:
+        eng: Engine = self.model._engine
+        if not eng.shadow_valid:
+            eng.refresh_shadow()
+        self.ids.copy_(phonemes.reshape(-1), non_blocking=True)          # int64 -> int32 on the device (or pinned H2D)
+        if attention_mask is None:
+            self.kv_len.fill_(self.L)
+        else:
+            self.kv_len.copy_(attention_mask.to(eng.device, non_blocking=True).ne(0).sum(dim=1))
+        self.graph.replay()
+        return self.out.view(self.B, self.L, -1).clone()
+
+
 class _FusedModel(nn.Module):
     _heads: List[str] = []
 
@@ -106,6 +143,7 @@ class _FusedModel(nn.Module):
         self._engine: Optional[Engine] = None
         self._stager: Optional[BatchStager] = None
         self._versions: List[int] = []
+        self._graphs = {}
 
     # ------------------------------------------------------------------ engine / arena management
     def _arena_params(self):
@@ -130,6 +168,7 @@ class _FusedModel(nn.Module):
             self._engine = eng
             self._stager = BatchStager(device)
             self._versions = []
+            self._graphs = {}
         # (re)adopt: parameters whose storage is not the arena view (first call, .to(), load with assign=True ...)
         stale = False
         for name, p in named:
@@ -177,16 +216,32 @@ class _FusedModel(nn.Module):
         need_grad = torch.is_grad_enabled() and any(p.requires_grad for p in params)
         return _FullLogitsFn.apply(self, batch, list(self._heads), need_grad, *params)
 
-    def encode(self, phonemes: torch.Tensor, attention_mask: Optional[torch.Tensor] = None) -> torch.Tensor:
-        """Encoder-only forward (``AlbertModel(...).last_hidden_state``, R/README.md:91): bf16 [B, L, H], no grad."""
+    def encode(self, phonemes: torch.Tensor, attention_mask: Optional[torch.Tensor] = None, *,
+               use_graph: bool = False) -> torch.Tensor:
+        """Encoder-only forward (``AlbertModel(...).last_hidden_state``, R/README.md:91): bf16 [B, L, H], no grad.
+
+        ``use_graph=True`` replays a CUDA graph of the ~90 kernel launches captured once per (B, L)
+        shape: no per-call host staging, no device->host sync (the eager path reads the mask back to validate it), so
+        short inference batches are not launch-bound.  The mask must still be a right-padded prefix mask."""
         eng = self._ensure_engine(phonemes.device)
+        if use_graph:
+            key = (int(phonemes.shape[0]), int(phonemes.shape[1]))
+            g = self._graphs.get(key)
+            if g is None:
+                g = self._graphs[key] = _EncoderGraph(self, *key)
+            return g(phonemes, attention_mask)
         batch = self._stage_inputs(phonemes, attention_mask)
         with torch.no_grad():
             hidden = eng.forward(batch, train=False)
         return hidden.view(batch.B, batch.L, -1).clone()  # the workspace is reused by the next call
 
     # ------------------------------------------------------------------ fused training step
-    def stage_batch(self, batch: Sequence) -> DeviceBatch:
+    def new_stager(self) -> BatchStager:
+        """A private pair of pinned/device staging slots (``BatchFeeder`` owns one, so a batch it staged ahead survives
+        any number of interleaved ``loss`` / ``encode`` / ``loss_and_backward`` calls that stage through the model's own)."""
+        return BatchStager(next(self.parameters()).device)
+
+    def stage_batch(self, batch: Sequence, stager: Optional[BatchStager] = None) -> DeviceBatch:
         """Host half of ``loss_and_backward``: flatten the collate tuple into the integer arrays the kernels read, fill one
         pinned buffer and enqueue its H2D copy (asynchronous).  Calling it for batch i+1 right after the kernels of step i
         have been enqueued hides the host work behind the GPU (``plbert_b200.batch.BatchFeeder`` does exactly that)."""
@@ -206,7 +261,7 @@ class _FusedModel(nn.Module):
             heads.append("token_predictor")
         # drop the padding rows when there are any: same loss and gradients, fewer tokens to process
         packed = self.pack_sequences and min(int(x) for x in lengths) < masked.shape[1]
-        db = self._stager.stage(masked, lengths, midx, label_tensors, packed=packed)
+        db = (stager or self._stager).stage(masked, lengths, midx, label_tensors, packed=packed)
         db.heads = heads
         return db
 
@@ -225,6 +280,15 @@ class _FusedModel(nn.Module):
         loss = eng.loss_and_backward(db, db.heads)
         self._publish_grads()
         return loss
+
+    def loss(self, batch) -> torch.Tensor:
+        """Loss of one batch without gradients — ``process_batch`` under ``torch.no_grad()`` as the reference's
+        ``validate`` runs it (R/train.py:288-305).  Same batch forms as ``loss_and_backward``."""
+        db = batch if isinstance(batch, DeviceBatch) else self.stage_batch(batch)
+        if not db.heads:
+            raise _abi.PlbError("loss needs a batch staged with labels (stage_batch)")
+        eng = self._ensure_engine(db.ids.device)
+        return eng.loss_only(db, db.heads)
 
 
 class MultiTaskModel(_FusedModel):

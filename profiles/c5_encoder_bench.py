@@ -46,15 +46,20 @@ def main():
     def ours():
         return model.encode(ids, mask)
 
+    def ours_graph():
+        return model.encode(ids, mask, use_graph=True)
+
     def hf():
         with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
             return enc(ids, attention_mask=mask).last_hidden_state
 
     a, b = ours().float(), hf().float()
     cos = torch.nn.functional.cosine_similarity(a.flatten(), b.flatten(), dim=0).item()
-    ms_o, ms_h = timeit(ours, args.iters), timeit(hf, args.iters)
+    assert torch.equal(ours(), ours_graph())
+    ms_o, ms_g, ms_h = timeit(ours, args.iters), timeit(ours_graph, args.iters), timeit(hf, args.iters)
     print(json.dumps({"config": f"C5: encoder-only forward {args.batch}x{args.seq}, bf16, no grad", "cosine_vs_hf": cos,
                       "plbert_b200": {"ms": ms_o, "tokens_per_s": tokens / (ms_o * 1e-3)},
+                      "plbert_b200_cuda_graph": {"ms": ms_g, "tokens_per_s": tokens / (ms_g * 1e-3)},
                       "hf_autocast_bf16": {"ms": ms_h, "tokens_per_s": tokens / (ms_h * 1e-3)}}))
 
 

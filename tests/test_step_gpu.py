@@ -194,6 +194,8 @@ def test_batch_feeder_matches_direct_calls(dev):
                 loss = feed.step()
                 opt.step()
                 losses.append(loss.item())
+                for vb in batches:   # validation-style calls in between must not disturb the batch staged ahead
+                    model.loss(vb)
             with pytest.raises(StopIteration):
                 feed.step()
         else:
@@ -209,6 +211,33 @@ def test_batch_feeder_matches_direct_calls(dev):
         if "pooler" in n or "key.bias" in n:   # never updated / true gradient identically zero
             continue
         assert cosine((p - build_ref[n]).cpu().numpy(), (out[1][1][n] - build_ref[n]).cpu().numpy()) > 0.9, n
+
+
+def test_encoder_graph_replay_equals_eager(dev):
+    """Encoder-only inference through a captured CUDA graph returns bit-identical hidden states to the
+    eager launch sequence — for new inputs, padded batches and after the weights changed."""
+    import plbert_b200 as P
+    from plbert_b200.batch import synthetic_collate_batch
+    cfgv = [188, 32, 128, 2, 256, 3, 128, 0]
+    model = build_model(cfgv, False, dev, seed=8)
+    g = torch.Generator().manual_seed(0)
+    for trial in range(3):
+        ids = torch.randint(1, 185, (5, 96), generator=g).to(dev)
+        lens = torch.tensor([96, 96, 70, 33, 9]) if trial else torch.full((5,), 96)
+        mask = (torch.arange(96)[None, :] < lens[:, None]).int().to(dev)
+        eager = model.encode(ids, mask if trial else None)
+        graphed = model.encode(ids, mask if trial else None, use_graph=True)
+        assert graphed.shape == (5, 96, 128) and graphed.dtype == torch.bfloat16
+        for b, n in enumerate(lens.tolist()):
+            assert torch.equal(eager[b, :n], graphed[b, :n]), (trial, b)
+    assert len(model._graphs) == 1
+    # weights move (one optimizer step): the replay must see them
+    opt = P.FusedAdamW(model.parameters(), lr=1e-2)
+    model.loss_and_backward(synthetic_collate_batch(4, 128, seed=5, word_pred_prob=0.3))
+    opt.step()
+    after = model.encode(ids, mask, use_graph=True)
+    assert not torch.equal(after, graphed)
+    assert torch.equal(after[0], model.encode(ids, mask)[0])
 
 
 def test_reference_style_forward_backward(dev):
