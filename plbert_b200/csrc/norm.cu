@@ -26,51 +26,102 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
 }
 
 // y = LN(z) * w + b ; stats[row] = (mean, rstd)
-template <int MAXC>
+// Every warp keeps FWD_DEPTH rows in flight: lane 0 streams the warp's next rows into a private shared-memory ring with
+// 1-D bulk copies (cp.async.bulk + mbarrier), so the bytes in flight per SM (~150 KB) no longer depend on registers or on
+// how many warps are resident — the register-resident version waited out a full HBM round trip per row and reached 5 TB/s.
+constexpr int FWD_DEPTH = 4;
+template <int MAXC, bool kFull>   // kFull: H == MAXC * 256, every lane owns MAXC whole chunks (no per-chunk predicates)
 __global__ void __launch_bounds__(WARPS * 32) ln_fwd_kernel(const __nv_bfloat16* __restrict__ z, int T, int H,
                                                             const float* __restrict__ w, const float* __restrict__ b,
                                                             float eps, __nv_bfloat16* __restrict__ y,
                                                             float* __restrict__ stats) {
+  extern __shared__ __align__(128) uint8_t ln_smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int nchunk = H >> 3;
-  for (int row = blockIdx.x * WARPS + warp; row < T; row += gridDim.x * WARPS) {
-    const uint4* zr = reinterpret_cast<const uint4*>(z + static_cast<size_t>(row) * H);
-    float x[MAXC][8];
-    float sum = 0.f;
+  const uint32_t row_bytes = static_cast<uint32_t>(H) * 2;
+  uint8_t* ring = ln_smem + static_cast<size_t>(warp) * FWD_DEPTH * row_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ln_smem + static_cast<size_t>(WARPS) * FWD_DEPTH * row_bytes) + warp * FWD_DEPTH;
+  const int first = blockIdx.x * WARPS + warp, stride = gridDim.x * WARPS;
+  auto issue = [&](int k) {  // lane 0 only
+    const long row = first + static_cast<long>(k) * stride;
+    if (row < T) {
+      const int st = k % FWD_DEPTH;
+      mbar_arrive_expect_tx(&bars[st], row_bytes);
+      bulk_load_1d(ring + st * row_bytes, z + row * H, row_bytes, &bars[st]);
+    }
+  };
+  if (lane == 0) {
+    for (int i = 0; i < FWD_DEPTH; ++i) mbar_init(&bars[i], 1);
+    fence_mbar_init();
+    for (int k = 0; k < FWD_DEPTH; ++k) issue(k);
+  }
+  __syncwarp();
+  // weight / bias of this lane's columns stay in registers for the whole kernel (per-row __ldg's were the top stall:
+  // with the ring there are few resident warps to hide their latency), as fp32 pairs for the packed FFMA2 math
+  f32x2 ww[MAXC][4], bb[MAXC][4];
+#pragma unroll
+  for (int i = 0; i < MAXC; ++i) {
+    const int c = lane + 32 * i;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const bool ok = kFull || c < nchunk;
+      ww[i][q] = f2_pack(ok ? __ldg(w + c * 8 + 2 * q) : 0.f, ok ? __ldg(w + c * 8 + 2 * q + 1) : 0.f);
+      bb[i][q] = f2_pack(ok ? __ldg(b + c * 8 + 2 * q) : 0.f, ok ? __ldg(b + c * 8 + 2 * q + 1) : 0.f);
+    }
+  }
+  const float invH = 1.f / H;
+  int k = 0;
+  for (int row = first; row < T; row += stride, ++k) {
+    const int st = k % FWD_DEPTH;
+    mbar_wait(&bars[st], (k / FWD_DEPTH) & 1);
+    const uint32_t src = smem_u32(ring + st * row_bytes);
+    f32x2 x[MAXC][4];
+    f32x2 sum2 = f2_splat(0.f);
 #pragma unroll
     for (int i = 0; i < MAXC; ++i) {
       const int c = lane + 32 * i;
-      if (c < nchunk) {
-        unpack8(zr[c], x[i]);
+      if (kFull || c < nchunk) {
+        const uint4 v = lds128(src + c * 16);
+        const uint32_t wv[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-        for (int k = 0; k < 8; ++k) sum += x[i][k];
+        for (int q = 0; q < 4; ++q) {
+          x[i][q] = f2_from_bf16x2(wv[q]);
+          sum2 = f2_add(sum2, x[i][q]);
+        }
+      } else {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) x[i][q] = f2_splat(0.f);
       }
     }
-    const float mean = warp_sum(sum) / H;
-    float sq = 0.f;
+    __syncwarp();                    // every lane has its chunks in registers: the slot can be refilled
+    if (lane == 0) issue(k + FWD_DEPTH);
+    float s_lo, s_hi;
+    f2_unpack(sum2, s_lo, s_hi);
+    const float mean = warp_sum(s_lo + s_hi) * invH;
+    const f32x2 nmean = f2_splat(-mean);
+    f32x2 sq2 = f2_splat(0.f);
 #pragma unroll
     for (int i = 0; i < MAXC; ++i)
-      if (lane + 32 * i < nchunk) {
+      if (kFull || lane + 32 * i < nchunk) {
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          const float d = x[i][k] - mean;
-          sq += d * d;
+        for (int q = 0; q < 4; ++q) {
+          const f32x2 d = f2_add(x[i][q], nmean);
+          sq2 = f2_fma(d, d, sq2);
         }
       }
-    const float rstd = rsqrtf(warp_sum(sq) / H + eps);
+    f2_unpack(sq2, s_lo, s_hi);
+    const float rstd = rsqrtf(warp_sum(s_lo + s_hi) * invH + eps);
+    const f32x2 rstd2 = f2_splat(rstd), nmr = f2_splat(-mean * rstd);
     uint4* yr = reinterpret_cast<uint4*>(y + static_cast<size_t>(row) * H);
 #pragma unroll
     for (int i = 0; i < MAXC; ++i) {
       const int c = lane + 32 * i;
-      if (c < nchunk) {
-        const float4 w0 = __ldg(reinterpret_cast<const float4*>(w + c * 8)), w1 = __ldg(reinterpret_cast<const float4*>(w + c * 8 + 4));
-        const float4 b0 = __ldg(reinterpret_cast<const float4*>(b + c * 8)), b1 = __ldg(reinterpret_cast<const float4*>(b + c * 8 + 4));
-        const float ww[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
-        const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-        float o[8];
+      if (kFull || c < nchunk) {
+        uint32_t o[4];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) o[k] = (x[i][k] - mean) * rstd * ww[k] + bb[k];
-        yr[c] = pack8(o);
+        for (int q = 0; q < 4; ++q)   // ((x - mean) rstd) w + b, the normalised value first like the reference
+          o[q] = f2_to_bf16x2(f2_fma(f2_fma(x[i][q], rstd2, nmr), ww[i][q], bb[i][q]));
+        yr[c] = make_uint4(o[0], o[1], o[2], o[3]);
       }
     }
     if (lane == 0) {
@@ -81,107 +132,157 @@ __global__ void __launch_bounds__(WARPS * 32) ln_fwd_kernel(const __nv_bfloat16*
 }
 
 // dz = LN'(dy); dw += sum dy*xhat; db += sum dy; colsum += sum dz (bias gradient of the producing Linear)
-// A row is split over WPR warps (each lane owns ONE 16-byte chunk), so the per-thread column partials are only
-// 3 x 8 registers and two 12-warp CTAs fit per SM; the two row statistics cross the WPR warps through shared memory.
-constexpr int LNB_ROWS = 4;  // rows in flight per CTA
-template <int WPR>
-__global__ void __launch_bounds__(LNB_ROWS * WPR * 32, (LNB_ROWS * WPR * 32 <= 384) ? 2 : 1)
+// One warp per row, like the forward kernel: each warp streams its rows (z and dy) through a private BWD_DEPTH-deep
+// shared-memory ring filled by 1-D bulk copies, so nothing synchronises across warps inside the loop.  The first
+// version split a row over three warps (one 16-byte chunk per lane) and spent 270 instructions per 8 elements on
+// barriers, statistics exchange and predication (68 % issue-slot utilisation at 4.4 TB/s); here a lane owns all its
+// chunks, the math runs on fp32 pairs, and phase two re-derives xhat / g from the raw bf16 words instead of keeping them.
+constexpr int BWD_WARPS = 6;  // per CTA, two CTAs per SM
+constexpr int BWD_DEPTH = 4;  // rows in flight per warp
+template <int MAXC, bool kFull>
+__global__ void __launch_bounds__(BWD_WARPS * 32, 2)
 ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ z,
               const float* __restrict__ stats, const float* __restrict__ w, int T, int H,
               __nv_bfloat16* __restrict__ dz, float* __restrict__ dw_acc, float* __restrict__ db_acc,
               float* __restrict__ colsum_acc) {
-  extern __shared__ float s_red[];                      // [3][H] column partials of the CTA
-  __shared__ float s_row[2][LNB_ROWS][WPR][2];          // per-row partial statistics (double buffered)
+  extern __shared__ __align__(128) uint8_t ln_smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int rslot = warp / WPR, wr = warp % WPR;        // row slot of this warp, position within the row
-  const int c = wr * 32 + lane;                         // 16-byte chunk of the row owned by this thread
   const int nchunk = H >> 3;
-  const bool active = c < nchunk;
+  const uint32_t row_bytes = static_cast<uint32_t>(H) * 2;
+  uint8_t* ring = ln_smem + static_cast<size_t>(warp) * BWD_DEPTH * 2 * row_bytes;   // slot = z row | dy row
+  uint8_t* after = ln_smem + static_cast<size_t>(BWD_WARPS) * BWD_DEPTH * 2 * row_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(after) + warp * BWD_DEPTH;
+  float* s_red = reinterpret_cast<float*>(after + BWD_WARPS * BWD_DEPTH * 8);          // [3][H] column partials of the CTA
+  const long first = static_cast<long>(blockIdx.x) * BWD_WARPS + warp, stride = static_cast<long>(gridDim.x) * BWD_WARPS;
+  auto issue = [&](long k) {  // lane 0 only: slot k % BWD_DEPTH <- the warp's k-th row
+    const long row = first + k * stride;
+    if (row < T) {
+      const int st = static_cast<int>(k % BWD_DEPTH);
+      uint8_t* dst = ring + st * 2 * row_bytes;
+      mbar_arrive_expect_tx(&bars[st], 2 * row_bytes);
+      bulk_load_1d(dst, z + row * H, row_bytes, &bars[st]);
+      bulk_load_1d(dst + row_bytes, dy + row * H, row_bytes, &bars[st]);
+    }
+  };
+  if (lane == 0) {
+    for (int i = 0; i < BWD_DEPTH; ++i) mbar_init(&bars[i], 1);
+    fence_mbar_init();
+    for (int k = 0; k < BWD_DEPTH; ++k) issue(k);
+  }
   for (int i = threadIdx.x; i < 3 * H; i += blockDim.x) s_red[i] = 0.f;
   __syncthreads();
 
-  float ww[8], pdw[8], pdb[8], pcs[8];
+  f32x2 ww[MAXC][4], pdw[MAXC][4], pdb[MAXC][4], pcs[MAXC][4];
 #pragma unroll
-  for (int k = 0; k < 8; ++k) {
-    ww[k] = active ? __ldg(w + c * 8 + k) : 0.f;
-    pdw[k] = pdb[k] = pcs[k] = 0.f;
+  for (int i = 0; i < MAXC; ++i) {
+    const int c = lane + 32 * i;
+    const bool ok = kFull || c < nchunk;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      ww[i][q] = f2_pack(ok ? __ldg(w + c * 8 + 2 * q) : 0.f, ok ? __ldg(w + c * 8 + 2 * q + 1) : 0.f);
+      pdw[i][q] = pdb[i][q] = pcs[i][q] = f2_splat(0.f);
+    }
   }
   const float invH = 1.f / H;
-  int it = 0;
-  // software pipeline: the loads of the next row are in flight while the current row is reduced
-  uint4 nz = make_uint4(0, 0, 0, 0), nd = make_uint4(0, 0, 0, 0);
-  float nmean = 0.f, nrstd = 0.f;
-  auto prefetch = [&](int row0) {
-    const int row = row0 + rslot;
-    if (row < T) {
-      nmean = stats[2 * row];
-      nrstd = stats[2 * row + 1];
-      if (active) {
-        nz = *reinterpret_cast<const uint4*>(z + static_cast<size_t>(row) * H + c * 8);
-        nd = *reinterpret_cast<const uint4*>(dy + static_cast<size_t>(row) * H + c * 8);
-      }
-    }
+  // (mean, rstd) of a row is 8 bytes: a plain load BWD_DEPTH rows ahead, queued in registers
+  auto load_stats = [&](long row) -> float2 {   // volatile asm: issued here, not sunk to its use four rows later
+    float2 v = make_float2(0.f, 0.f);
+    if (row < T) asm volatile("ld.global.nc.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(stats + 2 * row));
+    return v;
   };
-  prefetch(blockIdx.x * LNB_ROWS);
-  for (int row0 = blockIdx.x * LNB_ROWS; row0 < T; row0 += gridDim.x * LNB_ROWS, ++it) {
-    const int row = row0 + rslot;
-    const bool rv = row < T;
-    float xh[8], g[8];
-    float s1 = 0.f, s2 = 0.f;
-    const float mean = nmean, rstd = nrstd;
-    const uint4 cz = nz, cd = nd;
-    if (row0 + gridDim.x * LNB_ROWS < T) prefetch(row0 + gridDim.x * LNB_ROWS);
-    if (rv && active) {
-      float zz[8], dd[8];
-      unpack8(cz, zz);
-      unpack8(cd, dd);
+  float2 sq[BWD_DEPTH];
 #pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        xh[k] = (zz[k] - mean) * rstd;
-        pdw[k] += dd[k] * xh[k];
-        pdb[k] += dd[k];
-        g[k] = dd[k] * ww[k];
-        s1 += g[k];
-        s2 += g[k] * xh[k];
+  for (int u = 0; u < BWD_DEPTH; ++u) sq[u] = load_stats(first + u * stride);
+
+  for (long k0 = 0; first + k0 * stride < T; k0 += BWD_DEPTH) {
+#pragma unroll
+    for (int u = 0; u < BWD_DEPTH; ++u) {
+      const long k = k0 + u, row = first + k * stride;
+      if (row < T) {
+        const float mean = sq[u].x, rstd = sq[u].y;
+        sq[u] = load_stats(row + BWD_DEPTH * stride);
+        mbar_wait(&bars[u], static_cast<uint32_t>(k0 / BWD_DEPTH) & 1);
+        const uint32_t src = smem_u32(ring + u * 2 * row_bytes);
+        uint4 rz[MAXC], rd[MAXC];
+#pragma unroll
+        for (int i = 0; i < MAXC; ++i) {
+          const int c = lane + 32 * i;
+          if (kFull || c < nchunk) {
+            rz[i] = lds128(src + c * 16);
+            rd[i] = lds128(src + row_bytes + c * 16);
+          } else {
+            rz[i] = rd[i] = make_uint4(0, 0, 0, 0);   // zero dy: no contribution to any sum
+          }
+        }
+        __syncwarp();                    // the slot is in registers: refill it
+        if (lane == 0) issue(k + BWD_DEPTH);
+        const f32x2 rstd2 = f2_splat(rstd), nmr = f2_splat(-mean * rstd);
+        // ---- phase 1: column partials and the two row sums ----
+        f32x2 s1v = f2_splat(0.f), s2v = f2_splat(0.f);
+#pragma unroll
+        for (int i = 0; i < MAXC; ++i) {
+          const uint32_t zw[4] = {rz[i].x, rz[i].y, rz[i].z, rz[i].w}, dw_[4] = {rd[i].x, rd[i].y, rd[i].z, rd[i].w};
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const f32x2 df = f2_from_bf16x2(dw_[q]);
+            const f32x2 xh = f2_fma(f2_from_bf16x2(zw[q]), rstd2, nmr);
+            pdw[i][q] = f2_fma(df, xh, pdw[i][q]);
+            pdb[i][q] = f2_add(pdb[i][q], df);
+            const f32x2 g = f2_mul(df, ww[i][q]);
+            s1v = f2_add(s1v, g);
+            s2v = f2_fma(g, xh, s2v);
+          }
+        }
+        float a0, a1, b0, b1;
+        f2_unpack(s1v, a0, a1);
+        f2_unpack(s2v, b0, b1);
+        float s1 = a0 + a1, s2 = b0 + b1;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {   // the two reductions interleaved
+          s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+          s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+        }
+        // dz = rstd (g - s1/H - xh s2/H)  =  (g - xh * s2/H) * rstd - rstd * s1/H
+        const f32x2 ns2 = f2_splat(-s2 * invH), c0 = f2_splat(-s1 * invH * rstd);
+        // ---- phase 2: xh and g again from the raw words (cheaper than 48 live registers), outputs ----
+        uint4* out = reinterpret_cast<uint4*>(dz + static_cast<size_t>(row) * H);
+#pragma unroll
+        for (int i = 0; i < MAXC; ++i) {
+          const int c = lane + 32 * i;
+          if (kFull || c < nchunk) {
+            const uint32_t zw[4] = {rz[i].x, rz[i].y, rz[i].z, rz[i].w}, dw_[4] = {rd[i].x, rd[i].y, rd[i].z, rd[i].w};
+            uint32_t o[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const f32x2 xh = f2_fma(f2_from_bf16x2(zw[q]), rstd2, nmr);
+              const f32x2 g = f2_mul(f2_from_bf16x2(dw_[q]), ww[i][q]);
+              o[q] = f2_to_bf16x2(f2_fma(f2_fma(xh, ns2, g), rstd2, c0));
+              // the bias gradient must see exactly the values the GEMMs will read -> sum the rounded outputs
+              pcs[i][q] = f2_add(pcs[i][q], f2_from_bf16x2(o[q]));
+            }
+            out[c] = make_uint4(o[0], o[1], o[2], o[3]);
+          }
+        }
       }
-    }
-    s1 = warp_sum(s1);
-    s2 = warp_sum(s2);
-    if (WPR > 1) {
-      if (lane == 0) {
-        s_row[it & 1][rslot][wr][0] = s1;
-        s_row[it & 1][rslot][wr][1] = s2;
-      }
-      asm volatile("bar.sync %0, %1;" ::"r"(1 + rslot), "n"(WPR * 32) : "memory");
-      s1 = 0.f;
-      s2 = 0.f;
-#pragma unroll
-      for (int q = 0; q < WPR; ++q) {
-        s1 += s_row[it & 1][rslot][q][0];
-        s2 += s_row[it & 1][rslot][q][1];
-      }
-    }
-    s1 *= invH;
-    s2 *= invH;
-    if (rv && active) {
-      float o[8];
-#pragma unroll
-      for (int k = 0; k < 8; ++k) o[k] = rstd * (g[k] - s1 - xh[k] * s2);
-      const uint4 packed = pack8(o);
-      *reinterpret_cast<uint4*>(dz + static_cast<size_t>(row) * H + c * 8) = packed;
-      // the bias gradient must see exactly the values the GEMMs will read -> sum the rounded outputs
-      float r[8];
-      unpack8(packed, r);
-#pragma unroll
-      for (int k = 0; k < 8; ++k) pcs[k] += r[k];
     }
   }
-  if (active) {
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      atomicAdd(&s_red[c * 8 + k], pdw[k]);
-      atomicAdd(&s_red[H + c * 8 + k], pdb[k]);
-      atomicAdd(&s_red[2 * H + c * 8 + k], pcs[k]);
+  for (int i = 0; i < MAXC; ++i) {
+    const int c = lane + 32 * i;
+    if (kFull || c < nchunk) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        float lo, hi;
+        f2_unpack(pdw[i][q], lo, hi);
+        atomicAdd(&s_red[c * 8 + 2 * q], lo);
+        atomicAdd(&s_red[c * 8 + 2 * q + 1], hi);
+        f2_unpack(pdb[i][q], lo, hi);
+        atomicAdd(&s_red[H + c * 8 + 2 * q], lo);
+        atomicAdd(&s_red[H + c * 8 + 2 * q + 1], hi);
+        f2_unpack(pcs[i][q], lo, hi);
+        atomicAdd(&s_red[2 * H + c * 8 + 2 * q], lo);
+        atomicAdd(&s_red[2 * H + c * 8 + 2 * q + 1], hi);
+      }
     }
   }
   __syncthreads();
@@ -365,8 +466,21 @@ extern "C" int plb_ln_fwd(const void* z, int T, int H, const float* w, const flo
   PLB_REQUIRE(H % 8 == 0 && H >= 8 && H <= 8 * 32 * LN_MAXC, PLB_ERR_UNSUPPORTED, "ln_fwd: H=%d must be a multiple of 8, <= %d", H,
               8 * 32 * LN_MAXC);
   const int nc = (H / 8 + 31) / 32;
-  auto kern = nc == 1 ? ln_fwd_kernel<1> : nc == 2 ? ln_fwd_kernel<2> : nc == 3 ? ln_fwd_kernel<3> : ln_fwd_kernel<4>;
-  kern<<<row_grid(T, 8), WARPS * 32, 0, static_cast<cudaStream_t>(stream)>>>(
+  PLB_REQUIRE((reinterpret_cast<uintptr_t>(z) & 15) == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0, PLB_ERR_ARG,
+              "ln_fwd: z / y must be 16-byte aligned");
+  const bool full = H == nc * 256;
+  auto kern = nc == 1 ? (full ? ln_fwd_kernel<1, true> : ln_fwd_kernel<1, false>)
+            : nc == 2 ? (full ? ln_fwd_kernel<2, true> : ln_fwd_kernel<2, false>)
+            : nc == 3 ? (full ? ln_fwd_kernel<3, true> : ln_fwd_kernel<3, false>)
+                      : (full ? ln_fwd_kernel<4, true> : ln_fwd_kernel<4, false>);
+  // per-warp ring of FWD_DEPTH rows + its mbarriers
+  const int smem = WARPS * FWD_DEPTH * (H * 2 + 8);
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);  // idempotent
+  PLB_REQUIRE(e == cudaSuccess, PLB_ERR_CUDA, "ln_fwd: cudaFuncSetAttribute(smem=%d): %s", smem, cudaGetErrorString(e));
+  int per_sm = 1;   // resident CTAs per SM (registers and shared memory): the grid is persistent
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, WARPS * 32, smem);
+  PLB_REQUIRE(e == cudaSuccess && per_sm >= 1, PLB_ERR_CUDA, "ln_fwd: occupancy query failed: %s", cudaGetErrorString(e));
+  kern<<<row_grid(T, per_sm), WARPS * 32, smem, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const __nv_bfloat16*>(z), T, H, w, b, eps, static_cast<__nv_bfloat16*>(y), stats);
   return check_launch("plb_ln_fwd");
 }
@@ -377,9 +491,22 @@ extern "C" int plb_ln_bwd(const void* dy, const void* z, const float* stats, con
   PLB_REQUIRE(H % 8 == 0 && H >= 8 && H <= 8 * 32 * LN_MAXC, PLB_ERR_UNSUPPORTED, "ln_bwd: H=%d must be a multiple of 8, <= %d", H,
               8 * 32 * LN_MAXC);
   const int nc = (H / 8 + 31) / 32;
-  auto kern = nc == 1 ? ln_bwd_kernel<1> : nc == 2 ? ln_bwd_kernel<2> : nc == 3 ? ln_bwd_kernel<3> : ln_bwd_kernel<4>;
-  const int need = (T + LNB_ROWS - 1) / LNB_ROWS, cap = sm_count() * 4;
-  kern<<<need < cap ? need : cap, LNB_ROWS * nc * 32, 3 * H * sizeof(float), static_cast<cudaStream_t>(stream)>>>(
+  PLB_REQUIRE((reinterpret_cast<uintptr_t>(z) & 15) == 0 && (reinterpret_cast<uintptr_t>(dy) & 15) == 0 &&
+                  (reinterpret_cast<uintptr_t>(dz) & 15) == 0, PLB_ERR_ARG, "ln_bwd: dy / z / dz must be 16-byte aligned");
+  const bool full = H == nc * 256;
+  auto kern = nc == 1 ? (full ? ln_bwd_kernel<1, true> : ln_bwd_kernel<1, false>)
+            : nc == 2 ? (full ? ln_bwd_kernel<2, true> : ln_bwd_kernel<2, false>)
+            : nc == 3 ? (full ? ln_bwd_kernel<3, true> : ln_bwd_kernel<3, false>)
+                      : (full ? ln_bwd_kernel<4, true> : ln_bwd_kernel<4, false>);
+  // per-warp rings of BWD_DEPTH (z row | dy row) slots + their mbarriers + the CTA's [3][H] column partials
+  const int smem = BWD_WARPS * BWD_DEPTH * (2 * H * 2 + 8) + 3 * H * static_cast<int>(sizeof(float));
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);  // idempotent
+  PLB_REQUIRE(e == cudaSuccess, PLB_ERR_CUDA, "ln_bwd: cudaFuncSetAttribute(smem=%d): %s", smem, cudaGetErrorString(e));
+  int per_sm = 1;   // resident CTAs per SM: the grid is persistent
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, BWD_WARPS * 32, smem);
+  PLB_REQUIRE(e == cudaSuccess && per_sm >= 1, PLB_ERR_CUDA, "ln_bwd: occupancy query failed: %s", cudaGetErrorString(e));
+  const int need = (T + BWD_WARPS - 1) / BWD_WARPS, cap = sm_count() * per_sm;
+  kern<<<need < cap ? need : cap, BWD_WARPS * 32, smem, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const __nv_bfloat16*>(dy), static_cast<const __nv_bfloat16*>(z), stats, w, T, H,
       static_cast<__nv_bfloat16*>(dz), dw_accum, db_accum, colsum_accum);
   return check_launch("plb_ln_bwd");
