@@ -50,6 +50,7 @@ enum Epi : int { kNone = 0, kResidual = 1, kGelu = 2, kGeluBwd = 3, kAtomicF32 =
 struct GemmParams {
   int M, N, K;
   int m_tiles, n_tiles, splits;
+  int m_fast;         // 1: consecutive units walk down M (the B tile stays hot in L2), 0: along N (the A tile stays hot)
   int k_iters;        // ceil(K / BK)
   int k_per_split;    // k iterations per split
   int num_units;      // m_tiles * n_tiles * splits (m_tiles counts 128*kCta-row tiles)
@@ -76,8 +77,13 @@ __device__ __forceinline__ void unit_coords(const GemmParams& p, int u, int& m_b
   const int tiles = p.m_tiles * p.n_tiles;
   const int tile = u % tiles;
   const int split = u / tiles;
-  n_blk = tile % p.n_tiles;
-  m_blk = tile / p.n_tiles;
+  if (p.m_fast) {
+    m_blk = tile % p.m_tiles;
+    n_blk = tile / p.m_tiles;
+  } else {
+    n_blk = tile % p.n_tiles;
+    m_blk = tile / p.n_tiles;
+  }
   k_begin = split * p.k_per_split;
   k_end = min(k_begin + p.k_per_split, p.k_iters);
 }
@@ -477,6 +483,11 @@ extern "C" int plb_gemm_bf16(int op, int epilogue, int M, int N, int K, const vo
   p.M = M; p.N = N; p.K = K;
   p.m_tiles = (M + BM * ctas - 1) / (BM * ctas);
   p.n_tiles = (N + BN - 1) / BN;
+  // Units run concurrently in launch order, so the operand that consecutive units SHARE is read from HBM once and the other
+  // one is streamed once per tile row/column.  Stream the smaller one: for the layer GEMMs (M = tokens >> N) that is the
+  // weight matrix (walk along N); for the 64 k-row token head on the masked rows (N*K = 98 MB of weights vs 17 MB of
+  // activations) walking along N would pull the whole weight matrix through L2 once per 256 activation rows.
+  p.m_fast = (op != PLB_GEMM_WGRAD && static_cast<long long>(N) > static_cast<long long>(M)) ? 1 : 0;
   p.k_iters = (K + BK - 1) / BK;
   p.bias = bias;
   p.splits = 1;
