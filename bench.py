@@ -56,14 +56,20 @@ def measured_peaks():
 
 
 def gemm_dram_traffic(two_heads):
-    """Average DRAM bytes (read + write) per GEMM launch of one step, from the committed ncu capture of the same step
-    (profiles/r1e_gemm_dram_traffic*.json; `ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum`).  None if absent."""
-    path = os.path.join(ROOT, "profiles", "r1e_gemm_dram_traffic_multitask.json" if two_heads else "r1e_gemm_dram_traffic.json")
-    try:
-        with open(path) as f:
-            return json.load(f)["avg_dram_bytes_per_launch"]
-    except (OSError, KeyError, ValueError):
-        return None
+    """Average DRAM bytes (read + write) per GEMM launch of one step, from the newest committed ncu capture of the same
+    step (profiles/r1*_gemm_dram_traffic*.json; `ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum`, reduced by
+    profiles/gemm_dram_traffic.py).  None if absent."""
+    import glob
+    suffix = "_multitask.json" if two_heads else ".json"
+    files = sorted(f for f in glob.glob(os.path.join(ROOT, "profiles", "r1*_gemm_dram_traffic*.json"))
+                   if f.endswith("_gemm_dram_traffic" + suffix))
+    for path in reversed(files):
+        try:
+            with open(path) as f:
+                return json.load(f)["avg_dram_bytes_per_launch"]
+        except (OSError, KeyError, ValueError):
+            continue
+    return None
 
 
 class ClockSampler:
