@@ -61,6 +61,10 @@ int plb_length_to_mask(const int32_t* lengths, int B, int L, int32_t* attn_mask,
  *   PLB_EPI_RESIDUAL  C = acc (+ bias) + aux_in[m,n]
  *   PLB_EPI_GELU      aux_out = u = acc (+ bias);  C = gelu_new(u)        (HF/activations.py:66)
  *   PLB_EPI_GELU_BWD  C = acc * gelu_new'(aux_in[m,n])
+ *   PLB_EPI_ROWDOT    C = acc;  aux_out is FP32: aux_out[(n / 64) * ld_aux_out + m] += sum over the 64-column block of n
+ *                     of bf16(C[m, n']) * aux_in[m, n'] — with C = dO (the O-projection DGRAD, HF:198-200) and aux_in = O this
+ *                     is attention's delta = rowsum(dO o O) per (head, row), fused into the GEMM
+ *                     that produces dO.  N %% 64 == 0; the caller zeroes aux_out first (two 32-column partials are added).
  */
 #define PLB_GEMM_FWD 0
 #define PLB_GEMM_DGRAD 1
@@ -70,6 +74,7 @@ int plb_length_to_mask(const int32_t* lengths, int B, int L, int32_t* attn_mask,
 #define PLB_EPI_RESIDUAL 1
 #define PLB_EPI_GELU 2
 #define PLB_EPI_GELU_BWD 3
+#define PLB_EPI_ROWDOT 4
 
 int plb_gemm_bf16(int op, int epilogue, int M, int N, int K,
                   const void* A, int lda, const void* B, int ldb,
@@ -140,7 +145,8 @@ int plb_attn_fwd_tc(const void* qkv, int ld_qkv, const int32_t* seq_start, const
                     void* ctx, int ld_ctx, float* lse2, plb_stream_t stream);
 
 /* Backward on tcgen05 (delta + dQ kernel + dK/dV kernel).  If dbias_qkv_accum != NULL (fp32 [3*heads*64]) the column
- * sums of dqkv — the bias gradient of the fused QKV projection — are accumulated into it by the same kernels. */
+ * sums of dqkv — the bias gradient of the fused QKV projection — are accumulated into it by the same kernels.
+ * ctx == NULL: delta[heads, total_rows] already holds rowsum(dO o O) (PLB_EPI_ROWDOT produced it) and is only read. */
 int plb_attn_bwd_tc(const void* qkv, int ld_qkv, const int32_t* seq_start, const int32_t* q_len,
                     const int32_t* kv_len, int B, int heads, int head_dim, int max_q_len, int total_rows,
                     const void* ctx, const void* dctx, int ld_ctx, const float* lse2, float* delta,

@@ -14,7 +14,7 @@ PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("PLBERT_B200_LIB") or os.path.join(PKG_DIR, "libplbert_b200.so")
 
 GEMM_FWD, GEMM_DGRAD, GEMM_WGRAD = 0, 1, 2
-EPI_NONE, EPI_RESIDUAL, EPI_GELU, EPI_GELU_BWD = 0, 1, 2, 3
+EPI_NONE, EPI_RESIDUAL, EPI_GELU, EPI_GELU_BWD, EPI_ROWDOT = 0, 1, 2, 3, 4
 ABI_VERSION = 1
 
 

@@ -1153,13 +1153,13 @@ extern "C" int plb_attn_bwd_tc(const void* qkv, int ld_qkv, const int32_t* seq_s
                                const void* ctx, const void* dctx, int ld_ctx, const float* lse2, float* delta,
                                void* dqkv, int ld_dqkv, float* dbias_qkv_accum, plb_stream_t stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  PLB_REQUIRE(qkv && seq_start && q_len && kv_len && ctx && dctx && lse2 && delta && dqkv, PLB_ERR_ARG, "attn_bwd_tc: null pointer");
+  PLB_REQUIRE(qkv && seq_start && q_len && kv_len && dctx && lse2 && delta && dqkv, PLB_ERR_ARG, "attn_bwd_tc: null pointer");
   PLB_REQUIRE(head_dim == D, PLB_ERR_UNSUPPORTED, "attn_bwd_tc: head_dim %d not supported (only 64)", head_dim);
   PLB_REQUIRE(B > 0 && heads > 0 && total_rows > 0, PLB_ERR_ARG, "attn_bwd_tc: bad sizes");
   PLB_REQUIRE(max_q_len > 0 && max_q_len <= MAX_BOXES * 128, PLB_ERR_UNSUPPORTED,
               "attn_bwd_tc: sequences longer than %d rows are not supported (got %d)", MAX_BOXES * 128, max_q_len);
   PLB_REQUIRE(ld_qkv % 8 == 0 && ld_ctx % 8 == 0 && ld_dqkv % 8 == 0 && (reinterpret_cast<uintptr_t>(qkv) % 16) == 0 &&
-                  (reinterpret_cast<uintptr_t>(ctx) % 16) == 0 && (reinterpret_cast<uintptr_t>(dctx) % 16) == 0 &&
+                  (reinterpret_cast<uintptr_t>(ctx) % 16) == 0 && (reinterpret_cast<uintptr_t>(dctx) % 16) == 0 &&  /* NULL ctx passes */
                   (reinterpret_cast<uintptr_t>(dqkv) % 16) == 0,
               PLB_ERR_ARG, "attn_bwd_tc: operands must be 16-byte aligned with ld %% 8 == 0");
   CUtensorMap tm_qkv128, tm_qkv64, tm_dctx128, tm_dctx64;
@@ -1177,11 +1177,14 @@ extern "C" int plb_attn_bwd_tc(const void* qkv, int ld_qkv, const int32_t* seq_s
   }
   AttnTcParams p{seq_start, q_len, kv_len, heads, total_rows, 1.4426950408889634f / sqrtf((float)head_dim),
                  1.f / sqrtf((float)head_dim)};
-  const int dgrid = (total_rows + 7) / 8 < sm_count() * 8 ? (total_rows + 7) / 8 : sm_count() * 8;
-  attn_delta_kernel<<<dgrid, 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(dctx), static_cast<const __nv_bfloat16*>(ctx),
-                                               ld_ctx, total_rows, heads, total_rows, delta);
-  int rc = check_launch("plb_attn_bwd_tc(delta)");
-  if (rc) return rc;
+  int rc = PLB_OK;
+  if (ctx != nullptr) {  // otherwise delta was produced by the O-projection DGRAD (PLB_EPI_ROWDOT)
+    const int dgrid = (total_rows + 7) / 8 < sm_count() * 8 ? (total_rows + 7) / 8 : sm_count() * 8;
+    attn_delta_kernel<<<dgrid, 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(dctx), static_cast<const __nv_bfloat16*>(ctx),
+                                                 ld_ctx, total_rows, heads, total_rows, delta);
+    rc = check_launch("plb_attn_bwd_tc(delta)");
+    if (rc) return rc;
+  }
   attn_bwd_dq_tc_kernel<<<B * heads, BWD_THREADS, DqSmem::kAlloc, stream>>>(tm_qkv128, tm_dctx128, p, lse2, delta,
                                                                             static_cast<__nv_bfloat16*>(dqkv), ld_dqkv,
                                                                             dbias_qkv_accum);

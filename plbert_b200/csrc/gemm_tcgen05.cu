@@ -45,7 +45,7 @@ constexpr int GRP_COLS = EPI_COLS / EPI_GROUPS;   // columns of a chunk one thre
 constexpr int GRP_PIECES = GRP_COLS / 8;          // 16-byte pieces of a staged row one thread handles
 constexpr int TMEM_COLS = 512;
 
-enum Epi : int { kNone = 0, kResidual = 1, kGelu = 2, kGeluBwd = 3, kAtomicF32 = 4 };
+enum Epi : int { kNone = 0, kResidual = 1, kGelu = 2, kGeluBwd = 3, kAtomicF32 = 4, kRowDot = 5 };
 
 struct GemmParams {
   int M, N, K;
@@ -57,6 +57,8 @@ struct GemmParams {
   const float* bias;  // [N] or null
   float* c_f32;       // WGRAD output
   int ldc;
+  float* rowdot;      // kRowDot: fp32 [N / 64][rowdot_ld] accumulators of sum_n C[m,n] * aux_in[m,n] per 64-column block
+  int rowdot_ld;
 };
 
 template <int kStages, int kBufs, int kCta>
@@ -239,7 +241,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CU
     float* s_bias = reinterpret_cast<float*>(smem + L::kBiasOff);
     const uint32_t s_bias_addr = smem_u32(s_bias);
     const int epi_tid = threadIdx.x - 64;
-    constexpr bool kHasAuxIn = (kEpi == kResidual || kEpi == kGeluBwd);
+    constexpr bool kHasAuxIn = (kEpi == kResidual || kEpi == kGeluBwd || kEpi == kRowDot);
     constexpr bool kDual = (kEpi == kGelu);
     constexpr int kSlots = kDual ? kBufs / 2 : kBufs;
     static_assert(kEpi == kAtomicF32 || kSlots >= 2, "need at least two staging slots");
@@ -332,6 +334,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CU
           if constexpr (EPI_GROUPS == 1) tmem_ld_32x32(taddr + c * EPI_COLS + 32, v1);
           if (kHasAuxIn) mbar_wait(&epi_in[slot], (seq / kSlots) & 1);
           tmem_ld_wait();
+          f32x2 dot2 = f2_splat(0.f);  // kRowDot: this thread's part of sum_n C[m,n] * aux_in[m,n] over the chunk
 
 #pragma unroll
           for (int jl = 0; jl < GRP_PIECES; ++jl) {  // this thread's 16-byte pieces of its 128-byte staged row
@@ -351,14 +354,17 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CU
               f[2] = f2_add(f[2], f2_pack(b1.x, b1.y)); f[3] = f2_add(f[3], f2_pack(b1.z, b1.w));
             }
             const uint32_t piece = my_row + ((j ^ (row & 7)) << 4);
+            uint32_t aw[4] = {0u, 0u, 0u, 0u};
             if (kHasAuxIn) {
               const uint4 a = lds128(piece);
-              const uint32_t aw[4] = {a.x, a.y, a.z, a.w};
+              aw[0] = a.x; aw[1] = a.y; aw[2] = a.z; aw[3] = a.w;
+              if (kEpi != kRowDot) {
 #pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                const f32x2 x = f2_from_bf16x2(aw[i]);
-                if (kEpi == kResidual) f[i] = f2_add(f[i], x);
-                else f[i] = f2_mul(f[i], gelu_new_grad_x2(x));  // kGeluBwd: acc * gelu'(u)
+                for (int i = 0; i < 4; ++i) {
+                  const f32x2 x = f2_from_bf16x2(aw[i]);
+                  if (kEpi == kResidual) f[i] = f2_add(f[i], x);
+                  else f[i] = f2_mul(f[i], gelu_new_grad_x2(x));  // kGeluBwd: acc * gelu'(u)
+                }
               }
             }
             if (kDual) {
@@ -375,7 +381,20 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CU
             uint4 o;
             o.x = f2_to_bf16x2(f[0]); o.y = f2_to_bf16x2(f[1]);
             o.z = f2_to_bf16x2(f[2]); o.w = f2_to_bf16x2(f[3]);
+            if (kEpi == kRowDot) {  // the dot product runs over the ROUNDED outputs: what the consumer of C will read
+              dot2 = f2_fma(f2_from_bf16x2(o.x), f2_from_bf16x2(aw[0]), dot2);
+              dot2 = f2_fma(f2_from_bf16x2(o.y), f2_from_bf16x2(aw[1]), dot2);
+              dot2 = f2_fma(f2_from_bf16x2(o.z), f2_from_bf16x2(aw[2]), dot2);
+              dot2 = f2_fma(f2_from_bf16x2(o.w), f2_from_bf16x2(aw[3]), dot2);
+            }
             sts128(piece, o);
+          }
+          if (kEpi == kRowDot) {
+            float lo, hi;
+            f2_unpack(dot2, lo, hi);
+            const int m = m0 + row;
+            // out-of-range columns of the chunk contribute exact zeros (TMA zero-fills aux_in and B)
+            if (m < p.M) atomicAdd(p.rowdot + static_cast<size_t>(nc / EPI_COLS) * p.rowdot_ld + m, lo + hi);
           }
           fence_proxy_async_smem();
           if (leader && !kHasAuxIn) {
@@ -543,7 +562,13 @@ extern "C" int plb_gemm_bf16(int op, int epilogue, int M, int N, int K, const vo
   p.num_units = p.m_tiles * p.n_tiles;
   if (!tensor_map_bf16(&tc, C, M, N, ldc, BM, EPI_COLS)) return PLB_ERR_CUDA;
   tin = tout = tc;
-  if (epilogue == PLB_EPI_RESIDUAL || epilogue == PLB_EPI_GELU_BWD) {
+  if (epilogue == PLB_EPI_ROWDOT) {
+    PLB_REQUIRE(op == PLB_GEMM_DGRAD && aux_out && ld_aux_out >= M && (N % EPI_COLS) == 0 && bias == nullptr, PLB_ERR_ARG,
+                "gemm: ROWDOT needs op DGRAD, an fp32 aux_out with ld_aux_out >= M, N %% 64 == 0 and no bias");
+    p.rowdot = static_cast<float*>(aux_out);
+    p.rowdot_ld = ld_aux_out;
+  }
+  if (epilogue == PLB_EPI_RESIDUAL || epilogue == PLB_EPI_GELU_BWD || epilogue == PLB_EPI_ROWDOT) {
     PLB_REQUIRE(aux_in && (ld_aux_in % 8) == 0 && ((uintptr_t)aux_in % 16) == 0, PLB_ERR_ARG,
                 "gemm: epilogue %d needs an aligned aux_in", epilogue);
     if (!tensor_map_bf16(&tin, aux_in, M, N, ld_aux_in, BM, EPI_COLS)) return PLB_ERR_CUDA;
@@ -566,6 +591,7 @@ extern "C" int plb_gemm_bf16(int op, int epilogue, int M, int N, int K, const vo
       case PLB_EPI_NONE:     PLB_LAUNCH(false, true, kNone, 4, 2, 6, 2);
       case PLB_EPI_RESIDUAL: PLB_LAUNCH(false, true, kResidual, 3, 4, 5, 4);
       case PLB_EPI_GELU_BWD: PLB_LAUNCH(false, true, kGeluBwd, 3, 4, 5, 4);
+      case PLB_EPI_ROWDOT:   PLB_LAUNCH(false, true, kRowDot, 3, 4, 5, 4);
       default: break;
     }
   }

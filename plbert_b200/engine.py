@@ -23,7 +23,7 @@ from typing import Dict, List, Optional, Tuple
 import torch
 
 from . import _abi
-from ._abi import EPI_GELU, EPI_GELU_BWD, EPI_NONE, EPI_RESIDUAL, GEMM_DGRAD, GEMM_FWD, GEMM_WGRAD, call, ptr
+from ._abi import EPI_GELU, EPI_GELU_BWD, EPI_NONE, EPI_RESIDUAL, EPI_ROWDOT, GEMM_DGRAD, GEMM_FWD, GEMM_WGRAD, call, ptr
 from .batch import DeviceBatch
 
 _LAYER = "encoder.encoder.albert_layer_groups.0.albert_layers.0."
@@ -364,6 +364,7 @@ class Engine:
         o = self.layout.offsets
         g_wqkv = self.grads[o[att + "query.weight"]:o[att + "query.weight"] + 3 * H * H].view(3 * H, H)
         g_bqkv = self.grads[o[att + "query.bias"]:o[att + "query.bias"] + 3 * H]
+        delta_flat = self.delta.view(-1)   # indexed [head * T + row] by the kernels
         for l in reversed(range(c.num_hidden_layers)):
             A = self.acts[l]
             x_in = self.acts[l - 1]["y"] if l > 0 else self.x0
@@ -383,13 +384,16 @@ class Engine:
                  ptr(self.d_z), ptr(self.g(att + "LayerNorm.weight")), ptr(self.g(att + "LayerNorm.bias")),
                  ptr(self.g(att + "dense.bias")), s)
             self._gemm(GEMM_WGRAD, EPI_NONE, H, H, T, self.d_z, H, A["ctx"], H, self.g(att + "dense.weight"), H)
-            self._gemm(GEMM_DGRAD, EPI_NONE, T, H, H, self.d_z, H, self.w(att + "dense.weight"), H, self.d_ctx, H)
+            # dO = dz Wo, and in the same epilogue attention's delta[h, row] = sum_d dO o O over each head's 64 columns
+            delta_flat[:nh * T].zero_()
+            self._gemm(GEMM_DGRAD, EPI_ROWDOT, T, H, H, self.d_z, H, self.w(att + "dense.weight"), H, self.d_ctx, H,
+                       aux_in=A["ctx"], ld_in=H, aux_out=self.delta, ld_out=T)
             call("plb_attn_bwd_tc", ptr(A["qkv"]), 3 * H, ptr(b.seq_start), ptr(b.q_len), ptr(b.kv_len), b.B, nh, H // nh, b.L,
-                 T, ptr(A["ctx"]), ptr(self.d_ctx), H, ptr(A["lse"]), ptr(self.delta), ptr(self.d_qkv), 3 * H,
-                 ptr(g_bqkv), s)  # also accumulates the QKV bias gradient (column sums of dqkv)
+                 T, 0, ptr(self.d_ctx), H, ptr(A["lse"]), ptr(self.delta), ptr(self.d_qkv), 3 * H,
+                 ptr(g_bqkv), s)  # ctx = NULL: delta is given; also accumulates the QKV bias gradient (column sums of dqkv)
             self._gemm(GEMM_WGRAD, EPI_NONE, 3 * H, H, T, self.d_qkv, 3 * H, x_in, H, g_wqkv, H)
             self._gemm(GEMM_DGRAD, EPI_RESIDUAL, T, H, 3 * H, self.d_qkv, 3 * H, wqkv, H, dy, H, aux_in=self.d_z, ld_in=H)
-            self.launches += 6  # 2 ln_bwd, 1 colsum, attention bwd = 3 kernels (delta, dQ, dK/dV)
+            self.launches += 5  # 2 ln_bwd, 1 colsum, attention bwd = 2 kernels (dQ, dK/dV); the delta memset is torch's
 
         # ---- embedding side -----------------------------------------------------------------------
         mp = "encoder.encoder.embedding_hidden_mapping_in."

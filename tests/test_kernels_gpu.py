@@ -102,6 +102,27 @@ def test_gemm_dgrad(dev, M, N, K, epi):
     assert rel(C[:, :N].float(), ref) < 6e-3
 
 
+@pytest.mark.parametrize("M,N,K", [(128, 64, 64), (1000, 768, 768), (4097, 256, 192), (77, 128, 2048)])
+def test_gemm_rowdot_epilogue(dev, M, N, K):
+    """PLB_EPI_ROWDOT: C = A W and, per 64-column block (= attention head), sum_n bf16(C[m,n]) * aux_in[m,n] accumulated
+    into an fp32 [N/64, M] array — attention's delta = rowsum(dO o O) fused into the GEMM that produces dO."""
+    A = torch.randn(M, K, device=dev).to(BF)
+    W = (torch.randn(K, N, device=dev) / math.sqrt(K)).to(BF)
+    O = torch.randn(M, N, device=dev).to(BF)
+    C = torch.full((M, N), float("nan"), device=dev, dtype=BF)
+    delta = torch.zeros(N // 64, M + 5, device=dev)          # ld_aux_out > M is allowed
+    _gemm(_abi.GEMM_DGRAD, _abi.EPI_ROWDOT, M, N, K, A, W, C, None, O, delta)
+    assert rel(C.float(), A.float() @ W.float()) < 6e-3
+    want = (C.float() * O.float()).view(M, N // 64, 64).sum(-1).T      # over the kernel's own ROUNDED outputs
+    assert (delta[:, :M] - want).abs().max() <= 1e-5 * want.abs().max() + 1e-6
+    assert not delta[:, M:].any()
+    # accumulates: a second launch doubles it
+    _gemm(_abi.GEMM_DGRAD, _abi.EPI_ROWDOT, M, N, K, A, W, C, None, O, delta)
+    assert (delta[:, :M] - 2 * want).abs().max() <= 2e-5 * want.abs().max() + 1e-6
+    with pytest.raises(_abi.PlbError):
+        _gemm(_abi.GEMM_FWD, _abi.EPI_ROWDOT, M, N, K, A, W.T.contiguous(), C, None, O, delta)
+
+
 @pytest.mark.parametrize("M,N,K", [(128, 256, 64), (188, 768, 1000), (2304, 768, 20000), (768, 2048, 4096), (768, 128, 3000)])
 def test_gemm_wgrad_accumulates(dev, M, N, K):
     ldm = (M + 7) // 8 * 8
@@ -255,6 +276,12 @@ def test_attention_fwd_bwd(dev, B, L, nh, lens, fwd, bwd):
         # fused bias gradient = column sums of the stored (rounded) dqkv, accumulated on top of the initial ones
         want = dqkv.float().sum(0)
         assert (dbias - 1 - want).abs().max() <= 1e-3 * want.abs().max() + 1e-4
+        # ctx == NULL: delta is an input (the O-projection DGRAD's ROWDOT epilogue produced it) -> identical gradients
+        d_in = (dctx.float() * ctx.float()).view(T, nh, 64).sum(-1).T.contiguous()
+        dqkv2 = torch.full((T, 3 * H), float("nan"), device=dev, dtype=BF)
+        call(bwd, ptr(qkv), 3 * H, ptr(seq_start), ptr(q_len), ptr(lens_t), B, nh, 64, L, T, 0, ptr(dctx), H,
+             ptr(lse), ptr(d_in), ptr(dqkv2), 3 * H, 0, S())
+        assert rel(dqkv2.float(), dqkv.float()) < 2e-3
     else:
         call(bwd, ptr(qkv), 3 * H, ptr(seq_start), ptr(q_len), ptr(lens_t), B, nh, 64, L, T, ptr(ctx), ptr(dctx), H,
              ptr(lse), ptr(delta), ptr(dqkv), 3 * H, S())
