@@ -84,5 +84,7 @@ def call(name: str, *args) -> None:
 
 
 def ptr(t) -> int:
-    """Device pointer of a torch tensor (None -> NULL)."""
-    return 0 if t is None else t.data_ptr()
+    """Device pointer of a torch tensor (None -> NULL); a plain int is passed through (cached arena addresses)."""
+    if t is None:
+        return 0
+    return t if isinstance(t, int) else t.data_ptr()

@@ -151,6 +151,12 @@ class Engine:
         self._cap_M = 0
         self.loss_buf = torch.zeros(1, dtype=torch.float32, device=device)
         self.comm_stream: Optional[torch.cuda.Stream] = None
+        # raw addresses of every tensor inside the (never reallocated) arenas: building torch views costs 3-5 us each and
+        # the step makes ~700 of them — host time that is exposed whenever the caller synchronises every step
+        lay = self.layout
+        self.pp = {n: self.params.data_ptr() + 4 * o for n, o in lay.offsets.items()}   # fp32 master
+        self.gp = {n: self.grads.data_ptr() + 4 * o for n, o in lay.offsets.items()}    # fp32 gradient
+        self.wp = {n: self.shadow.data_ptr() + 2 * o for n, o in lay.offsets.items()}   # bf16 shadow
 
     # ------------------------------------------------------------------ parameter views
     def view(self, arena: torch.Tensor, name: str) -> torch.Tensor:
@@ -215,15 +221,6 @@ class Engine:
              ptr(aux_out), ld_out, _stream())
         self.launches += 1
 
-    def _layer_weights(self):
-        att = _LAYER + "attention."
-        c = self.cfg
-        H = c.hidden_size
-        o = self.layout.offsets
-        wqkv = self.shadow[o[att + "query.weight"]:o[att + "query.weight"] + 3 * H * H].view(3 * H, H)
-        bqkv = self.params[o[att + "query.bias"]:o[att + "query.bias"] + 3 * H]
-        return wqkv, bqkv
-
     def forward(self, b: DeviceBatch, train: bool) -> torch.Tensor:
         """Encoder forward; returns last_hidden_state as bf16 [T, H] (a workspace view)."""
         c = self.cfg
@@ -236,14 +233,14 @@ class Engine:
             self.refresh_shadow()
         s = _stream()
         att = _LAYER + "attention."
-        call("plb_embed_ln_fwd", ptr(b.ids), ptr(b.pos), T, E, ptr(self.p(_EMB + "word_embeddings.weight")),
-             ptr(self.p(_EMB + "position_embeddings.weight")), ptr(self.p(_EMB + "token_type_embeddings.weight")),
-             ptr(self.p(_EMB + "LayerNorm.weight")), ptr(self.p(_EMB + "LayerNorm.bias")), c.layer_norm_eps,
+        call("plb_embed_ln_fwd", ptr(b.ids), ptr(b.pos), T, E, self.pp[_EMB + "word_embeddings.weight"],
+             self.pp[_EMB + "position_embeddings.weight"], self.pp[_EMB + "token_type_embeddings.weight"],
+             self.pp[_EMB + "LayerNorm.weight"], self.pp[_EMB + "LayerNorm.bias"], c.layer_norm_eps,
              ptr(self.e), ptr(self.e_stats), s)
         self.launches += 1
         mp = "encoder.encoder.embedding_hidden_mapping_in."
-        self._gemm(GEMM_FWD, EPI_NONE, T, H, E, self.e, E, self.w(mp + "weight"), E, self.x0, H, bias=self.p(mp + "bias"))
-        wqkv, bqkv = self._layer_weights()
+        self._gemm(GEMM_FWD, EPI_NONE, T, H, E, self.e, E, self.wp[mp + "weight"], E, self.x0, H, bias=self.pp[mp + "bias"])
+        wqkv, bqkv = self.wp[att + "query.weight"], self.pp[att + "query.bias"]   # q|k|v are adjacent: one [3H, H] matrix
         x = self.x0
         for l in range(c.num_hidden_layers):
             A = self.acts[l if train else l % 2]
@@ -251,16 +248,16 @@ class Engine:
             call("plb_attn_fwd_tc", ptr(A["qkv"]), 3 * H, ptr(b.seq_start), ptr(b.q_len), ptr(b.kv_len), b.B, nh, H // nh,
                  b.L, T, ptr(A["ctx"]), H, ptr(A["lse"]), s)
             self.launches += 1
-            self._gemm(GEMM_FWD, EPI_RESIDUAL, T, H, H, A["ctx"], H, self.w(att + "dense.weight"), H, A["z1"], H,
-                       bias=self.p(att + "dense.bias"), aux_in=x, ld_in=H)
-            call("plb_ln_fwd", ptr(A["z1"]), T, H, ptr(self.p(att + "LayerNorm.weight")), ptr(self.p(att + "LayerNorm.bias")),
+            self._gemm(GEMM_FWD, EPI_RESIDUAL, T, H, H, A["ctx"], H, self.wp[att + "dense.weight"], H, A["z1"], H,
+                       bias=self.pp[att + "dense.bias"], aux_in=x, ld_in=H)
+            call("plb_ln_fwd", ptr(A["z1"]), T, H, self.pp[att + "LayerNorm.weight"], self.pp[att + "LayerNorm.bias"],
                  c.layer_norm_eps, ptr(A["a"]), ptr(A["st1"]), s)
-            self._gemm(GEMM_FWD, EPI_GELU, T, I, H, A["a"], H, self.w(_LAYER + "ffn.weight"), H, A["g"], I,
-                       bias=self.p(_LAYER + "ffn.bias"), aux_out=A["u"], ld_out=I)
-            self._gemm(GEMM_FWD, EPI_RESIDUAL, T, H, I, A["g"], I, self.w(_LAYER + "ffn_output.weight"), I, A["z2"], H,
-                       bias=self.p(_LAYER + "ffn_output.bias"), aux_in=A["a"], ld_in=H)
-            call("plb_ln_fwd", ptr(A["z2"]), T, H, ptr(self.p(_LAYER + "full_layer_layer_norm.weight")),
-                 ptr(self.p(_LAYER + "full_layer_layer_norm.bias")), c.layer_norm_eps, ptr(A["y"]), ptr(A["st2"]), s)
+            self._gemm(GEMM_FWD, EPI_GELU, T, I, H, A["a"], H, self.wp[_LAYER + "ffn.weight"], H, A["g"], I,
+                       bias=self.pp[_LAYER + "ffn.bias"], aux_out=A["u"], ld_out=I)
+            self._gemm(GEMM_FWD, EPI_RESIDUAL, T, H, I, A["g"], I, self.wp[_LAYER + "ffn_output.weight"], I, A["z2"], H,
+                       bias=self.pp[_LAYER + "ffn_output.bias"], aux_in=A["a"], ld_in=H)
+            call("plb_ln_fwd", ptr(A["z2"]), T, H, self.pp[_LAYER + "full_layer_layer_norm.weight"],
+                 self.pp[_LAYER + "full_layer_layer_norm.bias"], c.layer_norm_eps, ptr(A["y"]), ptr(A["st2"]), s)
             self.launches += 2
             x = A["y"]
         return x[:T]
@@ -360,33 +357,31 @@ class Engine:
         self.grads_clean = False
         self.have_grads = True
         # ---- 12 applications of the shared layer, last to first ----------------------------------
-        wqkv, _ = self._layer_weights()
-        o = self.layout.offsets
-        g_wqkv = self.grads[o[att + "query.weight"]:o[att + "query.weight"] + 3 * H * H].view(3 * H, H)
-        g_bqkv = self.grads[o[att + "query.bias"]:o[att + "query.bias"] + 3 * H]
+        wqkv = self.wp[att + "query.weight"]                                        # q|k|v adjacent: [3H, H]
+        g_wqkv, g_bqkv = self.gp[att + "query.weight"], self.gp[att + "query.bias"]
         delta_flat = self.delta.view(-1)   # indexed [head * T + row] by the kernels
         for l in reversed(range(c.num_hidden_layers)):
             A = self.acts[l]
             x_in = self.acts[l - 1]["y"] if l > 0 else self.x0
             # y = LN2(z2), z2 = a + g W2^T + b2
-            call("plb_ln_bwd", ptr(dy), ptr(A["z2"]), ptr(A["st2"]), ptr(self.p(_LAYER + "full_layer_layer_norm.weight")), T, H,
-                 ptr(self.d_z), ptr(self.g(_LAYER + "full_layer_layer_norm.weight")),
-                 ptr(self.g(_LAYER + "full_layer_layer_norm.bias")), ptr(self.g(_LAYER + "ffn_output.bias")), s)
-            self._gemm(GEMM_WGRAD, EPI_NONE, H, I, T, self.d_z, H, A["g"], I, self.g(_LAYER + "ffn_output.weight"), I)
-            self._gemm(GEMM_DGRAD, EPI_GELU_BWD, T, I, H, self.d_z, H, self.w(_LAYER + "ffn_output.weight"), I, self.d_u, I,
+            call("plb_ln_bwd", ptr(dy), ptr(A["z2"]), ptr(A["st2"]), self.pp[_LAYER + "full_layer_layer_norm.weight"], T, H,
+                 ptr(self.d_z), self.gp[_LAYER + "full_layer_layer_norm.weight"],
+                 self.gp[_LAYER + "full_layer_layer_norm.bias"], self.gp[_LAYER + "ffn_output.bias"], s)
+            self._gemm(GEMM_WGRAD, EPI_NONE, H, I, T, self.d_z, H, A["g"], I, self.gp[_LAYER + "ffn_output.weight"], I)
+            self._gemm(GEMM_DGRAD, EPI_GELU_BWD, T, I, H, self.d_z, H, self.wp[_LAYER + "ffn_output.weight"], I, self.d_u, I,
                        aux_in=A["u"], ld_in=I)
-            call("plb_colsum", ptr(self.d_u), I, T, I, ptr(self.g(_LAYER + "ffn.bias")), s)
-            self._gemm(GEMM_WGRAD, EPI_NONE, I, H, T, self.d_u, I, A["a"], H, self.g(_LAYER + "ffn.weight"), H)
-            self._gemm(GEMM_DGRAD, EPI_RESIDUAL, T, H, I, self.d_u, I, self.w(_LAYER + "ffn.weight"), H, self.d_a, H,
+            call("plb_colsum", ptr(self.d_u), I, T, I, self.gp[_LAYER + "ffn.bias"], s)
+            self._gemm(GEMM_WGRAD, EPI_NONE, I, H, T, self.d_u, I, A["a"], H, self.gp[_LAYER + "ffn.weight"], H)
+            self._gemm(GEMM_DGRAD, EPI_RESIDUAL, T, H, I, self.d_u, I, self.wp[_LAYER + "ffn.weight"], H, self.d_a, H,
                        aux_in=self.d_z, ld_in=H)
             # a = LN1(z1), z1 = x + ctx Wo^T + bo
-            call("plb_ln_bwd", ptr(self.d_a), ptr(A["z1"]), ptr(A["st1"]), ptr(self.p(att + "LayerNorm.weight")), T, H,
-                 ptr(self.d_z), ptr(self.g(att + "LayerNorm.weight")), ptr(self.g(att + "LayerNorm.bias")),
-                 ptr(self.g(att + "dense.bias")), s)
-            self._gemm(GEMM_WGRAD, EPI_NONE, H, H, T, self.d_z, H, A["ctx"], H, self.g(att + "dense.weight"), H)
+            call("plb_ln_bwd", ptr(self.d_a), ptr(A["z1"]), ptr(A["st1"]), self.pp[att + "LayerNorm.weight"], T, H,
+                 ptr(self.d_z), self.gp[att + "LayerNorm.weight"], self.gp[att + "LayerNorm.bias"],
+                 self.gp[att + "dense.bias"], s)
+            self._gemm(GEMM_WGRAD, EPI_NONE, H, H, T, self.d_z, H, A["ctx"], H, self.gp[att + "dense.weight"], H)
             # dO = dz Wo, and in the same epilogue attention's delta[h, row] = sum_d dO o O over each head's 64 columns
             delta_flat[:nh * T].zero_()
-            self._gemm(GEMM_DGRAD, EPI_ROWDOT, T, H, H, self.d_z, H, self.w(att + "dense.weight"), H, self.d_ctx, H,
+            self._gemm(GEMM_DGRAD, EPI_ROWDOT, T, H, H, self.d_z, H, self.wp[att + "dense.weight"], H, self.d_ctx, H,
                        aux_in=A["ctx"], ld_in=H, aux_out=self.delta, ld_out=T)
             call("plb_attn_bwd_tc", ptr(A["qkv"]), 3 * H, ptr(b.seq_start), ptr(b.q_len), ptr(b.kv_len), b.B, nh, H // nh, b.L,
                  T, 0, ptr(self.d_ctx), H, ptr(A["lse"]), ptr(self.delta), ptr(self.d_qkv), 3 * H,
@@ -397,15 +392,15 @@ class Engine:
 
         # ---- embedding side -----------------------------------------------------------------------
         mp = "encoder.encoder.embedding_hidden_mapping_in."
-        call("plb_colsum", ptr(dy), H, T, H, ptr(self.g(mp + "bias")), s)
-        self._gemm(GEMM_WGRAD, EPI_NONE, H, E, T, dy, H, self.e, E, self.g(mp + "weight"), E)
-        self._gemm(GEMM_DGRAD, EPI_NONE, T, E, H, dy, H, self.w(mp + "weight"), E, self.d_e, E)
-        call("plb_embed_ln_bwd", ptr(self.d_e), ptr(b.ids), ptr(b.pos), T, E, c.vocab_size, ptr(self.p(_EMB + "word_embeddings.weight")),
-             ptr(self.p(_EMB + "position_embeddings.weight")), ptr(self.p(_EMB + "token_type_embeddings.weight")),
-             ptr(self.p(_EMB + "LayerNorm.weight")), ptr(self.e_stats), c.pad_token_id,
-             ptr(self.g(_EMB + "word_embeddings.weight")), ptr(self.g(_EMB + "position_embeddings.weight")),
-             ptr(self.g(_EMB + "token_type_embeddings.weight")), ptr(self.g(_EMB + "LayerNorm.weight")),
-             ptr(self.g(_EMB + "LayerNorm.bias")), s)
+        call("plb_colsum", ptr(dy), H, T, H, self.gp[mp + "bias"], s)
+        self._gemm(GEMM_WGRAD, EPI_NONE, H, E, T, dy, H, self.e, E, self.gp[mp + "weight"], E)
+        self._gemm(GEMM_DGRAD, EPI_NONE, T, E, H, dy, H, self.wp[mp + "weight"], E, self.d_e, E)
+        call("plb_embed_ln_bwd", ptr(self.d_e), ptr(b.ids), ptr(b.pos), T, E, c.vocab_size, self.pp[_EMB + "word_embeddings.weight"],
+             self.pp[_EMB + "position_embeddings.weight"], self.pp[_EMB + "token_type_embeddings.weight"],
+             self.pp[_EMB + "LayerNorm.weight"], ptr(self.e_stats), c.pad_token_id,
+             self.gp[_EMB + "word_embeddings.weight"], self.gp[_EMB + "position_embeddings.weight"],
+             self.gp[_EMB + "token_type_embeddings.weight"], self.gp[_EMB + "LayerNorm.weight"],
+             self.gp[_EMB + "LayerNorm.bias"], s)
         self.launches += 2
         self._after_encoder_backward()
 
