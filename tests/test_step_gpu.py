@@ -150,6 +150,39 @@ def test_step_matches_oracle(dev, two_heads, varlen):
     assert all(set(v) == {"step", "exp_avg", "exp_avg_sq"} for v in sd["state"].values())
 
 
+def test_training_trajectory_tracks_oracle(dev):
+    """Eight optimizer steps (lr 1e-3 so that the weights really move) on eight different batches: the CUDA path's loss at
+    every step stays within the north star's bf16 bar (rel 2e-2) of the fp64 oracle trained on the same batches from the
+    same weights — forward, backward, in-place shared-layer accumulation and AdamW compose correctly over time."""
+    from plbert_b200.batch import BatchFeeder, synthetic_collate_batch
+    import plbert_b200 as P
+    cfgv = [188, 32, 128, 2, 256, 3, 128, 211]
+    model = build_model(cfgv, True, dev, seed=13)
+    params = {k: v.detach().cpu().double().numpy() for k, v in model.state_dict().items()}
+    model_init = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    batches = [synthetic_collate_batch(4, 128, seed=50 + i, variable_length=(i % 2 == 1), min_length=16, with_token_ids=True,
+                                       num_tokens=211, word_pred_prob=0.3) for i in range(8)]
+    opt = P.FusedAdamW(model.parameters(), lr=1e-3)
+    feed = BatchFeeder(model, batches)
+    got, want, state = [], [], {}
+    for tok, lab, msk, lens, midx in batches:
+        loss = feed.step()
+        opt.step()
+        got.append(loss.item())
+        total, _, grads, _ = O.loss_and_grads(params, oracle_cfg(cfgv), msk.numpy(), lab.numpy(), lens, midx, token_labels=tok.numpy())
+        O.adamw_step(params, grads, state, lr=1e-3)
+        want.append(float(total))
+    moved = max(float(np.abs(params[n] - v.detach().cpu().double().numpy()).max()) for n, v in model_init.items())
+    assert moved > 4e-3, moved                                  # eight steps at lr 1e-3 really moved the weights
+    for i, (a, b) in enumerate(zip(got, want)):
+        assert abs(a - b) <= 2e-2 * abs(b), (i, got, want)
+    # the weights after eight steps agree as well (AdamW normalises tiny gradients to +-lr, hence the loose direction bar)
+    for n, p in model.named_parameters():
+        if "pooler" in n or n.endswith("attention.key.bias"):
+            continue
+        assert cosine(p.detach().cpu().double().numpy(), params[n]) > 0.999, n
+
+
 def test_packed_layout_equals_padded_layout(dev):
     """Variable-length batches run without their padding rows.  The reference computes the padded
     rows and never reads them, so loss and gradients must not change; only the fp32 summation order of the weight
