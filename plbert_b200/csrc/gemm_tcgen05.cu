@@ -8,11 +8,13 @@
 //   DGRAD (A K-major,  B MN-major):  C[M,N]  = A[M,K] W[K,N]
 //   WGRAD (A MN-major, B MN-major):  C[M,N] += A[K,M]^T B[K,N]   (fp32 atomics, split-K)
 //
-// CTA = 6 warps: warp 0 TMA producer, warp 1 TMEM owner + single-thread MMA issuer, warps 2..5
-// epilogue (one accumulator row per thread, tcgen05.ld 32x32b).  Tile 128 x 256 x 64, fp32
-// accumulators double-buffered in TMEM (2 x 256 columns) so the epilogue of unit i overlaps the
-// main loop of unit i+1.  Epilogue output goes registers -> swizzled smem -> TMA store; a residual /
-// pre-activation operand comes in by TMA into the same staging buffer and is updated in place.
+// CTA = 11 warps: warp 0 TMA producer, warp 1 TMEM owner + single-thread MMA issuer, warps 2..9
+// epilogue (one accumulator row per thread, tcgen05.ld 32x32b; the two warps that share a TMEM lane
+// quadrant take 32 columns each of every 64-column chunk), warp 10 store warp (TMA stores of staged
+// chunks + aux-operand prefetches).  Tile 128 x 256 x 64, fp32 accumulators double-buffered in TMEM
+// (2 x 256 columns) so the epilogue of unit i overlaps the main loop of unit i+1.  Epilogue output goes
+// registers -> swizzled smem -> TMA store; a residual / pre-activation operand comes in by TMA into the
+// same staging buffer and is updated in place.
 #include "common.cuh"
 
 #include <cstdlib>
@@ -40,7 +42,12 @@ constexpr int MN_BOX_BYTES = 64 * 64 * 2;       // one MN-major TMA box: 64 K-ro
 constexpr int EPI_GROUPS = PLB_EPI_GROUPS;
 static_assert(EPI_GROUPS == 1 || EPI_GROUPS == 2, "one or two epilogue warp groups");
 constexpr int EPI_THREADS = 128 * EPI_GROUPS;
-constexpr int NUM_THREADS = 64 + EPI_THREADS;
+// A dedicated store warp (one elected thread) issues the TMA stores of finished chunks and the aux-in prefetches and hands
+// the staging slots back through mbarriers, so the epilogue warps never meet at a CTA barrier per chunk and never wait
+// behind the leader's bulk-group waits (ncu: 13-22 % of the fused-epilogue kernels' samples sat on that barrier; the
+// GELU' DGRAD gained 7 %, the O projection 4 % — profiles/r1f_gemm_selftest_perf.txt).
+constexpr int STORE_WARP = 2 + EPI_THREADS / 32;  // warp index of the store warp
+constexpr int NUM_THREADS = 64 + EPI_THREADS + 32;
 constexpr int GRP_COLS = EPI_COLS / EPI_GROUPS;   // columns of a chunk one thread handles
 constexpr int GRP_PIECES = GRP_COLS / 8;          // 16-byte pieces of a staged row one thread handles
 constexpr int TMEM_COLS = 512;
@@ -68,7 +75,8 @@ struct SmemLayout {
   static constexpr int kEpiOff = kStages * kStageBytes;
   static constexpr int kBarOff = kEpiOff + kBufs * EPI_BUF_BYTES;
   // full[kStages], empty[kStages], tmem_full[2], tmem_empty[2], epi_in[kBufs], tmem ptr
-  static constexpr int kNumBars = 2 * kStages + 4 + kBufs;
+  // full[kStages], empty[kStages], tmem_full[2], tmem_empty[2], epi_in[kBufs], chunk_ready[kBufs], slot_free[kBufs]
+  static constexpr int kNumBars = 2 * kStages + 4 + 3 * kBufs;
   static constexpr int kBiasOff = kBarOff + kNumBars * 8 + 16;   // fp32 bias of the current tile: BN floats
   static constexpr int kBytes = kBiasOff + BN * 4;
   static constexpr int kAlloc = kBytes + 1024;  // slack for manual 1024 B alignment
@@ -113,6 +121,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CU
   uint64_t* tmem_full = bars + 2 * kStages;
   uint64_t* tmem_empty = bars + 2 * kStages + 2;
   uint64_t* epi_in = bars + 2 * kStages + 4;
+  uint64_t* chunk_ready = epi_in + kBufs;   // epilogue warps -> store warp: the chunk is staged (count = epilogue warps)
+  uint64_t* slot_free = chunk_ready + kBufs;  // store warp -> epilogue warps: the slot's store has been read out
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + L::kNumBars);
 
   const int warp = threadIdx.x >> 5;
@@ -130,7 +140,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CU
       mbar_init(&tmem_full[i], 1);
       mbar_init(&tmem_empty[i], 4 * EPI_GROUPS * kCta);  // one arrive per epilogue warp of every CTA of the pair
     }
-    for (int i = 0; i < kBufs; ++i) mbar_init(&epi_in[i], 1);
+    for (int i = 0; i < kBufs; ++i) {
+      mbar_init(&epi_in[i], 1);
+      mbar_init(&chunk_ready[i], EPI_THREADS / 32);
+      mbar_init(&slot_free[i], 1);
+    }
     fence_mbar_init();
   }
   if (warp == 1) {
@@ -231,12 +245,65 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CU
       }
     }
     __syncwarp();
+  } else if (warp == STORE_WARP) {
+    // =========================== store warp ===========================
+    // Walks the same (unit, chunk) sequence as the epilogue warps: waits until a chunk is staged, stores it, and once
+    // the store has been read out of shared memory recycles the slot (aux-in prefetch of chunk seq + kSlots, or a
+    // slot_free arrive when there is no aux operand).
+    constexpr bool kHasAuxIn = (kEpi == kResidual || kEpi == kGeluBwd || kEpi == kRowDot);
+    constexpr bool kDual = (kEpi == kGelu);
+    constexpr int kSlots = kDual ? kBufs / 2 : kBufs;
+    if (kEpi != kAtomicF32 && elect_one_sync()) {
+      uint8_t* epi_smem = smem + L::kEpiOff;
+      int la_u = unit0, la_c = 0;
+      uint32_t la_seq = 0;
+      auto la_issue = [&]() {  // aux load of the next not-yet-issued chunk, if any
+        while (la_u < p.num_units) {
+          int m_blk, n_blk, k_begin, k_end;
+          unit_coords(p, la_u, m_blk, n_blk, k_begin, k_end);
+          const int n0 = n_blk * BN + la_c * EPI_COLS;
+          if (la_c < BN / EPI_COLS && n0 < p.N) {
+            const int slot = la_seq % kSlots;
+            mbar_arrive_expect_tx(&epi_in[slot], EPI_BUF_BYTES);
+            tma_load_2d(epi_smem + slot * EPI_BUF_BYTES, &tm_aux_in, &epi_in[slot], n0, (m_blk * kCta + rank) * BM);
+            ++la_seq;
+            ++la_c;
+            return;
+          }
+          la_u += unit_stride;
+          la_c = 0;
+        }
+      };
+      if (kHasAuxIn)
+        for (int i = 0; i < kSlots; ++i) la_issue();
+      uint32_t seq = 0;
+      for (int u = unit0; u < p.num_units; u += unit_stride) {
+        int m_blk, n_blk, k_begin, k_end;
+        unit_coords(p, u, m_blk, n_blk, k_begin, k_end);
+        const int m0 = (m_blk * kCta + rank) * BM, n0 = n_blk * BN;
+        for (int c = 0; c < BN / EPI_COLS; ++c) {
+          const int nc = n0 + c * EPI_COLS;
+          if (nc >= p.N) break;
+          const int slot = seq % kSlots;
+          uint8_t* buf = epi_smem + (kDual ? 2 * slot : slot) * EPI_BUF_BYTES;
+          mbar_wait(&chunk_ready[slot], (seq / kSlots) & 1);
+          tma_store_2d(&tm_c, buf, nc, m0);
+          if (kDual) tma_store_2d(&tm_aux_out, buf + EPI_BUF_BYTES, nc, m0);
+          bulk_commit();
+          bulk_wait_read<0>();                       // the slot has left shared memory
+          if (kHasAuxIn) la_issue();                 // chunk seq + kSlots goes into it; epi_in[slot] announces it
+          else mbar_arrive(&slot_free[slot]);
+          ++seq;
+        }
+      }
+      bulk_wait<0>();  // all stores globally visible before exit
+    }
+    __syncwarp();
   } else {
     // =========================== epilogue (warps 2..) ===========================
     const int quad = warp & 3;             // TMEM lane quadrant this warp may read
     const int grp = (warp - 2) >> 2;       // which column half of every chunk this warp handles (0 with one group)
     const int row = quad * 32 + lane;      // accumulator row owned by this thread
-    const bool leader = (threadIdx.x == 64);
     uint8_t* epi_smem = smem + L::kEpiOff;
     float* s_bias = reinterpret_cast<float*>(smem + L::kBiasOff);
     const uint32_t s_bias_addr = smem_u32(s_bias);
@@ -249,31 +316,6 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CU
     int acc = 0;
     uint32_t acc_phase = 0;
     uint32_t seq = 0;  // running chunk sequence number (staging slot = seq % kSlots)
-
-    // look-ahead iterator for the aux-in prefetch (leader only)
-    int la_u = unit0, la_c = 0;
-    uint32_t la_seq = 0;
-    auto la_issue = [&]() {
-      // issue the aux load for the next not-yet-issued chunk, if any
-      while (la_u < p.num_units) {
-        int m_blk, n_blk, k_begin, k_end;
-        unit_coords(p, la_u, m_blk, n_blk, k_begin, k_end);
-        const int n0 = n_blk * BN + la_c * EPI_COLS;
-        if (la_c < BN / EPI_COLS && n0 < p.N) {
-          const int slot = la_seq % kSlots;
-          mbar_arrive_expect_tx(&epi_in[slot], EPI_BUF_BYTES);
-          tma_load_2d(epi_smem + slot * EPI_BUF_BYTES, &tm_aux_in, &epi_in[slot], n0, (m_blk * kCta + rank) * BM);
-          ++la_seq;
-          ++la_c;
-          return;
-        }
-        la_u += unit_stride;
-        la_c = 0;
-      }
-    };
-    if (kHasAuxIn && leader) {
-      for (int i = 0; i < kSlots - 1; ++i) la_issue();
-    }
 
     const uint32_t lead_tmem_empty0 = (kCta == 2) ? mapa_u32(smem_u32(&tmem_empty[0]), 0) : 0;
     for (int u = unit0; u < p.num_units; u += unit_stride) {
@@ -333,6 +375,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CU
           tmem_ld_32x32(taddr + c * EPI_COLS + grp * GRP_COLS, v0);
           if constexpr (EPI_GROUPS == 1) tmem_ld_32x32(taddr + c * EPI_COLS + 32, v1);
           if (kHasAuxIn) mbar_wait(&epi_in[slot], (seq / kSlots) & 1);
+          else mbar_wait(&slot_free[slot], ((seq / kSlots) & 1) ^ 1);  // the previous use of the slot has been stored
           tmem_ld_wait();
           f32x2 dot2 = f2_splat(0.f);  // kRowDot: this thread's part of sum_n C[m,n] * aux_in[m,n] over the chunk
 
@@ -397,20 +440,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CU
             if (m < p.M) atomicAdd(p.rowdot + static_cast<size_t>(nc / EPI_COLS) * p.rowdot_ld + m, lo + hi);
           }
           fence_proxy_async_smem();
-          if (leader && !kHasAuxIn) {
-            // by this barrier the slot chunk seq+1 will write must have been read out by its last store
-            bulk_wait_read<(kSlots >= 2 ? kSlots - 2 : 0)>();
-          }
-          epi_bar_sync();
-          if (leader) {
-            tma_store_2d(&tm_c, buf, nc, m0);
-            if (kDual) tma_store_2d(&tm_aux_out, buf + EPI_BUF_BYTES, nc, m0);
-            bulk_commit();
-            if (kHasAuxIn) {
-              bulk_wait_read<1>();  // store seq-1 has left its slot -> prefetch chunk seq+kSlots-1 into it
-              la_issue();
-            }
-          }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&chunk_ready[slot]);  // one arrival per epilogue warp: the store warp takes it from here
           ++seq;
         }
       }
@@ -423,7 +454,6 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CU
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
-    if (leader && kEpi != kAtomicF32) bulk_wait<0>();  // all stores globally visible before exit
   }
 
   tc_fence_before();
@@ -583,7 +613,11 @@ extern "C" int plb_gemm_bf16(int op, int epilogue, int M, int N, int K, const vo
     switch (epilogue) {
       case PLB_EPI_NONE:     PLB_LAUNCH(false, false, kNone, 4, 2, 6, 2);
       case PLB_EPI_RESIDUAL: PLB_LAUNCH(false, false, kResidual, 3, 4, 5, 4);
-      case PLB_EPI_GELU:     PLB_LAUNCH(false, false, kGelu, 3, 4, 5, 4);
+#ifndef PLB_GELU_S2
+#define PLB_GELU_S2 5
+#define PLB_GELU_B2 4
+#endif
+      case PLB_EPI_GELU:     PLB_LAUNCH(false, false, kGelu, 3, 4, PLB_GELU_S2, PLB_GELU_B2);
       default: break;
     }
   } else {

@@ -119,7 +119,10 @@ static void run_case(int op, int epi, int M, int N, int K, bool with_bias) {
   if (bias) cudaFree(bias);
 }
 
+static const char* g_only = nullptr;  // --only <substring>: time just the matching perf cases (and skip the checks)
+
 static void perf_case(const char* label, int op, int epi, int M, int N, int K) {
+  if (g_only && !strstr(label, g_only)) return;
   int a_rows, a_cols, b_rows, b_cols;
   if (op == PLB_GEMM_FWD) { a_rows = M; a_cols = K; b_rows = N; b_cols = K; }
   else if (op == PLB_GEMM_DGRAD) { a_rows = M; a_cols = K; b_rows = K; b_cols = N; }
@@ -159,7 +162,9 @@ static void perf_case(const char* label, int op, int epi, int M, int N, int K) {
 
 int main(int argc, char** argv) {
   bool perf = argc > 1 && !strcmp(argv[1], "--perf");
+  if (perf && argc > 3 && !strcmp(argv[2], "--only")) g_only = argv[3];
   printf("plbert_b200 ABI %d, SMs %d\n", plb_abi_version(), plb_device_sm_count());
+  if (!g_only) {
   // aligned single tile, then multi-tile / multi-unit, then ragged shapes (TMA zero fill + clipping)
   run_case(PLB_GEMM_FWD, PLB_EPI_NONE, 128, 256, 64, false);
   run_case(PLB_GEMM_FWD, PLB_EPI_NONE, 128, 256, 256, true);
@@ -182,6 +187,7 @@ int main(int argc, char** argv) {
   run_case(PLB_GEMM_WGRAD, PLB_EPI_NONE, 2304, 768, 20000, false);
   run_case(PLB_GEMM_WGRAD, PLB_EPI_NONE, 768, 128, 5000, false);
   printf("%s (%d failing cases)\n", g_fail ? "SELFTEST FAILED" : "SELFTEST PASSED", g_fail);
+  }
   if (perf) {
     const int T = 98304;
     perf_case("fwd qkv   (bias)", PLB_GEMM_FWD, PLB_EPI_NONE, T, 2304, 768);
