@@ -348,7 +348,7 @@ def test_gather_scatter_bit_exact(dev):
     assert (acc[0] == 4).all() and not acc[1:].any()
 
 
-@pytest.mark.parametrize("M,V", [(1000, 188), (37, 97), (300, 5000)])
+@pytest.mark.parametrize("M,V", [(1000, 188), (37, 97), (300, 5000), (300, 5003), (200, 64000), (151, 65536), (40, 70000)])
 def test_masked_ce(dev, M, V):
     ld = (V + 7) // 8 * 8
     z = torch.zeros(M, ld, device=dev, dtype=BF)
