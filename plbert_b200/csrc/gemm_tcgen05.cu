@@ -52,6 +52,19 @@ constexpr int GRP_COLS = EPI_COLS / EPI_GROUPS;   // columns of a chunk one thre
 constexpr int GRP_PIECES = GRP_COLS / 8;          // 16-byte pieces of a staged row one thread handles
 constexpr int TMEM_COLS = 512;
 
+// Timeline instrumentation of ONE epilogue warp (CTA 0, warp 2): compiled only into the trace library that
+// profiles/gemm_trace.py builds with -DPLB_GEMM_TRACE; the product library contains none of it.
+#ifdef PLB_GEMM_TRACE
+__device__ unsigned long long g_gemm_trace[8192];
+#define PLB_GT(tag)                                                                                   \
+  do {                                                                                                \
+    if (blockIdx.x == 0 && warp == 2 && lane == 0 && gt_n < 8192)                                      \
+      g_gemm_trace[gt_n++] = (static_cast<unsigned long long>(tag) << 56) | (clock64() & 0xffffffffffffffULL); \
+  } while (0)
+#else
+#define PLB_GT(tag) do {} while (0)
+#endif
+
 enum Epi : int { kNone = 0, kResidual = 1, kGelu = 2, kGeluBwd = 3, kAtomicF32 = 4, kRowDot = 5 };
 
 struct GemmParams {
@@ -82,21 +95,47 @@ struct SmemLayout {
   static constexpr int kAlloc = kBytes + 1024;  // slack for manual 1024 B alignment
 };
 
-__device__ __forceinline__ void unit_coords(const GemmParams& p, int u, int& m_blk, int& n_blk, int& k_begin,
-                                            int& k_end) {
-  const int tiles = p.m_tiles * p.n_tiles;
-  const int tile = u % tiles;
-  const int split = u / tiles;
-  if (p.m_fast) {
-    m_blk = tile % p.m_tiles;
-    n_blk = tile / p.m_tiles;
-  } else {
-    n_blk = tile % p.n_tiles;
-    m_blk = tile / p.n_tiles;
+// Walks the units unit0, unit0 + stride, ... of a persistent CTA without per-unit integer divisions: the div/mod chain
+// of the straightforward index -> (m, n, split) mapping cost ~470 clk per tile on the epilogue's critical path
+// (profiles/r1f_gemm_epilogue_timeline.txt).  The position is kept as (fast tile, slow tile, split) digits and advanced
+// by the pre-divided stride with carries.  unit = (split * slow_size + slow) * fast_size + fast; the fast digit is the
+// tile dimension consecutive units walk along (GemmParams::m_fast).
+struct UnitWalker {
+  int u, stride;
+  int m_blk, n_blk, k_begin, k_end;
+  int f, s, sp, F, Sn, df, ds, dsp;
+  __device__ __forceinline__ UnitWalker(const GemmParams& p, int unit0, int stride_) : u(unit0), stride(stride_) {
+    F = p.m_fast ? p.m_tiles : p.n_tiles;
+    Sn = p.m_fast ? p.n_tiles : p.m_tiles;
+    int t = unit0 / F;
+    f = unit0 - t * F;
+    sp = t / Sn;
+    s = t - sp * Sn;
+    t = stride_ / F;
+    df = stride_ - t * F;
+    dsp = t / Sn;
+    ds = t - dsp * Sn;
+    set(p);
   }
-  k_begin = split * p.k_per_split;
-  k_end = min(k_begin + p.k_per_split, p.k_iters);
-}
+  __device__ __forceinline__ void set(const GemmParams& p) {
+    m_blk = p.m_fast ? f : s;
+    n_blk = p.m_fast ? s : f;
+    k_begin = sp * p.k_per_split;
+    k_end = min(k_begin + p.k_per_split, p.k_iters);
+  }
+  __device__ __forceinline__ bool valid(const GemmParams& p) const { return u < p.num_units; }
+  __device__ __forceinline__ void next(const GemmParams& p) {
+    u += stride;
+    f += df;
+    int carry = f >= F ? 1 : 0;
+    f -= carry ? F : 0;
+    s += ds + carry;
+    carry = s >= Sn ? 1 : 0;
+    s -= carry ? Sn : 0;
+    sp += dsp + carry;
+    set(p);
+  }
+};
 
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory"); }
 
@@ -160,10 +199,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CU
     if (elect_one_sync()) {  // elect.sync (not lane == 0): ptxas then emits the TMA / MMA instructions without waterfall loops
       int stage = 0;
       uint32_t phase = 0;
-      for (int u = unit0; u < p.num_units; u += unit_stride) {
-        int m_blk, n_blk, k_begin, k_end;
-        unit_coords(p, u, m_blk, n_blk, k_begin, k_end);
-        const int m0 = (m_blk * kCta + rank) * BM, n0 = n_blk * BN + rank * B_ROWS;
+      for (UnitWalker w(p, unit0, unit_stride); w.valid(p); w.next(p)) {
+        const int k_begin = w.k_begin, k_end = w.k_end;
+        const int m0 = (w.m_blk * kCta + rank) * BM, n0 = w.n_blk * BN + rank * B_ROWS;
         for (int kb = k_begin; kb < k_end; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * STAGE_BYTES;
@@ -215,9 +253,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CU
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int u = unit0; u < p.num_units; u += unit_stride) {
-        int m_blk, n_blk, k_begin, k_end;
-        unit_coords(p, u, m_blk, n_blk, k_begin, k_end);
+      for (UnitWalker w(p, unit0, unit_stride); w.valid(p); w.next(p)) {
+        const int k_begin = w.k_begin, k_end = w.k_end;
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + acc * BN;
@@ -255,13 +292,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CU
     constexpr int kSlots = kDual ? kBufs / 2 : kBufs;
     if (kEpi != kAtomicF32 && elect_one_sync()) {
       uint8_t* epi_smem = smem + L::kEpiOff;
-      int la_u = unit0, la_c = 0;
+      UnitWalker la(p, unit0, unit_stride);
+      int la_c = 0;
       uint32_t la_seq = 0;
       auto la_issue = [&]() {  // aux load of the next not-yet-issued chunk, if any
-        while (la_u < p.num_units) {
-          int m_blk, n_blk, k_begin, k_end;
-          unit_coords(p, la_u, m_blk, n_blk, k_begin, k_end);
-          const int n0 = n_blk * BN + la_c * EPI_COLS;
+        while (la.valid(p)) {
+          const int m_blk = la.m_blk;
+          const int n0 = la.n_blk * BN + la_c * EPI_COLS;
           if (la_c < BN / EPI_COLS && n0 < p.N) {
             const int slot = la_seq % kSlots;
             mbar_arrive_expect_tx(&epi_in[slot], EPI_BUF_BYTES);
@@ -270,17 +307,15 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CU
             ++la_c;
             return;
           }
-          la_u += unit_stride;
+          la.next(p);
           la_c = 0;
         }
       };
       if (kHasAuxIn)
         for (int i = 0; i < kSlots; ++i) la_issue();
       uint32_t seq = 0;
-      for (int u = unit0; u < p.num_units; u += unit_stride) {
-        int m_blk, n_blk, k_begin, k_end;
-        unit_coords(p, u, m_blk, n_blk, k_begin, k_end);
-        const int m0 = (m_blk * kCta + rank) * BM, n0 = n_blk * BN;
+      for (UnitWalker w(p, unit0, unit_stride); w.valid(p); w.next(p)) {
+        const int m0 = (w.m_blk * kCta + rank) * BM, n0 = w.n_blk * BN;
         for (int c = 0; c < BN / EPI_COLS; ++c) {
           const int nc = n0 + c * EPI_COLS;
           if (nc >= p.N) break;
@@ -316,15 +351,20 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CU
     int acc = 0;
     uint32_t acc_phase = 0;
     uint32_t seq = 0;  // running chunk sequence number (staging slot = seq % kSlots)
+#ifdef PLB_GEMM_TRACE
+    int gt_n = 0;
+#endif
 
     const uint32_t lead_tmem_empty0 = (kCta == 2) ? mapa_u32(smem_u32(&tmem_empty[0]), 0) : 0;
-    for (int u = unit0; u < p.num_units; u += unit_stride) {
-      int m_blk, n_blk, k_begin, k_end;
-      unit_coords(p, u, m_blk, n_blk, k_begin, k_end);
-      const int m0 = (m_blk * kCta + rank) * BM, n0 = n_blk * BN;
+    for (UnitWalker w(p, unit0, unit_stride); w.valid(p); w.next(p)) {
+      const int m0 = (w.m_blk * kCta + rank) * BM, n0 = w.n_blk * BN;
+      PLB_GT(1);  // tile start
       if (kEpi != kAtomicF32 && p.bias != nullptr) {
         // stage this tile's bias in shared memory: the per-element __ldg it replaces serialised the epilogue
-        // (the compiler cannot hoist global loads across the generic staging stores)
+        // (the compiler cannot hoist global loads across the generic staging stores).  The epilogue warps no longer meet
+        // at a barrier per chunk, so a fast warp must not overwrite the bias while a slow one still reads the previous
+        // tile's: one barrier before the writes, one after.
+        epi_bar_sync();
 #pragma unroll
         for (int i = 0; i < BN / EPI_THREADS; ++i) {
           const int n = n0 + epi_tid + i * EPI_THREADS;
@@ -334,6 +374,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CU
       }
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
+      PLB_GT(2);  // accumulator ready
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BN;
 
       if (kEpi == kAtomicF32) {
@@ -376,7 +417,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CU
           if constexpr (EPI_GROUPS == 1) tmem_ld_32x32(taddr + c * EPI_COLS + 32, v1);
           if (kHasAuxIn) mbar_wait(&epi_in[slot], (seq / kSlots) & 1);
           else mbar_wait(&slot_free[slot], ((seq / kSlots) & 1) ^ 1);  // the previous use of the slot has been stored
+          PLB_GT(3);  // slot / aux operand ready
           tmem_ld_wait();
+          PLB_GT(4);  // accumulator chunk in registers
           f32x2 dot2 = f2_splat(0.f);  // kRowDot: this thread's part of sum_n C[m,n] * aux_in[m,n] over the chunk
 
 #pragma unroll
@@ -439,7 +482,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CU
             // out-of-range columns of the chunk contribute exact zeros (TMA zero-fills aux_in and B)
             if (m < p.M) atomicAdd(p.rowdot + static_cast<size_t>(nc / EPI_COLS) * p.rowdot_ld + m, lo + hi);
           }
+          PLB_GT(5);  // math done, chunk staged
           fence_proxy_async_smem();
+          PLB_GT(6);  // proxy fence done
           __syncwarp();
           if (lane == 0) mbar_arrive(&chunk_ready[slot]);  // one arrival per epilogue warp: the store warp takes it from here
           ++seq;
@@ -453,6 +498,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CU
         else mbar_arrive(&tmem_empty[acc]);
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      PLB_GT(7);  // tile handed back
     }
   }
 
@@ -633,3 +679,17 @@ extern "C" int plb_gemm_bf16(int op, int epilogue, int M, int N, int K, const vo
   set_error("gemm: op %d does not support epilogue %d", op, epilogue);
   return PLB_ERR_UNSUPPORTED;
 }
+
+#ifdef PLB_GEMM_TRACE
+// trace library only: copies the timeline of the last launches (tag << 56 | clock64) to the host
+extern "C" int plb_debug_gemm_trace(unsigned long long* host_out, int n) {
+  if (n > 8192) n = 8192;
+  cudaError_t e = cudaMemcpyFromSymbol(host_out, plb::g_gemm_trace, sizeof(unsigned long long) * n);
+  return e == cudaSuccess ? 0 : -1;
+}
+extern "C" int plb_debug_gemm_trace_clear() {
+  static unsigned long long zeros[8192];
+  cudaError_t e = cudaMemcpyToSymbol(plb::g_gemm_trace, zeros, sizeof(zeros));
+  return e == cudaSuccess ? 0 : -1;
+}
+#endif
