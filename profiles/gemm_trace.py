@@ -30,15 +30,16 @@ def main():
     S = torch.cuda.current_stream().cuda_stream
     bf = torch.bfloat16
     T = 98304
-    cases = [("fwd qkv (bias)", 0, 0, 2304, 768), ("fwd o (bias+residual)", 0, 1, 768, 768), ("fwd ffn1 (bias+gelu, dual store)", 0, 2, 2048, 768),
-             ("dgrad ffn2 (x gelu')", 1, 3, 2048, 768)]
-    for label, op, epi, N, K in cases:
+    cases = [("fwd qkv (bias)", 0, 0, 2304, 768, True), ("fwd o (bias+residual)", 0, 1, 768, 768, True),
+             ("fwd ffn1 (bias+gelu, dual store)", 0, 2, 2048, 768, True), ("dgrad ffn2 (x gelu')", 1, 3, 2048, 768, False),
+             ("fwd ffn1 WITHOUT bias (how much of the chunk time is the bias LDS?)", 0, 2, 2048, 768, False)]
+    for label, op, epi, N, K, with_bias in cases:
         A = torch.randn(T, K, device=dev).to(bf)
         W = (torch.randn(N, K, device=dev) if op == 0 else torch.randn(K, N, device=dev)).to(bf)
         C = torch.empty(T, N, device=dev, dtype=bf)
         X = torch.randn(T, N, device=dev).to(bf)
         U = torch.empty(T, N, device=dev, dtype=bf)
-        bias = torch.randn(N, device=dev) if op == 0 else None
+        bias = torch.randn(N, device=dev) if with_bias else None
         for _ in range(2):
             lib.plb_debug_gemm_trace_clear()
             call("plb_gemm_bf16", op, epi, T, N, K, ptr(A), K, ptr(W), W.stride(0), ptr(C), N, ptr(bias),
