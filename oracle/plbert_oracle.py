@@ -385,10 +385,11 @@ def calculate_loss(logits: np.ndarray, labels: np.ndarray, input_lengths: Sequen
 # ----------------------------------------------------------------------------------------------
 def loss_and_grads(params: Params, cfg: OracleConfig, masked_phonemes: np.ndarray, phoneme_labels: np.ndarray,
                    input_lengths: Sequence[int], masked_indices: Sequence[Sequence[int]],
-                   token_labels: Optional[np.ndarray] = None, dtype=np.float64):
+                   token_labels: Optional[np.ndarray] = None, dtype=np.float64, token_rows: str = "masked"):
     """One forward+backward of the reference step: R/train.py:381-390 ``process_batch`` followed by
     ``loss.backward()`` (R/train.py:356).  With ``token_labels`` the same loss template is applied to
-    ``token_predictor`` and the two losses are summed (unpinned half, see module docstring)."""
+    ``token_predictor`` and the two losses are summed (unpinned half, see module docstring); ``token_rows="all_valid"``
+    runs the token loss over every valid position of a sample instead of its masked ones (upstream's word loss)."""
     lengths = [int(x) for x in input_lengths]
     attn = attention_mask_from_lengths(lengths)
     assert attn.shape[1] == np.asarray(masked_phonemes).shape[1], "batch must be padded to max(input_lengths)"
@@ -402,7 +403,10 @@ def loss_and_grads(params: Params, cfg: OracleConfig, masked_phonemes: np.ndarra
         heads.append(("token_predictor", token_labels))
     for head, labels in heads:
         logits = head_logits(params, hidden, head, dtype)
-        loss, dlogits = calculate_loss(logits, labels, lengths, masked_indices)
+        rows = masked_indices
+        if head == "token_predictor" and token_rows == "all_valid":
+            rows = [list(range(n)) for n in lengths]
+        loss, dlogits = calculate_loss(logits, labels, lengths, rows)
         W = params[head + ".weight"].astype(dtype, copy=False)
         grads[head + ".weight"] = dlogits.reshape(B * L, -1).T @ hidden.reshape(B * L, H)
         grads[head + ".bias"] = dlogits.reshape(B * L, -1).sum(0)

@@ -48,6 +48,20 @@ def flatten_masked_indices(input_lengths: Sequence[int], masked_indices: Sequenc
     return (flat + base).astype(np.int32), weights.astype(np.float32)
 
 
+def flatten_all_valid(input_lengths: Sequence[int], seq_stride, label_stride: int):
+    """Row set "every valid position" (upstream's word loss: per-sample mean over ALL positions of the sample, then the
+    mean over samples): ``rows[k] = base_b + i`` for i < len_b in the reference's iteration order, the matching index
+    into the padded [B, label_stride] label tensors, and ``weights[k] = 1 / (B * len_b)``.  ``seq_stride`` as in
+    ``flatten_masked_indices`` (padded row length, or the array of first rows in the packed layout)."""
+    lengths = np.asarray(input_lengths, dtype=np.int64)
+    B = lengths.shape[0]
+    sample = np.repeat(np.arange(B, dtype=np.int64), lengths)
+    within = np.arange(int(lengths.sum()), dtype=np.int64) - np.repeat(np.cumsum(lengths) - lengths, lengths)
+    base = sample * int(seq_stride) if np.isscalar(seq_stride) else np.asarray(seq_stride, dtype=np.int64)[sample]
+    weights = (1.0 / (B * lengths[sample].astype(np.float64))).astype(np.float32)
+    return (base + within).astype(np.int32), sample * int(label_stride) + within, weights
+
+
 @dataclass
 class DeviceBatch:
     """One batch resident in HBM: padded [B, L] row layout (row = b * L + j) or, with ``packed``, the sequences back to
@@ -69,6 +83,12 @@ class DeviceBatch:
     packed: bool = False
     n_rows: int = -1           # activation rows: B * L (padded) or sum of the lengths (packed)
     heads: List[str] = field(default_factory=list)   # head of every entry of ``labels`` (set by model.stage_batch)
+    # second row set: EVERY valid position, weight 1 / (B * len_b) — the upstream word-loss convention;
+    # ``all_valid[i]`` says that ``labels[i]`` (and head i) uses it instead of the masked rows
+    rows_all: Optional[torch.Tensor] = None   # int32 [M_all]
+    weights_all: Optional[torch.Tensor] = None
+    M_all: int = 0
+    all_valid: List[bool] = field(default_factory=list)
 
     @property
     def T(self) -> int:
@@ -102,7 +122,8 @@ class BatchStager:
 
     def stage(self, masked_phonemes: torch.Tensor, input_lengths: Sequence[int],
               masked_indices: Optional[Sequence[Sequence[int]]] = None,
-              label_tensors: Sequence[torch.Tensor] = (), packed: bool = False) -> DeviceBatch:
+              label_tensors: Sequence[torch.Tensor] = (), packed: bool = False,
+              all_valid_heads: Sequence[int] = ()) -> DeviceBatch:
         """``packed``: drop the padding rows: the sequences are laid out back to back, so every
         per-token kernel (GEMMs, LayerNorm, attention query tiles) only sees valid tokens.  The reference computes the
         padded rows and never reads them (R/train.py:125), so the loss and every gradient are unchanged."""
@@ -138,13 +159,21 @@ class BatchStager:
             rows, weights = np.zeros(0, np.int32), np.zeros(0, np.float32)
             label_rows = rows
         M = rows.shape[0]
+        all_valid = [i in set(all_valid_heads) for i in range(len(label_tensors))]
+        M_all = 0
+        if any(all_valid):
+            # every valid position of every sample, in the reference's iteration order (sample by sample, position by position);
+            # per-sample mean, then mean over samples: weight 1 / (B * len_b)
+            rows_all, label_rows_all, weights_all = flatten_all_valid(lengths, starts if packed else L, L)
+            M_all = rows_all.shape[0]
         labs = []
-        for lt in label_tensors:
+        for i, lt in enumerate(label_tensors):
             flat = lt.reshape(-1)
-            labs.append(flat[torch.from_numpy(label_rows.astype(np.int64))].to(torch.int32).cpu().numpy() if M else
-                        np.zeros(0, np.int32))
-        # layout (int32 words): ids[T] | pos[T] | seq_start[B] | q_len[B] | kv_len[B] | rows[M] | weights[M] | labels..
-        n = 2 * T + 3 * B + 2 * M + len(labs) * M
+            sel, m_i = (label_rows_all, M_all) if all_valid[i] else (label_rows.astype(np.int64), M)
+            labs.append(flat[torch.from_numpy(sel)].to(torch.int32).cpu().numpy() if m_i else np.zeros(0, np.int32))
+        # layout (int32 words): ids[T] | pos[T] | seq_start[B] | q_len[B] | kv_len[B] | rows[M] | weights[M] | labels.. |
+        # rows_all[M_all] | weights_all[M_all]
+        n = 2 * T + 3 * B + 2 * M + sum(la.shape[0] for la in labs) + 2 * M_all
         slot, pinned, dev = self._buffers(n)
         host = pinned.numpy()
         o = 0
@@ -158,7 +187,10 @@ class BatchStager:
         host[o:o + M] = rows; o += M
         host[o:o + M] = weights.view(np.int32); o += M
         for la in labs:
-            host[o:o + M] = la; o += M
+            host[o:o + la.shape[0]] = la; o += la.shape[0]
+        if M_all:
+            host[o:o + M_all] = rows_all; o += M_all
+            host[o:o + M_all] = weights_all.view(np.int32); o += M_all
         dev[:n].copy_(pinned[:n], non_blocking=True)
         if self._done[slot] is None:
             self._done[slot] = torch.cuda.Event()
@@ -175,7 +207,12 @@ class BatchStager:
                             kv_len=take(B))
         batch.rows = take(M)
         batch.weights = take(M).view(torch.float32)
-        batch.labels = [take(M) for _ in labs]
+        batch.labels = [take(la.shape[0]) for la in labs]
+        if M_all:
+            batch.rows_all = take(M_all)
+            batch.weights_all = take(M_all).view(torch.float32)
+        batch.M_all = M_all
+        batch.all_valid = all_valid
         batch.M = M
         batch.num_valid_tokens = int(lengths.sum())
         batch.h2d_bytes = 4 * n

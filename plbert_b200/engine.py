@@ -272,6 +272,41 @@ class Engine:
         return out[:, :V]
 
     # ------------------------------------------------------------------ loss + backward
+    ROW_CHUNK = 16384   # rows of the all-valid token head handled per pass (logits chunk: 16384 x 64000 bf16 = 2.1 GB)
+
+    def _head_chunk(self, hidden, head: str, rows, weights, labels, m: int, accumulate_loss: bool, backward: bool) -> None:
+        """One chunk of one head on its own row set: gather -> logits -> CE (loss accumulated into loss_buf) and, with
+        ``backward``, bias / weight gradients, dgrad and scatter-add of the rows' gradient into ``d_y``."""
+        H = self.cfg.hidden_size
+        s = _stream()
+        V = self.layout.shapes[head + ".weight"][0]
+        ldv = (V + 7) // 8 * 8
+        logits = self.logits[:m * ldv].view(m, ldv)
+        call("plb_gather_rows", ptr(hidden), H, ptr(rows), m, H, ptr(self.h_rows), H, s)
+        self._gemm(GEMM_FWD, EPI_NONE, m, V, H, self.h_rows, H, self.wp[head + ".weight"], H, logits, ldv,
+                   bias=self.pp[head + ".bias"])
+        call("plb_masked_ce", ptr(logits), ldv, m, V, ptr(labels), ptr(weights), ptr(self.row_loss), ptr(self.loss_buf),
+             1 if accumulate_loss else 0, s)
+        self.launches += 2
+        if backward:
+            call("plb_colsum", ptr(logits), ldv, m, V, self.gp[head + ".bias"], s)
+            self._gemm(GEMM_WGRAD, EPI_NONE, V, H, m, logits, ldv, self.h_rows, H, self.gp[head + ".weight"], H)
+            self._gemm(GEMM_DGRAD, EPI_NONE, m, H, V, logits, ldv, self.wp[head + ".weight"], H, self.dh_rows, H)
+            call("plb_scatter_add_rows", ptr(self.dh_rows), H, ptr(rows), m, H, ptr(self.d_y), H, s)
+            self.launches += 2
+
+    def _all_valid_heads(self, b: DeviceBatch, heads: List[str], hidden, loss_started: bool, backward: bool) -> bool:
+        """Heads whose loss runs over every valid position (``DeviceBatch.all_valid``), ROW_CHUNK rows at a time."""
+        for i, head in enumerate(heads):
+            if not (i < len(b.all_valid) and b.all_valid[i]):
+                continue
+            for lo in range(0, b.M_all, self.ROW_CHUNK):
+                m = min(self.ROW_CHUNK, b.M_all - lo)
+                self._head_chunk(hidden, head, b.rows_all[lo:lo + m], b.weights_all[lo:lo + m], b.labels[i][lo:lo + m], m,
+                                 loss_started, backward)
+                loss_started = True
+        return loss_started
+
     def loss_and_backward(self, b: DeviceBatch, heads: List[str]) -> torch.Tensor:
         """Forward, masked-row CE over ``heads`` (b.labels[i] belongs to heads[i]), full backward into the fp32
         gradient arena.  Returns the loss as a 0-dim fp32 device tensor (sum over heads)."""
@@ -279,65 +314,82 @@ class Engine:
         T, H, I, E = b.T, c.hidden_size, c.intermediate_size, c.embedding_size
         nh, M = c.num_attention_heads, b.M
         s = _stream()
+        uses_all = [i < len(b.all_valid) and b.all_valid[i] for i in range(len(heads))]
+        masked_heads = [(i, h) for i, h in enumerate(heads) if not uses_all[i]]
+        n_all = b.M_all if any(uses_all) else 0
         self.begin_backward()
         hidden = self.forward(b, train=True)
-        if M == 0:
+        self._ensure_row_workspace(max(M, min(n_all, self.ROW_CHUNK)))
+        if (M == 0 or not masked_heads) and n_all == 0:
             # R/train.py:129: no masked rows anywhere -> loss 0 and no gradient reaches any parameter
             self.loss_buf.zero_()
             self.have_grads = False
             return self.loss_buf[0]
         self.grads_clean = False
         self.have_grads = True
-
-        # ---- heads on the masked rows only -------------------------------------------------------
-        call("plb_gather_rows", ptr(hidden), H, ptr(b.rows), M, H, ptr(self.h_rows), H, s)
-        self.launches += 1
-        for i, head in enumerate(heads):
-            V = self.layout.shapes[head + ".weight"][0]
-            ldv = (V + 7) // 8 * 8
-            logits = self.logits[:M * ldv].view(M, ldv)
-            self._gemm(GEMM_FWD, EPI_NONE, M, V, H, self.h_rows, H, self.w(head + ".weight"), H, logits, ldv,
-                       bias=self.p(head + ".bias"))
-            call("plb_masked_ce", ptr(logits), ldv, M, V, ptr(b.labels[i]), ptr(b.weights), ptr(self.row_loss),
-                 ptr(self.loss_buf), 1 if i > 0 else 0, s)
-            call("plb_colsum", ptr(logits), ldv, M, V, ptr(self.g(head + ".bias")), s)
-            self.launches += 3
-            self._gemm(GEMM_WGRAD, EPI_NONE, V, H, M, logits, ldv, self.h_rows, H, self.g(head + ".weight"), H)
-            if i == 0:
-                self._gemm(GEMM_DGRAD, EPI_NONE, M, H, V, logits, ldv, self.w(head + ".weight"), H, self.dh_rows, H)
-            else:
-                self._gemm(GEMM_DGRAD, EPI_RESIDUAL, M, H, V, logits, ldv, self.w(head + ".weight"), H, self.dh_rows, H,
-                           aux_in=self.dh_rows, ld_in=H)
-        self._after_head_backward()
         dy = self.d_y
         dy[:T].zero_()
-        call("plb_scatter_add_rows", ptr(self.dh_rows), H, ptr(b.rows), M, H, ptr(dy), H, s)
-        self.launches += 1
+        loss_started = False
+
+        # ---- heads on the masked rows only: one gather, the heads' row gradients summed, one scatter -------------------
+        if M > 0 and masked_heads:
+            call("plb_gather_rows", ptr(hidden), H, ptr(b.rows), M, H, ptr(self.h_rows), H, s)
+            self.launches += 1
+            for k, (i, head) in enumerate(masked_heads):
+                V = self.layout.shapes[head + ".weight"][0]
+                ldv = (V + 7) // 8 * 8
+                logits = self.logits[:M * ldv].view(M, ldv)
+                self._gemm(GEMM_FWD, EPI_NONE, M, V, H, self.h_rows, H, self.wp[head + ".weight"], H, logits, ldv,
+                           bias=self.pp[head + ".bias"])
+                call("plb_masked_ce", ptr(logits), ldv, M, V, ptr(b.labels[i]), ptr(b.weights), ptr(self.row_loss),
+                     ptr(self.loss_buf), 1 if loss_started else 0, s)
+                loss_started = True
+                call("plb_colsum", ptr(logits), ldv, M, V, self.gp[head + ".bias"], s)
+                self.launches += 3
+                self._gemm(GEMM_WGRAD, EPI_NONE, V, H, M, logits, ldv, self.h_rows, H, self.gp[head + ".weight"], H)
+                if k == 0:
+                    self._gemm(GEMM_DGRAD, EPI_NONE, M, H, V, logits, ldv, self.wp[head + ".weight"], H, self.dh_rows, H)
+                else:
+                    self._gemm(GEMM_DGRAD, EPI_RESIDUAL, M, H, V, logits, ldv, self.wp[head + ".weight"], H, self.dh_rows, H,
+                               aux_in=self.dh_rows, ld_in=H)
+            call("plb_scatter_add_rows", ptr(self.dh_rows), H, ptr(b.rows), M, H, ptr(dy), H, s)
+            self.launches += 1
+        elif masked_heads:
+            self.loss_buf.zero_()   # masked heads contribute 0 (every sample's mask set is empty)
+            loss_started = True
+        # ---- heads over every valid position (upstream word loss), chunked ---------------------------------------------
+        if n_all:
+            self._all_valid_heads(b, heads, hidden, loss_started, backward=True)
+        self._after_head_backward()
         self.encoder_backward(b)
         return self.loss_buf[0]
 
     def loss_only(self, b: DeviceBatch, heads: List[str]) -> torch.Tensor:
-        """Forward + masked-row CE without the backward pass (validation, R/train.py:288-305 under ``no_grad``).
+        """Forward + CE without the backward pass (validation, R/train.py:288-305 under ``no_grad``).
         Uses the two-set activation ping-pong of the inference forward; leaves gradients and optimizer state alone."""
         c = self.cfg
         H, M = c.hidden_size, b.M
         s = _stream()
+        uses_all = [i < len(b.all_valid) and b.all_valid[i] for i in range(len(heads))]
+        masked_heads = [(i, h) for i, h in enumerate(heads) if not uses_all[i]]
+        n_all = b.M_all if any(uses_all) else 0
         hidden = self.forward(b, train=False)
-        if M == 0:
-            self.loss_buf.zero_()
-            return self.loss_buf[0].clone()
-        self._ensure_row_workspace(M)
-        call("plb_gather_rows", ptr(hidden), H, ptr(b.rows), M, H, ptr(self.h_rows), H, s)
-        self.launches += 1
-        for i, head in enumerate(heads):
-            V = self.layout.shapes[head + ".weight"][0]
-            ldv = (V + 7) // 8 * 8
-            logits = self.logits[:M * ldv].view(M, ldv)
-            self._gemm(GEMM_FWD, EPI_NONE, M, V, H, self.h_rows, H, self.w(head + ".weight"), H, logits, ldv,
-                       bias=self.p(head + ".bias"))
-            call("plb_masked_ce", ptr(logits), ldv, M, V, ptr(b.labels[i]), ptr(b.weights), ptr(self.row_loss),
-                 ptr(self.loss_buf), 1 if i > 0 else 0, s)
+        self.loss_buf.zero_()
+        self._ensure_row_workspace(max(M, min(n_all, self.ROW_CHUNK)))
+        if M > 0 and masked_heads:
+            call("plb_gather_rows", ptr(hidden), H, ptr(b.rows), M, H, ptr(self.h_rows), H, s)
             self.launches += 1
+            for i, head in masked_heads:
+                V = self.layout.shapes[head + ".weight"][0]
+                ldv = (V + 7) // 8 * 8
+                logits = self.logits[:M * ldv].view(M, ldv)
+                self._gemm(GEMM_FWD, EPI_NONE, M, V, H, self.h_rows, H, self.wp[head + ".weight"], H, logits, ldv,
+                           bias=self.pp[head + ".bias"])
+                call("plb_masked_ce", ptr(logits), ldv, M, V, ptr(b.labels[i]), ptr(b.weights), ptr(self.row_loss),
+                     ptr(self.loss_buf), 1, s)
+                self.launches += 1
+        if n_all:
+            self._all_valid_heads(b, heads, hidden, True, backward=False)
         return self.loss_buf[0].clone()
 
     def begin_backward(self) -> None:

@@ -274,7 +274,10 @@ class _FusedModel(nn.Module):
             heads.append("token_predictor")
         # drop the padding rows when there are any: same loss and gradients, fewer tokens to process
         packed = self.pack_sequences and min(int(x) for x in lengths) < masked.shape[1]
-        db = (stager or self._stager).stage(masked, lengths, midx, label_tensors, packed=packed)
+        # row set of the token head: the masked rows (default, the phoneme-loss template of R/train.py:107-131) or every
+        # valid position (upstream's word loss)
+        all_valid = [1] if (len(heads) > 1 and getattr(self, "token_rows", "masked") == "all_valid") else []
+        db = (stager or self._stager).stage(masked, lengths, midx, label_tensors, packed=packed, all_valid_heads=all_valid)
         db.heads = heads
         return db
 
@@ -308,6 +311,9 @@ class MultiTaskModel(_FusedModel):
     """R/model.py:5-18."""
 
     _heads = ["phoneme_predictor", "token_predictor"]
+    # rows the token-head loss runs over: "masked" (same rows as the phoneme loss) or "all_valid" (every valid position,
+    # per-sample mean — upstream yl4579/PL-BERT's word loss).  The reference fork has no token loss at all (SURVEY.md §0).
+    token_rows = "masked"
 
     def __init__(self, model, num_phonemes, num_tokens, hidden_size):
         super().__init__()

@@ -39,6 +39,19 @@ def test_flatten_edge_cases():
     assert rows.tolist() == [1, 3, 7] and np.allclose(w, [0.25, 0.25, 0.5])
 
 
+def test_flatten_all_valid_rows_weights_and_order():
+    """Row set of the upstream word loss: every valid position, sample by sample; weights sum to 1 (mean of per-sample means)."""
+    from plbert_b200.batch import flatten_all_valid
+    lengths, L = [5, 3, 1], 7
+    rows, label_rows, w = flatten_all_valid(lengths, L, L)
+    want = [b * L + i for b, n in enumerate(lengths) for i in range(n)]
+    assert rows.tolist() == want and label_rows.tolist() == want and rows.dtype == np.int32
+    assert np.allclose(w, [1 / (3 * n) for n in lengths for _ in range(n)]) and abs(w.sum() - 1.0) < 1e-6
+    starts = np.array([0, 5, 8])                      # packed layout: sequences back to back
+    prow, plab, pw = flatten_all_valid(lengths, starts, L)
+    assert prow.tolist() == list(range(9)) and plab.tolist() == want and np.array_equal(pw, w)
+
+
 def test_synthetic_batch_contract_and_statistics():
     tok, lab, msk, lens, midx = B.synthetic_collate_batch(64, 512, seed=5, with_token_ids=True)
     assert lab.dtype == torch.int64 and lab.shape == msk.shape == tok.shape == (64, 512)

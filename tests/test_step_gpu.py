@@ -183,6 +183,36 @@ def test_training_trajectory_tracks_oracle(dev):
         assert cosine(p.detach().cpu().double().numpy(), params[n]) > 0.999, n
 
 
+@pytest.mark.parametrize("packed", [False, True])
+def test_token_head_over_all_valid_positions(dev, packed):
+    """``MultiTaskModel.token_rows = "all_valid"``: the token-head loss runs over every valid position (upstream's word
+    loss) while the phoneme loss keeps the masked rows; the all-valid head is processed in row chunks."""
+    from plbert_b200.batch import synthetic_collate_batch
+    cfgv = [188, 32, 128, 2, 256, 3, 128, 211]
+    model = build_model(cfgv, True, dev, seed=17)
+    model.token_rows = "all_valid"
+    model.pack_sequences = packed
+    batch = synthetic_collate_batch(5, 128, seed=61, variable_length=True, min_length=9, with_token_ids=True, num_tokens=211,
+                                    word_pred_prob=0.25)
+    token_ids, labels, masked, lengths, midx = batch
+    midx[2] = []
+    params = {k: v.detach().cpu().double().numpy() for k, v in model.state_dict().items()}
+    total, losses, grads, _ = O.loss_and_grads(params, oracle_cfg(cfgv), masked.numpy(), labels.numpy(), lengths, midx,
+                                               token_labels=token_ids.numpy(), token_rows="all_valid")
+    model._ensure_engine(dev).ROW_CHUNK = 100           # several chunks, the last one ragged
+    loss = model.loss_and_backward(batch)
+    assert model.last_batch.M_all == sum(lengths) and model.last_batch.packed == packed
+    assert abs(loss.item() - total) <= 2e-2 * abs(total), (loss.item(), total, losses)
+    check_grads(model, grads, masked.shape[1])
+    assert abs(model.loss(batch).item() - total) <= 2e-2 * abs(total)          # validation path, same row sets
+    # all masks empty: the phoneme loss is 0, the token loss still runs
+    empty = (token_ids, labels, masked, lengths, [[] for _ in lengths])
+    t2, l2, _, _ = O.loss_and_grads(params, oracle_cfg(cfgv), masked.numpy(), labels.numpy(), lengths, empty[4],
+                                    token_labels=token_ids.numpy(), token_rows="all_valid")
+    got = model.loss_and_backward(empty).item()
+    assert abs(got - t2) <= 2e-2 * abs(t2) and abs(t2 - l2["token_predictor"]) < 1e-12
+
+
 def test_packed_layout_equals_padded_layout(dev):
     """Variable-length batches run without their padding rows.  The reference computes the padded
     rows and never reads them, so loss and gradients must not change; only the fp32 summation order of the weight
