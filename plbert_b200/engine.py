@@ -17,6 +17,7 @@ HBM layout
 """
 from __future__ import annotations
 
+import os
 from dataclasses import dataclass
 from typing import Dict, List, Optional, Tuple
 
@@ -33,6 +34,27 @@ ALIGN = 64  # elements: every tensor (group) starts on a 256-byte (fp32) / 128-b
 
 def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
+
+
+# NVTX ranges around the phases of a step (forward / heads / encoder backward / AdamW) when PLBERT_B200_NVTX=1, so that
+# `ncu --nvtx --nvtx-include "backward/"` or a timeline tool can select them; a no-op otherwise.
+_NVTX = os.environ.get("PLBERT_B200_NVTX", "0") not in ("", "0")
+
+
+class _Range:
+    __slots__ = ("name",)
+
+    def __init__(self, name: str):
+        self.name = name
+
+    def __enter__(self):
+        if _NVTX:
+            torch.cuda.nvtx.range_push(self.name)
+
+    def __exit__(self, *exc):
+        if _NVTX:
+            torch.cuda.nvtx.range_pop()
+        return False
 
 
 @dataclass
@@ -318,7 +340,8 @@ class Engine:
         masked_heads = [(i, h) for i, h in enumerate(heads) if not uses_all[i]]
         n_all = b.M_all if any(uses_all) else 0
         self.begin_backward()
-        hidden = self.forward(b, train=True)
+        with _Range("forward"):
+            hidden = self.forward(b, train=True)
         self._ensure_row_workspace(max(M, min(n_all, self.ROW_CHUNK)))
         if (M == 0 or not masked_heads) and n_all == 0:
             # R/train.py:129: no masked rows anywhere -> loss 0 and no gradient reaches any parameter
@@ -361,7 +384,8 @@ class Engine:
         if n_all:
             self._all_valid_heads(b, heads, hidden, loss_started, backward=True)
         self._after_head_backward()
-        self.encoder_backward(b)
+        with _Range("backward"):
+            self.encoder_backward(b)
         return self.loss_buf[0]
 
     def loss_only(self, b: DeviceBatch, heads: List[str]) -> torch.Tensor:
@@ -472,6 +496,8 @@ class Engine:
             return  # reference: parameters whose .grad is None are skipped entirely (no decay either)
         self.opt_step += 1
         n = self.layout.trainable_end
+        if _NVTX:
+            torch.cuda.nvtx.mark("adamw")
         call("plb_adamw_step", ptr(self.params), ptr(self.grads), ptr(self.exp_avg), ptr(self.exp_avg_sq), ptr(self.shadow),
              n, self.opt_step, lr, betas[0], betas[1], eps, weight_decay, grad_scale, 1, _stream())
         self.launches += 1

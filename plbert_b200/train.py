@@ -361,9 +361,19 @@ def train(args: Optional[Dict[str, object]] = None) -> Tuple[int, int]:
     tp = config["training_params"]
     print(f"Resuming training from '{log_dir}' with existing config." if resuming else f"Starting new training run in '{log_dir}'.")
     logger = MetricsLogger(log_dir, config, enabled=rank == 0, use_wandb=not args.get("no_wandb", False))
-    use_tok = bool(args.get("use_token_ids", False))
-    train_dl, val_dl = setup_dataset_and_dataloader(config, device, use_tok, int(args.get("num_tokens") or 64000))
-    model, optimizer, current_step = initialize_model(config, log_dir, resuming, device, use_tok, args.get("num_tokens"))
+    # optional block of the YAML that only this implementation reads (the reference's keys stay untouched):
+    #   b200_params: {use_token_ids, num_tokens, token_rows: masked|all_valid, pack_sequences, checkpoint_extension}
+    bp = dict(config.get("b200_params") or {})
+    use_tok = bool(args.get("use_token_ids") or bp.get("use_token_ids", False))
+    num_tokens = args.get("num_tokens") or bp.get("num_tokens")
+    train_dl, val_dl = setup_dataset_and_dataloader(config, device, use_tok, int(num_tokens or 64000))
+    model, optimizer, current_step = initialize_model(config, log_dir, resuming, device, use_tok, num_tokens)
+    if "pack_sequences" in bp:
+        model.pack_sequences = bool(bp["pack_sequences"])
+    if use_tok and "token_rows" in bp:
+        if bp["token_rows"] not in ("masked", "all_valid"):
+            raise ValueError("b200_params.token_rows must be 'masked' or 'all_valid'")
+        model.token_rows = bp["token_rows"]
     if world > 1:
         from .ddp import GradientSynchronizer
         sync = GradientSynchronizer(model._engine)   # broadcasts rank 0's weights, hooks the bucketed all-reduce
@@ -373,7 +383,7 @@ def train(args: Optional[Dict[str, object]] = None) -> Tuple[int, int]:
     t0 = time.time()
     step, epoch = train_loop(model, optimizer, train_dl, val_dl, current_step, int(tp["num_steps"]), int(tp["save_interval"]),
                              int(tp["log_interval"]), log_dir, logger, rank=rank, world=world,
-                             checkpoint_extension=str(args.get("checkpoint_extension", "t7")))
+                             checkpoint_extension=str(bp.get("checkpoint_extension") or args.get("checkpoint_extension", "t7")))
     torch.cuda.synchronize()
     if rank == 0:
         print(f"Training completed at step {step}, epoch {epoch} ({time.time() - t0:.1f} s)")

@@ -14,11 +14,13 @@ from plbert_b200.batch import BatchFeeder, synthetic_collate_batch
 TINY = dict(hidden_size=128, num_attention_heads=2, intermediate_size=256, max_position_embeddings=64, num_hidden_layers=2)
 
 
-def write_config(path, out_dir, **training):
-    cfg = {"training_params": dict(output_dir=str(out_dir), mixed_precision="fp16", batch_size=4, save_interval=3, log_interval=2,
-                                   num_steps=6, learning_rate=7e-5, training_dataset="synthetic", split="x", **training),
+def write_config(path, out_dir, b200=None, **training):
+    cfg = {"training_params": {**dict(output_dir=str(out_dir), mixed_precision="fp16", batch_size=4, save_interval=3, log_interval=2,
+                                      num_steps=6, learning_rate=7e-5, training_dataset="synthetic", split="x"), **training},
            "dataset_params": dict(word_separator=87, max_seq_length=64, word_pred_prob=0.3, phoneme_mask_prob=0.8, replace_prob=0.1),
            "model_params": dict(pretrained_model="", dropout=0.1, **TINY)}
+    if b200 is not None:
+        cfg["b200_params"] = b200
     with open(path, "w") as f:
         yaml.dump(cfg, f)
     return cfg

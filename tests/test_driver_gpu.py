@@ -46,6 +46,25 @@ def test_train_driver_runs_saves_validates_and_resumes(tmp_path):
     assert step2 == 7
 
 
+def test_train_driver_b200_params_block(tmp_path):
+    """The optional ``b200_params`` block of the YAML: two-head training with the token loss over every valid position,
+    reference-style ``.pth`` checkpoints."""
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from plbert_b200 import train as T
+    cfg_path = tmp_path / "config.yml"
+    write_config(cfg_path, tmp_path / "runs", synthetic_batches_per_epoch=4, num_steps=2, save_interval=2,
+                 b200=dict(use_token_ids=True, num_tokens=300, token_rows="all_valid", checkpoint_extension="pth"))
+    step, _ = T.train(T.parse_args(["--config_path", str(cfg_path), "--run_name", "mt", "--no_wandb"]))
+    assert step == 2
+    run = tmp_path / "runs" / "mt"
+    ck = torch.load(run / "step_2.pth", map_location="cpu", weights_only=False)
+    assert ck["net"]["module.token_predictor.weight"].shape == (300, 128)
+    rows = [json.loads(x) for x in open(run / "metrics.jsonl")]
+    losses = [r["phoneme_loss"] for r in rows if "phoneme_loss" in r]
+    assert len(losses) == 2 and all(8 < x < 14 for x in losses)      # ln(188) + ln(300) = 10.9 at initialisation
+
+
 def ck_cfg(path):
     import yaml
     with open(path) as f:
