@@ -294,10 +294,15 @@ class MetricsLogger:
 
 def train_loop(model, optimizer, train_dataloader, val_dataloader, current_step: int, num_steps: int, save_interval: int,
                log_interval: int, log_dir: str, logger: MetricsLogger, max_epochs: int = 10, rank: int = 0, world: int = 1,
-               checkpoint_extension: str = "t7") -> Tuple[int, int]:
+               checkpoint_extension: str = "t7", log_lag: int = 0) -> Tuple[int, int]:
     """R/train.py:338-379 with the fused step: validation first, then per batch ``BatchFeeder.step`` (forward + loss +
     backward on the batch staged during the previous step) and ``optimizer.step``; checkpoint + validation every
-    ``save_interval`` steps; stops at ``num_steps`` or after ``max_epochs`` passes."""
+    ``save_interval`` steps; stops at ``num_steps`` or after ``max_epochs`` passes.
+
+    ``log_lag`` = 0 reads every step's loss back right away like the reference (``loss.item()``, R/train.py:395 — one
+    device->host sync per step); ``log_lag`` = k logs a step's loss k steps later (the value is kept in a device scalar
+    meanwhile), so the host never waits for the step it has just enqueued.  Every loss is still logged, in order; the
+    queue is drained before checkpoints, validation and the end of training."""
     from .batch import BatchFeeder
     main = rank == 0
     say = print if main else (lambda *a, **k: None)
@@ -309,6 +314,18 @@ def train_loop(model, optimizer, train_dataloader, val_dataloader, current_step:
         say(f"Validation at step {current_step}: Phoneme Loss: {val:.4f}")
         return val
 
+    pending: deque = deque()   # (epoch, device loss) of steps whose loss has not been read back yet
+
+    def flush(keep: int) -> None:
+        while len(pending) > keep:
+            epoch, t = pending.popleft()
+            value = float(t.item())
+            losses.append(value)
+            row = {"phoneme_loss": value, "epoch": epoch}
+            if len(losses) == log_interval:
+                row["phoneme_loss_avg"] = sum(losses) / len(losses)
+            logger.log(row)
+
     current_epoch = 0
     run_validation(current_epoch)
     while current_epoch < max_epochs:
@@ -319,20 +336,20 @@ def train_loop(model, optimizer, train_dataloader, val_dataloader, current_step:
             loss = feed.step()          # process_batch + backward (R/train.py:351-356); next batch staged underneath
             optimizer.step()
             current_step += 1
-            value = float(loss.item())
-            losses.append(value)
-            row = {"phoneme_loss": value, "epoch": current_epoch}
-            if len(losses) == log_interval:
-                row["phoneme_loss_avg"] = sum(losses) / len(losses)
-            logger.log(row)
+            # the engine's loss scalar is overwritten by the next step: a lagged read needs its own copy
+            pending.append((current_epoch, loss.clone() if log_lag > 0 else loss))
+            flush(log_lag)
             if current_step % save_interval == 0:
+                flush(0)
                 if main:
                     say("Saving..")
                     path = save_checkpoint(model, optimizer, current_step, log_dir, current_epoch, extension=checkpoint_extension)
                     say(f"Checkpoint saved at: {path}")
                 run_validation(current_epoch)
             if current_step >= num_steps:
+                flush(0)
                 return current_step, current_epoch
+        flush(0)
     return current_step, current_epoch
 
 
@@ -362,7 +379,7 @@ def train(args: Optional[Dict[str, object]] = None) -> Tuple[int, int]:
     print(f"Resuming training from '{log_dir}' with existing config." if resuming else f"Starting new training run in '{log_dir}'.")
     logger = MetricsLogger(log_dir, config, enabled=rank == 0, use_wandb=not args.get("no_wandb", False))
     # optional block of the YAML that only this implementation reads (the reference's keys stay untouched):
-    #   b200_params: {use_token_ids, num_tokens, token_rows: masked|all_valid, pack_sequences, checkpoint_extension}
+    #   b200_params: {use_token_ids, num_tokens, token_rows: masked|all_valid, pack_sequences, checkpoint_extension, log_lag}
     bp = dict(config.get("b200_params") or {})
     use_tok = bool(args.get("use_token_ids") or bp.get("use_token_ids", False))
     num_tokens = args.get("num_tokens") or bp.get("num_tokens")
@@ -383,7 +400,8 @@ def train(args: Optional[Dict[str, object]] = None) -> Tuple[int, int]:
     t0 = time.time()
     step, epoch = train_loop(model, optimizer, train_dl, val_dl, current_step, int(tp["num_steps"]), int(tp["save_interval"]),
                              int(tp["log_interval"]), log_dir, logger, rank=rank, world=world,
-                             checkpoint_extension=str(bp.get("checkpoint_extension") or args.get("checkpoint_extension", "t7")))
+                             checkpoint_extension=str(bp.get("checkpoint_extension") or args.get("checkpoint_extension", "t7")),
+                             log_lag=int(bp.get("log_lag", 0)))
     torch.cuda.synchronize()
     if rank == 0:
         print(f"Training completed at step {step}, epoch {epoch} ({time.time() - t0:.1f} s)")

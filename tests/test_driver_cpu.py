@@ -116,6 +116,66 @@ def test_batch_feeder_stages_one_batch_ahead():
         feed.step()
 
 
+class _FakeModel(torch.nn.Module):
+    """CPU stand-in with the three calls train_loop makes; the loss is the number of the batch it was computed on."""
+
+    def __init__(self):
+        super().__init__()
+        self.w = torch.nn.Parameter(torch.zeros(1))
+        self.loss_buf = torch.zeros(1)
+        self.calls = []
+
+    def new_stager(self):
+        return None
+
+    def stage_batch(self, b, stager=None):
+        return b
+
+    def loss_and_backward(self, b):
+        self.loss_buf[0] = float(b)          # like the engine: ONE scalar buffer, overwritten by every step
+        self.calls.append(("step", b))
+        return self.loss_buf[0]
+
+    def loss(self, b):
+        self.calls.append(("val", b))
+        return torch.tensor(100.0 + b)
+
+
+class _FakeOpt:
+    def __init__(self):
+        self.steps = 0
+
+    def step(self):
+        self.steps += 1
+
+    def state_dict(self):
+        return {"state": {}, "param_groups": []}
+
+
+@pytest.mark.parametrize("log_lag", [0, 1, 3])
+def test_train_loop_cadence_and_lagged_logging(tmp_path, log_lag):
+    """R/train.py:338-379: validation first, checkpoint + validation every save_interval steps, stop at num_steps; with a
+    logging lag every step's loss is still logged, in order, with ITS value (the loss scalar is reused by the engine)."""
+    model, opt = _FakeModel(), _FakeOpt()
+    logger = T.MetricsLogger(str(tmp_path), {}, enabled=True, use_wandb=False)
+    train_dl, val_dl = [1, 2, 3, 4], [7, 8]                       # 4 batches per epoch
+    step, epoch = T.train_loop(model, opt, train_dl, val_dl, 0, num_steps=10, save_interval=3, log_interval=2,
+                               log_dir=str(tmp_path), logger=logger, log_lag=log_lag)
+    logger.close()
+    assert (step, epoch) == (10, 3) and opt.steps == 10
+    rows = [json.loads(x) for x in open(tmp_path / "metrics.jsonl")]
+    train_rows = [r for r in rows if "phoneme_loss" in r]
+    assert [r["phoneme_loss"] for r in train_rows] == [1, 2, 3, 4, 1, 2, 3, 4, 1, 2]
+    assert [r["epoch"] for r in train_rows] == [1, 1, 1, 1, 2, 2, 2, 2, 3, 3]
+    assert train_rows[1]["phoneme_loss_avg"] == 1.5 and "phoneme_loss_avg" not in train_rows[0]
+    val_rows = [r for r in rows if "val_phoneme_loss" in r]
+    assert [r["step"] for r in val_rows] == [0, 3, 6, 9] and all(r["val_phoneme_loss"] == 107.5 for r in val_rows)
+    assert sorted(f for f in os.listdir(tmp_path) if f.startswith("step_")) == ["step_3.t7", "step_6.t7", "step_9.t7"]
+    # all losses up to a checkpoint are in the log before the checkpoint's validation row
+    idx_val3 = rows.index(val_rows[1])
+    assert sum(1 for r in rows[:idx_val3] if "phoneme_loss" in r) == 3
+
+
 # ------------------------------------------------------------------------------------------------ converter (f3)
 def reference_style_checkpoint(path, two_heads=True, prefix="module.", upstream_names=False, vocab=188, vt=321):
     """A checkpoint as R/train.py:416-424 writes it, from the stock classes the reference wraps (R/model.py:5-30)."""
