@@ -179,6 +179,8 @@ class Engine:
         self.pp = {n: self.params.data_ptr() + 4 * o for n, o in lay.offsets.items()}   # fp32 master
         self.gp = {n: self.grads.data_ptr() + 4 * o for n, o in lay.offsets.items()}    # fp32 gradient
         self.wp = {n: self.shadow.data_ptr() + 2 * o for n, o in lay.offsets.items()}   # bf16 shadow
+        self.name_of_ptr = {v: k for k, v in self.pp.items()}                           # fp32 master address -> name
+        self.grad_views = {n: self.view(self.grads, n) for n in lay.offsets}            # what p.grad points at
 
     # ------------------------------------------------------------------ parameter views
     def view(self, arena: torch.Tensor, name: str) -> torch.Tensor:

@@ -145,6 +145,7 @@ class _FusedModel(nn.Module):
         self._versions: List[int] = []
         self._graphs = {}
         self._adopted = None   # [(parameter, arena data_ptr)] once every parameter is a view into the engine's arena
+        self._named = None     # cached (name, parameter) list for the per-step gradient publication
 
     # ------------------------------------------------------------------ engine / arena management
     def _arena_params(self):
@@ -194,6 +195,7 @@ class _FusedModel(nn.Module):
                 stale = True
             adopted.append((p, view.data_ptr()))
         self._adopted = adopted
+        self._named = named
         versions = [p._version for _, p in named]
         if stale or versions != self._versions:
             eng.shadow_valid = False  # someone wrote the fp32 weights through torch (load_state_dict, init, ...)
@@ -202,10 +204,12 @@ class _FusedModel(nn.Module):
 
     def _publish_grads(self) -> None:
         eng = self._engine
-        for name, p in self._arena_params():
+        if self._named is None:
+            self._named = self._arena_params()
+        for name, p in self._named:
             if name in eng.layout.frozen or not p.requires_grad:
                 continue
-            p.grad = eng.g(name) if eng.have_grads else None
+            p.grad = eng.grad_views[name] if eng.have_grads else None
 
     # ------------------------------------------------------------------ reference-compatible forward
     def _stage_inputs(self, phonemes: torch.Tensor, attention_mask: Optional[torch.Tensor]) -> DeviceBatch:

@@ -47,7 +47,7 @@ class FusedAdamW(torch.optim.Optimizer):
                 loss = closure()
         eng = self._engine()
         group = self.param_groups[0]
-        names = {v: k for k, v in ((n, eng.p(n).data_ptr()) for n in eng.layout.offsets)}
+        names = eng.name_of_ptr
         any_grad = False
         for p in group["params"]:
             if p.grad is None:
@@ -56,8 +56,8 @@ class FusedAdamW(torch.optim.Optimizer):
             if name is None or name in eng.layout.frozen:
                 raise _abi.PlbError("FusedAdamW: gradient on a parameter outside the trainable arena")
             any_grad = True
-            gview = eng.g(name)
-            if p.grad.data_ptr() != gview.data_ptr():
+            gview = eng.grad_views[name]
+            if p.grad is not gview and p.grad.data_ptr() != gview.data_ptr():
                 gview.copy_(p.grad)  # autograd (or the user, e.g. clipping) produced a separate tensor
                 eng.grads_clean = False
             st = self.state[p]
