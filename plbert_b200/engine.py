@@ -334,9 +334,7 @@ class Engine:
     def loss_and_backward(self, b: DeviceBatch, heads: List[str]) -> torch.Tensor:
         """Forward, masked-row CE over ``heads`` (b.labels[i] belongs to heads[i]), full backward into the fp32
         gradient arena.  Returns the loss as a 0-dim fp32 device tensor (sum over heads)."""
-        c = self.cfg
-        T, H, I, E = b.T, c.hidden_size, c.intermediate_size, c.embedding_size
-        nh, M = c.num_attention_heads, b.M
+        T, H, M = b.T, self.cfg.hidden_size, b.M
         s = _stream()
         uses_all = [i < len(b.all_valid) and b.all_valid[i] for i in range(len(heads))]
         masked_heads = [(i, h) for i, h in enumerate(heads) if not uses_all[i]]

@@ -227,7 +227,7 @@ class _FusedModel(nn.Module):
         return self._stager.stage(phonemes, lengths)
 
     def _forward_logits(self, phonemes, attention_mask):
-        eng = self._ensure_engine(phonemes.device)
+        self._ensure_engine(phonemes.device)
         batch = self._stage_inputs(phonemes, attention_mask)
         params = [p for _, p in self._arena_params()]
         need_grad = torch.is_grad_enabled() and any(p.requires_grad for p in params)
