@@ -130,16 +130,8 @@ int plb_ln_bwd(const void* dy, const void* z, const float* stats, const float* w
  * -inf key mask.  No [B,H,L,L] tensor exists.  ctx: bf16 [T, heads*64].  lse2: fp32 [heads, total_rows], the
  * row log-sum-exp in the log2 domain (saved for backward).  Backward writes dqkv (bf16, same layout as qkv;
  * rows of masked keys get exact zeros) and uses `delta` (fp32 [heads, total_rows]) as scratch. head_dim must be 64. */
-int plb_attn_fwd(const void* qkv, int ld_qkv, const int32_t* seq_start, const int32_t* q_len,
-                 const int32_t* kv_len, int B, int heads, int head_dim, int max_q_len, int total_rows,
-                 void* ctx, int ld_ctx, float* lse2, plb_stream_t stream);
-int plb_attn_bwd(const void* qkv, int ld_qkv, const int32_t* seq_start, const int32_t* q_len,
-                 const int32_t* kv_len, int B, int heads, int head_dim, int max_q_len, int total_rows,
-                 const void* ctx, const void* dctx, int ld_ctx, const float* lse2, float* delta,
-                 void* dqkv, int ld_dqkv, plb_stream_t stream);
-
-/* tcgen05 / TMEM implementation of the same contract (sequences up to 512 rows): K and V of a (sequence, head)
- * are TMA-loaded once into shared memory, S and O accumulate in tensor memory. */
+/* tcgen05 / TMEM implementation (sequences up to 512 rows): K and V of a (sequence, head) are TMA-loaded once into
+ * shared memory, S and O accumulate in tensor memory. */
 int plb_attn_fwd_tc(const void* qkv, int ld_qkv, const int32_t* seq_start, const int32_t* q_len,
                     const int32_t* kv_len, int B, int heads, int head_dim, int max_q_len, int total_rows,
                     void* ctx, int ld_ctx, float* lse2, plb_stream_t stream);

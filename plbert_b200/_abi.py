@@ -37,9 +37,7 @@ SIGNATURES = {
     "plb_embed_ln_bwd": [P, P, P, c_int, c_int, c_int, P, P, P, P, P, c_int, P, P, P, P, P, P],
     "plb_ln_fwd": [P, c_int, c_int, P, P, c_float, P, P, P],
     "plb_ln_bwd": [P, P, P, P, c_int, c_int, P, P, P, P, P],
-    "plb_attn_fwd": [P, c_int, P, P, P, c_int, c_int, c_int, c_int, c_int, P, c_int, P, P],
     "plb_attn_fwd_tc": [P, c_int, P, P, P, c_int, c_int, c_int, c_int, c_int, P, c_int, P, P],
-    "plb_attn_bwd": [P, c_int, P, P, P, c_int, c_int, c_int, c_int, c_int, P, P, c_int, P, P, P, c_int, P],
     "plb_attn_bwd_tc": [P, c_int, P, P, P, c_int, c_int, c_int, c_int, c_int, P, P, c_int, P, P, P, c_int, P, P],
     "plb_gather_rows": [P, c_int, P, c_int, c_int, P, c_int, P],
     "plb_scatter_add_rows": [P, c_int, P, c_int, c_int, P, c_int, P],

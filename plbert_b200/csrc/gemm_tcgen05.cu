@@ -551,16 +551,8 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, 
 using namespace plb;
 
 // CTA pairs (cta_group::2) halve the B-operand shared-memory traffic per SM; a single CTA is kept for problems with
-// fewer than two 128-row tiles.  PLB_GEMM_CTA=1 forces the single-CTA kernel (bring-up / A-B measurements only).
-static int pick_ctas(int M) {
-  static int forced = -1;
-  if (forced < 0) {
-    const char* e = getenv("PLB_GEMM_CTA");
-    forced = e ? atoi(e) : 0;
-  }
-  if (forced == 1 || forced == 2) return forced;
-  return M > BM ? 2 : 1;
-}
+// fewer than two 128-row tiles.
+static int pick_ctas(int M) { return M > BM ? 2 : 1; }
 
 extern "C" int plb_gemm_bf16(int op, int epilogue, int M, int N, int K, const void* A, int lda, const void* B,
                              int ldb, void* C, int ldc, const float* bias, const void* aux_in, int ld_aux_in,

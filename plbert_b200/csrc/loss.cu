@@ -70,15 +70,21 @@ __global__ void masked_ce_kernel(__nv_bfloat16* __restrict__ logits, int ld, int
   se = group_reduce(se, false);
   if (!active) return;
   const int y = labels[m];
-  const float w = weights[m];
+  const bool y_ok = y >= 0 && y < V;
+  // a label outside [0, V) contributes neither loss nor gradient (the whole row is ignored)
+  const float w = y_ok ? weights[m] : 0.f;
   const float lse = __logf(se) + mx;
-  if (tid == 0) row_loss[m] = (y >= 0 && y < V) ? w * (lse - __bfloat162float(z[y])) : 0.f;
+  if (!y_ok && tid == 0) row_loss[m] = 0.f;
   const float inv = w / se;
   for (int j = tid; j < ld; j += kThreads) {
     float g = 0.f;
     if (j < V) {
-      g = __expf(__bfloat162float(z[j]) - mx) * inv;
-      if (j == y) g -= w;
+      const float zj = __bfloat162float(z[j]);
+      g = __expf(zj - mx) * inv;
+      if (j == y) {  // the thread that owns the label column reads z[y] before it overwrites it: no cross-thread ordering
+        row_loss[m] = w * (lse - zj);
+        g -= w;
+      }
     }
     z[j] = __float2bfloat16(g);  // padding columns [V, ld) are zeroed so the dgrad/wgrad GEMMs may read them
   }
@@ -124,8 +130,9 @@ masked_ce_wide_kernel(__nv_bfloat16* __restrict__ logits, int ld, int M, int V, 
   for (int j = nvec * 8 + tid; j < V; j += 256) se += ex2_fast(fmaf(__bfloat162float(z[j]), 1.4426950408889634f, -mx2));
   se = block_reduce(se, false);
   const int y = labels[m];
-  const float wgt = weights[m];
-  if (tid == 0) row_loss[m] = (y >= 0 && y < V) ? wgt * (__logf(se) + mx - __bfloat162float(z[y])) : 0.f;
+  const bool y_ok = y >= 0 && y < V;
+  const float wgt = y_ok ? weights[m] : 0.f;  // a label outside [0, V): no loss and no gradient for the row
+  if (tid == 0) row_loss[m] = y_ok ? wgt * (__logf(se) + mx - __bfloat162float(z[y])) : 0.f;
   __syncthreads();  // z[y] has been read before anyone overwrites it
   const float inv = wgt / se;
   for (int c = tid; c < nvec; c += 256) {

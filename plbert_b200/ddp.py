@@ -55,14 +55,16 @@ class GradientSynchronizer:
     def __init__(self, engine, group=None):
         self.engine, self.group = engine, group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
-        self.stream = torch.cuda.Stream(device=engine.device) if self.world > 1 else None
+        # the collectives run on a side stream (CPU tensors — the gloo tests — are reduced in line)
+        self.on_gpu = engine.device.type == "cuda"
+        self.stream = torch.cuda.Stream(device=engine.device) if (self.world > 1 and self.on_gpu) else None
         lay = engine.layout
-        self.head_bounds = bucket_bounds(lay.head_end, lay.head_end)  # filled below
         self.head_bounds = [(0, lay.head_end)] if lay.head_end > 0 else []
         self.tail_bounds = [(lay.head_end, lay.trainable_end)]
         engine._after_head_backward = self._reduce_heads
         engine._after_encoder_backward = self._reduce_tail
         if self.world > 1:
+            engine.always_reduce = True   # a rank whose shard has no masked rows still joins the collectives
             broadcast_params(engine.params, 0, group)
             engine.shadow_valid = False
 
@@ -73,6 +75,9 @@ class GradientSynchronizer:
     def _launch(self, bounds) -> None:
         if self.world == 1 or not bounds:
             return
+        if not self.on_gpu:
+            all_reduce_buckets(self.engine.grads, bounds, self.group)
+            return
         self.stream.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(self.stream):
             all_reduce_buckets(self.engine.grads, bounds, self.group)
@@ -82,5 +87,5 @@ class GradientSynchronizer:
 
     def _reduce_tail(self) -> None:
         self._launch(self.tail_bounds)
-        if self.world > 1:
+        if self.world > 1 and self.on_gpu:
             torch.cuda.current_stream().wait_stream(self.stream)  # AdamW (next on the main stream) sees reduced grads

@@ -173,6 +173,7 @@ class Engine:
         self._cap_M = 0
         self.loss_buf = torch.zeros(1, dtype=torch.float32, device=device)
         self.comm_stream: Optional[torch.cuda.Stream] = None
+        self.always_reduce = False    # set by ddp.GradientSynchronizer (world > 1): every step ends in the collectives
         # raw addresses of every tensor inside the (never reallocated) arenas: building torch views costs 3-5 us each and
         # the step makes ~700 of them — host time that is exposed whenever the caller synchronises every step
         lay = self.layout
@@ -344,9 +345,7 @@ class Engine:
             hidden = self.forward(b, train=True)
         self._ensure_row_workspace(max(M, min(n_all, self.ROW_CHUNK)))
         if (M == 0 or not masked_heads) and n_all == 0:
-            # R/train.py:129: no masked rows anywhere -> loss 0 and no gradient reaches any parameter
-            self.loss_buf.zero_()
-            self.have_grads = False
+            self._empty_step()
             return self.loss_buf[0]
         self.grads_clean = False
         self.have_grads = True
@@ -387,6 +386,20 @@ class Engine:
         with _Range("backward"):
             self.encoder_backward(b)
         return self.loss_buf[0]
+
+    def _empty_step(self) -> None:
+        """R/train.py:129: no masked rows anywhere -> loss 0 and no gradient reaches any parameter (a single process then
+        skips the optimizer step, like torch does for ``grad is None``).  Under data parallelism the peers are (or will be)
+        inside the bucket all-reduces and will run AdamW on the averaged gradient, so this rank joins both collectives
+        with its all-zero contribution and steps like everybody else (DDP semantics, R/train.py:160,218-221) — returning
+        early would hang the other ranks and let the replicas drift apart."""
+        self.loss_buf.zero_()
+        if not self.always_reduce:
+            self.have_grads = False
+            return
+        self.have_grads = True
+        self._after_head_backward()
+        self._after_encoder_backward()
 
     def loss_only(self, b: DeviceBatch, heads: List[str]) -> torch.Tensor:
         """Forward + CE without the backward pass (validation, R/train.py:288-305 under ``no_grad``).

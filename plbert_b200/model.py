@@ -93,7 +93,16 @@ class _FullLogitsFn(torch.autograd.Function):
         eng.encoder_backward(b)
         grads = []
         for name, p in model._arena_params():
-            grads.append(eng.g(name) if (p.requires_grad and name not in eng.layout.frozen) else None)
+            if not p.requires_grad or name in eng.layout.frozen:
+                grads.append(None)
+                continue
+            view = eng.grad_views[name]
+            # p.grad may already BE this arena view (published by the fused path, or kept by zero_grad(set_to_none=False)):
+            # autograd would then add the returned view onto itself in place and double the gradient.  Dropping the alias
+            # makes AccumulateGrad store (a copy of) the fresh gradient instead.
+            if p.grad is not None and p.grad.data_ptr() == view.data_ptr():
+                p.grad = None
+            grads.append(view)
         return (None, None, None, None) + tuple(grads)
 
 

@@ -142,16 +142,24 @@ def setup_config_and_directories(args: Dict[str, object], config_path: str):
     return original, log_dir, False
 
 
-def shard_batch(batch: Sequence, rank: int, world: int):
+def shard_batch(batch: Sequence, rank: int, world: int, strict: bool = True):
     """This rank's contiguous slice of a global collate batch (``Accelerator(split_batches=True)``, R/train.py:220),
-    re-padded to the slice's own longest sequence (the collate contract: zero padding up to the batch maximum)."""
+    re-padded to the slice's own longest sequence (the collate contract: zero padding up to the batch maximum).
+
+    ``strict`` (training batches): the batch size must be a multiple of the number of processes, as ``split_batches=True``
+    demands.  ``strict=False`` (validation: ``drop_last=False`` leaves a last batch of any size, R/dataloader.py:264-273):
+    ranks get ceil/floor shares; a rank whose share is empty gets ``None``."""
     if world == 1:
         return batch
     *tensors, lengths, midx = batch
     B = len(lengths)
-    if B % world:
+    if B % world and strict:
         raise ValueError(f"batch size {B} is not divisible by the number of processes {world} (split_batches=True)")
-    lo, hi = rank * (B // world), (rank + 1) * (B // world)
+    base, extra = divmod(B, world)
+    lo = rank * base + min(rank, extra)
+    hi = lo + base + (1 if rank < extra else 0)
+    if hi == lo:
+        return None
     lens = [int(x) for x in lengths[lo:hi]]
     width = max(lens)
     return tuple(t[lo:hi, :width].contiguous() for t in tensors) + (lens, list(midx[lo:hi]))
@@ -247,18 +255,22 @@ def initialize_model(config, log_dir: str, resuming: bool, device, use_token_ids
 @torch.no_grad()
 def validate(model, val_dataloader: Iterable, rank: int = 0, world: int = 1) -> float:
     """R/train.py:288-305: mean batch loss over the validation loader (no gradients, weights untouched); with several
-    ranks every rank scores its slice of each batch and the mean is all-reduced."""
+    ranks every rank scores its slice of each batch and the sample-weighted mean is all-reduced."""
     total, n = 0.0, 0
     for batch in val_dataloader:
-        total += float(model.loss(shard_batch(batch, rank, world)).item())
+        if world == 1:
+            total += float(model.loss(batch).item())
+        else:
+            mine = shard_batch(batch, rank, world, strict=False)
+            if mine is not None:   # uneven last batch: a share may be empty; shares are weighted by their sample count
+                total += float(model.loss(mine).item()) * len(mine[-2]) / len(batch[-2])
         n += 1
-    mean = total / max(n, 1)
     if world > 1:
         import torch.distributed as dist
-        t = torch.tensor([mean], dtype=torch.float64, device=next(model.parameters()).device)
+        t = torch.tensor([total], dtype=torch.float64, device=next(model.parameters()).device)
         dist.all_reduce(t)
-        mean = float(t.item()) / world
-    return mean
+        total = float(t.item())
+    return total / max(n, 1)
 
 
 class MetricsLogger:
@@ -368,13 +380,15 @@ def train(args: Optional[Dict[str, object]] = None) -> Tuple[int, int]:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=device)
     if rank == 0:
-        config, log_dir, resuming = setup_config_and_directories(args, str(args["config_path"]))
-    if world > 1:  # rank 0 decides fresh-vs-resume (it may purge the directory); the others read the result
+        decided = [setup_config_and_directories(args, str(args["config_path"]))]
+    else:
+        decided = [None]
+    if world > 1:
+        # rank 0 alone decides fresh-vs-resume (it may purge or create the run directory, and once it has copied the config
+        # in, every later look at the directory says "resume"); the other ranks take its decision as is
         import torch.distributed as dist
-        dist.barrier()
-        if rank != 0:
-            config, log_dir, resuming = setup_config_and_directories(args, str(args["config_path"]))
-            resuming = True if find_latest_checkpoint(log_dir)[0] else resuming
+        dist.broadcast_object_list(decided, src=0)
+    config, log_dir, resuming = decided[0]
     tp = config["training_params"]
     print(f"Resuming training from '{log_dir}' with existing config." if resuming else f"Starting new training run in '{log_dir}'.")
     logger = MetricsLogger(log_dir, config, enabled=rank == 0, use_wandb=not args.get("no_wandb", False))

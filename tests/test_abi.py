@@ -31,7 +31,7 @@ def test_abi_version_and_error_slot():
     # argument validation happens before any CUDA call, so it works without a device and never throws
     rc = lib.plb_gemm_bf16(0, 0, 0, 8, 8, None, 8, None, 8, None, 8, None, None, 0, None, 0, None)
     assert rc == -1 and b"bad shape" in lib.plb_last_error_string()
-    rc = lib.plb_attn_fwd(1, 8, 1, 1, 1, 1, 1, 32, 8, 8, 1, 8, 1, None)
+    rc = lib.plb_attn_fwd_tc(1, 8, 1, 1, 1, 1, 1, 32, 8, 8, 1, 8, 1, None)
     assert rc == -3 and b"head_dim" in lib.plb_last_error_string()
     with pytest.raises(_abi.PlbError):
         _abi.call("plb_ln_fwd", 0, 4, 8, 0, 0, 1e-12, 0, 0, 0)

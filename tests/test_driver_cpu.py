@@ -61,6 +61,10 @@ def test_shard_batch_splits_contiguously_and_repads():
         assert torch.equal(t, tok[lo:lo + 2, :max(ln)])
     with pytest.raises(ValueError):
         T.shard_batch(batch, 0, 4)
+    # validation batches (drop_last=False) may be uneven: ceil/floor shares, every sample exactly once, empty share -> None
+    shares = [T.shard_batch(batch, r, 4, strict=False) for r in range(4)]
+    assert [len(s[3]) for s in shares] == [2, 2, 1, 1] and sum((s[3] for s in shares), []) == lens
+    assert [T.shard_batch(batch, r, 8, strict=False) is None for r in range(8)] == [False] * 6 + [True] * 2
 
 
 def test_synthetic_loader_is_deterministic_and_redraws_every_epoch(tmp_path):

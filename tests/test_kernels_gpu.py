@@ -264,7 +264,7 @@ def _attn_ref(qkv, B, L, nh, lens):
                                          # counts, fewer key tiles than query tiles, a single valid key
                                          (2, 128, 1, [128, 5]), (2, 256, 2, [256, 130]), (3, 384, 2, [384, 100, 257]),
                                          (4, 512, 2, [1, 128, 129, 511]), (3, 320, 1, [320, 64, 200]), (2, 448, 1, [448, 449 - 64])])
-@pytest.mark.parametrize("fwd,bwd", [("plb_attn_fwd", "plb_attn_bwd"), ("plb_attn_fwd_tc", "plb_attn_bwd_tc")])
+@pytest.mark.parametrize("fwd,bwd", [("plb_attn_fwd_tc", "plb_attn_bwd_tc")])
 def test_attention_fwd_bwd(dev, B, L, nh, lens, fwd, bwd):
     H, T = nh * 64, B * L
     qkv = torch.randn(T, 3 * H, device=dev).to(BF)
