@@ -64,7 +64,81 @@ def state_to_np(sd):
     return {k: v.detach().cpu().numpy().copy() for k, v in sd.items()}
 
 
+FULL = dict(hidden_size=768, num_attention_heads=12, intermediate_size=2048, max_position_embeddings=512,
+            num_hidden_layers=12, embedding_size=128)   # R/configs/config.yml:32-39 (embedding_size: HF default 128)
+SUBSAMPLE = 8192   # gradient elements kept per tensor in the full-size fixture
+
+
+def subsample_index(name: str, numel: int) -> np.ndarray:
+    """Fixed pseudo-random element subset of a tensor (all of it when small), shared by the generator and the tests."""
+    if numel <= SUBSAMPLE:
+        return np.arange(numel)
+    import zlib
+    return np.sort(np.random.default_rng(zlib.crc32(name.encode())).choice(numel, SUBSAMPLE, replace=False))
+
+
+def full_size_case():
+    """Case D: the BENCHMARKED architecture (H 768, 12 heads, 12 applications of the shared layer, E 128, I 2048, 512
+    positions, Vp 188) with a 5003-word token head, B = 3, L = 512 — one sample shorter than the others (padded), one
+    sample without masked rows — evaluated by the reference in float64.  The 10^7 parameters are not stored: they are
+    ``plbert_oracle.init_params(cfg, 188, 5003, seed=2024, ln_jitter=0.05)`` rounded to float32; of the gradients the
+    fixture keeps every tensor's norm and a fixed 8192-element subsample, which pins the oracle at this size (and the
+    oracle's full gradients then pin the CUDA path)."""
+    ref_train, ref_model, ref_data, ref_sym = import_reference()
+    from transformers import AlbertConfig, AlbertModel
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+    from oracle import plbert_oracle as O
+    symbols = ref_sym.symbols
+    Vp, Vt, seed = len(symbols), 5003, 2024
+    np.random.seed(31)
+    random.seed(31)
+    rng = np.random.default_rng(31)
+    recs = synthetic_records(2, rng, 130, 150, symbols, Vt) + synthetic_records(1, rng, 60, 60, symbols, Vt)
+    ds = ref_data.MaskedPhonemeDataset(recs, use_token_ids=True, word_separator=87, max_seq_length=512, word_pred_prob=0.15,
+                                       phoneme_mask_prob=0.8, replace_prob=0.1)
+    token_ids, labels, masked, lengths, midx = ref_data.Collater()([ds[i] for i in range(len(ds))])
+    midx = [list(m) for m in midx]
+    assert lengths[0] == 512 and lengths[-1] < 512 and all(len(m) > 0 for m in midx)
+    midx[1] = []   # a sample without masked rows is skipped by the loss (R/train.py:124)
+    cfg = O.OracleConfig(vocab_size=Vp, **FULL)
+    params = {k: v.astype(np.float32) for k, v in O.init_params(cfg, Vp, Vt, seed=seed, ln_jitter=0.05).items()}
+    net = ref_model.MultiTaskModel(AlbertModel(AlbertConfig(vocab_size=Vp, **FULL)), num_phonemes=Vp, num_tokens=Vt,
+                                   hidden_size=FULL["hidden_size"])
+    missing, unexpected = net.load_state_dict({k: torch.from_numpy(v) for k, v in params.items()}, strict=False)
+    assert not unexpected and all("pooler" in m or "position_ids" in m or "token_type_ids" in m for m in missing), missing
+    net = net.double().train()
+    criterion = torch.nn.CrossEntropyLoss()
+    attn = (~ref_train.length_to_mask(torch.Tensor(lengths))).int()
+    p_pred, t_pred = net(masked, attention_mask=attn)
+    loss_p = ref_train.calculate_phoneme_loss(p_pred, labels, lengths, midx, criterion)
+    loss_t = ref_train.calculate_phoneme_loss(t_pred, token_ids, lengths, midx, criterion)
+    (loss_p + loss_t).backward()
+    out = {"config": np.asarray([Vp, FULL["embedding_size"], FULL["hidden_size"], FULL["num_attention_heads"],
+                                 FULL["intermediate_size"], FULL["num_hidden_layers"], FULL["max_position_embeddings"], Vt],
+                                dtype=np.int64),
+           "param_seed": np.int64(seed), "ln_jitter": np.float64(0.05),
+           "token_ids": token_ids.numpy(), "labels": labels.numpy(), "masked": masked.numpy(),
+           "lengths": np.asarray(lengths, dtype=np.int64), "loss_phoneme": np.float64(loss_p.item()),
+           "loss_token": np.float64(loss_t.item())}
+    out["midx_flat"], out["midx_offs"] = ragged(midx)
+    hidden = net.encoder(masked, attention_mask=attn).last_hidden_state.detach().numpy().reshape(-1)
+    out["last_hidden_sub"] = hidden[subsample_index("last_hidden", hidden.size)]
+    for n, p in net.named_parameters():
+        if p.grad is None:
+            continue
+        g = p.grad.detach().numpy().reshape(-1)
+        out[f"gradnorm/{n}"] = np.float64(np.linalg.norm(g))
+        out[f"gradsub/{n}"] = g[subsample_index(n, g.size)]
+    np.savez_compressed(os.path.join(OUT, "full_size_step.npz"), **out)
+    print("case D: loss_p %.6f loss_t %.6f lengths %s masked rows %s" % (loss_p.item(), loss_t.item(), lengths,
+                                                                         [len(m) for m in midx]))
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "D":   # only the full-size case (a minute of float64 CPU work)
+        os.makedirs(OUT, exist_ok=True)
+        full_size_case()
+        return
     ref_train, ref_model, ref_data, ref_sym = import_reference()
     from transformers import AlbertConfig, AlbertModel
 
@@ -237,6 +311,7 @@ def main():
                         midx_offs=ragged(midx)[1], pad_id=np.int64(0),
                         mask_id=np.int64(symbols.index(ref_sym.PHONEME_MASK)),
                         sep_id=np.int64(symbols.index(ref_sym.PHONEME_SEPARATOR)), num_symbols=np.int64(Vp))
+    full_size_case()
     print("wrote fixtures to", os.path.abspath(OUT))
 
 

@@ -87,14 +87,17 @@ def param_shapes(cfg: OracleConfig, num_phonemes: int, num_tokens: Optional[int]
 
 
 def init_params(cfg: OracleConfig, num_phonemes: int, num_tokens: Optional[int], seed: int = 0,
-                dtype=np.float64) -> Params:
+                dtype=np.float64, ln_jitter: float = 0.0) -> Params:
     """Random parameters with the reference's init *statistics* (HF :304-318: normal(0, 0.02), LN w=1/b=0,
-    word_embeddings[0] = 0).  Not bit-identical to torch's RNG — parity tests copy weights instead."""
+    word_embeddings[0] = 0).  Not bit-identical to torch's RNG — parity tests copy weights instead.
+    ``ln_jitter`` > 0 draws the LayerNorm weights from normal(1, ln_jitter) so that their gradient paths are exercised.
+    numpy's ``Generator.normal`` stream is stable across numpy versions, so (cfg, seed) names one parameter set that the
+    fixture generator (which feeds it to the reference) and the tests can both rebuild without storing 10^7 numbers."""
     rng = np.random.default_rng(seed)
     p: Params = {}
     for name, shape in param_shapes(cfg, num_phonemes, num_tokens).items():
         if "LayerNorm.weight" in name or "layer_norm.weight" in name:
-            v = np.ones(shape)
+            v = np.ones(shape) if ln_jitter == 0.0 else rng.normal(1.0, ln_jitter, shape)
         elif name.endswith("bias"):
             v = rng.normal(0.0, 0.02, shape)  # non-zero biases exercise every bias-gradient path
         else:

@@ -125,3 +125,43 @@ def test_float32_oracle_within_north_star_tolerance(golden_dir):
     for k in z.files:
         if k.startswith("grad/") and not k.endswith("attention.key.bias"):
             assert _rel(grads[k[len("grad/"):]].astype(np.float64), z[k]) < 1e-4, k
+
+
+def load_full_size_case(golden_dir):
+    """Case D (oracle/make_golden.py:full_size_case): the benchmarked architecture evaluated by the reference.  Returns
+    (npz, oracle config, float32-rounded parameters as float64, masked index lists)."""
+    from oracle.make_golden import subsample_index  # noqa: F401  (same element subsets as the generator)
+    z = np.load(os.path.join(golden_dir, "full_size_step.npz"))
+    c = [int(x) for x in z["config"]]
+    cfg = O.OracleConfig(vocab_size=c[0], embedding_size=c[1], hidden_size=c[2], num_attention_heads=c[3], intermediate_size=c[4],
+                         num_hidden_layers=c[5], max_position_embeddings=c[6])
+    params = {k: v.astype(np.float32).astype(np.float64)
+              for k, v in O.init_params(cfg, c[0], c[7], seed=int(z["param_seed"]), ln_jitter=float(z["ln_jitter"])).items()}
+    offs = z["midx_offs"]
+    midx = [z["midx_flat"][offs[i]:offs[i + 1]].tolist() for i in range(len(offs) - 1)]
+    return z, cfg, params, midx
+
+
+def test_full_size_step_matches_reference(golden_dir):
+    """The oracle at the BENCHMARKED dimensions (H 768, 12 heads, 12 shared-layer applications, L 512, two heads) against the
+    reference's own float64 outputs: losses, every gradient tensor's norm and a fixed 8192-element subsample of each."""
+    from oracle.make_golden import subsample_index
+    z, cfg, params, midx = load_full_size_case(golden_dir)
+    assert (cfg.hidden_size, cfg.num_attention_heads, cfg.num_hidden_layers, cfg.intermediate_size) == (768, 12, 12, 2048)
+    assert z["masked"].shape == (3, 512) and min(z["lengths"]) < 512 and any(len(m) == 0 for m in midx)
+    total, losses, grads, hidden = O.loss_and_grads(params, cfg, z["masked"], z["labels"], z["lengths"], midx,
+                                                    token_labels=z["token_ids"])
+    assert abs(losses["phoneme_predictor"] - z["loss_phoneme"]) <= 1e-10 * abs(z["loss_phoneme"])
+    assert abs(losses["token_predictor"] - z["loss_token"]) <= 1e-10 * abs(z["loss_token"])
+    h = hidden.reshape(-1)
+    assert _rel(h[subsample_index("last_hidden", h.size)], z["last_hidden_sub"]) < 1e-9
+    names = {k[len("gradsub/"):] for k in z.files if k.startswith("gradsub/")}
+    assert names == set(grads), names ^ set(grads)
+    qb = float(z["gradnorm/" + O._LAYER + "attention.query.bias"])
+    for name in sorted(names):
+        g = grads[name].reshape(-1)
+        if name.endswith("attention.key.bias"):
+            assert np.linalg.norm(g) <= 1e-9 * qb and float(z["gradnorm/" + name]) <= 1e-9 * qb
+            continue
+        assert abs(np.linalg.norm(g) - z["gradnorm/" + name]) <= 1e-9 * z["gradnorm/" + name], name
+        assert _rel(g[subsample_index(name, g.size)], z["gradsub/" + name]) < 1e-8, name

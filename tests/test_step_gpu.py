@@ -333,6 +333,16 @@ def test_reference_style_forward_backward(dev):
     assert abs(loss.item() - total) <= 2e-2 * abs(total)
     check_grads(model, grads, masked.shape[1])
     opt.step()
+    # p.grad aliasing the gradient arena (the fused path publishes arena views; zero_grad(set_to_none=False) keeps them):
+    # the autograd node must not add the arena onto itself — d(sum of 8 positions' logits)/d(bias) = 8
+    model.loss_and_backward((labels, masked, lengths, midx))
+    assert model.phoneme_predictor.bias.grad.data_ptr() == model._engine.grad_views["phoneme_predictor.bias"].data_ptr()
+    opt.zero_grad(set_to_none=False)
+    pred = model(masked.to(dev), attention_mask=(~text_mask).int())
+    pred[0, :8].sum().backward()
+    g = model.phoneme_predictor.bias.grad
+    assert torch.allclose(g, torch.full_like(g, 8.0), rtol=1e-2), g[:4]
+    opt.step()
 
 
 def test_empty_batch_and_checkpoint_roundtrip(dev, tmp_path):
