@@ -8,7 +8,9 @@ into FusedAdamW) == one-rank step on the concatenated batch (R/t
 Every rank takes its contiguous share of each global batch (train.shard_batch), runs 3 optimizer steps; rank 0 then repeats
 the 3 steps alone on the whole batches from the same initial weights and compares
   * the averaged gradient of step 1 (cosine per tensor, worst reported),
-  * the weights after 3 steps (cosine of the UPDATE w3 - w0 per tensor; lr 1e-3 so that the weights really move),
+  * the weights after 3 steps (cosine of the UPDATE w3 - w0 per tensor; lr 1e-3 so that the weights really move; bar 0.99:
+    Adam normalises every element's step to ~lr, so elements whose gradient sits at the fp32 summation-order noise floor
+    may step the other way and the two trajectories then drift apart — the step-1 gradients are the exact comparison),
   * that all ranks hold bit-identical weights at the end.
 Case "empty_rank": the last rank's share has no masked rows at all (R/train.py:129) — it must still join both all-reduces and
 step (no hang, identical replicas); the averaged gradient is then (1/world) x the gradient of the other ranks' mean.
@@ -110,7 +112,7 @@ def main():
             if case == "equal":
                 rec["worst_update_cosine_after_3_steps"] = worst_u
             rec["pass"] = bool(worst_g >= 0.9999 and worst_ratio < 1e-2 and rec["replicas_bit_identical"]
-                               and (case != "equal" or worst_u >= 0.999))
+                               and (case != "equal" or worst_u >= 0.99))
             report["cases"][case] = rec
             del one, opt1, e1
         del model, opt, eng, sync
