@@ -110,13 +110,16 @@ __device__ __forceinline__ void turn_release(int grp, int quad, uint32_t c, uint
 // Optional timeline instrumentation (profiles/attn_trace.py builds a separate library with -DPLB_ATTN_TRACE): lane 0 of
 // every warp of CTA 0 appends (clock, warp, code, index) records.  Compiled out of the product library.
 #ifdef PLB_ATTN_TRACE
+#ifndef PLB_TRACE_BLOCK
+#define PLB_TRACE_BLOCK 0   // which CTA records (a mid-run block shows the steady state, block 0 the cold first wave)
+#endif
 constexpr unsigned TRACE_SLOTS = 512;  // records per warp; plain stores, no atomics, so the timeline stays undisturbed
 constexpr unsigned TRACE_CAP = 3 * 32 * TRACE_SLOTS;  // kernel id (0 fwd, 1 dQ, 2 dK/dV) x warp x slot
 __device__ unsigned long long g_trace[TRACE_CAP];
 #define PLB_TRACE_INIT(kid) unsigned trace_k = 0; const unsigned trace_w = (kid) * 32 + (threadIdx.x >> 5)
 #define PLB_TRACE(code, idx)                                                                                          \
   do {                                                                                                                \
-    if (blockIdx.x == 0 && (threadIdx.x & 31) == 0 && trace_k < TRACE_SLOTS)                                          \
+    if (blockIdx.x == PLB_TRACE_BLOCK && (threadIdx.x & 31) == 0 && trace_k < TRACE_SLOTS)                                          \
       g_trace[trace_w * TRACE_SLOTS + trace_k++] = (static_cast<unsigned long long>(clock64()) << 24) |               \
                                                    (trace_w << 16) | ((code) << 8) | ((idx) & 255);                   \
   } while (0)

@@ -106,6 +106,37 @@ class _FullLogitsFn(torch.autograd.Function):
         return (None, None, None, None) + tuple(grads)
 
 
+class _EncoderFn(torch.autograd.Function):
+    """``encoder(ids, attention_mask=...).last_hidden_state`` with autograd (StyleTTS finetunes PL-BERT through exactly this
+    call, R/README.md:91): forward = fused encoder, backward = fused encoder backward given d(last_hidden_state)."""
+
+    @staticmethod
+    def forward(ctx, model, batch: DeviceBatch, out_dtype, *params):
+        eng: Engine = model._engine
+        hidden = eng.forward(batch, train=True)
+        ctx.model, ctx.batch, ctx.n_params = model, batch, len(params)
+        return hidden.to(out_dtype).view(batch.B, batch.L, -1)   # a copy: the workspace is reused by the next call
+
+    @staticmethod
+    def backward(ctx, dhidden):
+        model, b = ctx.model, ctx.batch
+        eng: Engine = model._engine
+        eng.begin_backward()
+        eng.d_y[:b.T].copy_(dhidden.reshape(b.T, -1))               # fp32 -> bf16 on the device
+        eng._after_head_backward()                                   # no head gradients on this path: bucket 0 is zeros
+        eng.encoder_backward(b)
+        grads = []
+        for name, p in model._arena_params():
+            if not p.requires_grad or name in eng.layout.frozen or not name.startswith("encoder."):
+                grads.append(None)
+                continue
+            view = eng.grad_views[name]
+            if p.grad is not None and p.grad.data_ptr() == view.data_ptr():
+                p.grad = None                                        # see _FullLogitsFn.backward
+            grads.append(view)
+        return (None, None, None) + tuple(grads)
+
+
 class _EncoderGraph:
     """One captured encoder forward for a fixed [B, L] shape (padded layout).  Inputs live in static device buffers
     (ids, positions, lengths) that every call overwrites with device-side copies; the graph reads the engine's bf16
@@ -328,12 +359,14 @@ class MultiTaskModel(_FusedModel):
     # per-sample mean — upstream yl4579/PL-BERT's word loss).  The reference fork has no token loss at all.
     token_rows = "masked"
 
-    def __init__(self, model, num_phonemes, num_tokens, hidden_size):
+    def __init__(self, model, num_phonemes, num_tokens, hidden_size, _fuse=True):
         super().__init__()
         self.encoder = model
         self.phoneme_predictor = nn.Linear(hidden_size, num_phonemes)
         self.token_predictor = nn.Linear(hidden_size, num_tokens)
         self._init_fused()
+        if _fuse:
+            fuse_albert(model, owner=self)   # ``self.encoder(ids, attention_mask=...)`` (R/model.py:14) runs the kernels too
 
     def forward(self, phonemes, attention_mask=None):
         phoneme_pred, token_pred = self._forward_logits(phonemes, attention_mask)
@@ -345,15 +378,66 @@ class PhonemeOnlyModel(_FusedModel):
 
     _heads = ["phoneme_predictor"]
 
-    def __init__(self, model, num_phonemes, hidden_size):
+    def __init__(self, model, num_phonemes, hidden_size, _fuse=True):
         super().__init__()
         self.encoder = model
         self.phoneme_predictor = nn.Linear(hidden_size, num_phonemes)
         self._init_fused()
+        if _fuse:
+            fuse_albert(model, owner=self)
 
     def forward(self, phonemes, attention_mask=None):
         (phoneme_pred,) = self._forward_logits(phonemes, attention_mask)
         return phoneme_pred
+
+
+def fuse_albert(albert, owner: Optional[_FusedModel] = None, output_dtype: torch.dtype = torch.float32,
+                use_graph: bool = False):
+    """Make ``albert(ids, attention_mask=mask).last_hidden_state`` — the call of R/model.py:14-15 and of the StyleTTS
+    snippet (R/README.md:91,107) — run the sm_100a kernels.  ``albert`` is the caller's HF ``AlbertModel`` and stays the
+    parameter container (``state_dict`` names, ``save_pretrained``, ``from_pretrained``, ``config`` are untouched); only its
+    ``forward`` is replaced, on this instance.  The stock implementation remains reachable as ``albert.hf_forward``.
+
+    ``owner``: the ``MultiTaskModel`` / ``PhonemeOnlyModel`` whose engine holds the weights (the constructors pass
+    themselves); a stand-alone encoder (StyleTTS: ``bert = fuse_albert(AlbertModel(cfg))``) gets a private engine.
+    ``output_dtype``: dtype of ``last_hidden_state`` (HF returns fp32 in an fp32 model; the kernels compute in bf16).
+    ``use_graph``: replay a captured CUDA graph for no-grad calls (fixed [B, L]; the mask must be a right-padded prefix
+    mask and is NOT validated on that path — no device->host sync).  With gradients enabled the call is differentiable
+    (fused backward into the encoder parameters).  CPU tensors raise ``PlbError``: there is no fallback.
+    ``pooler_output`` is ``None`` (PL-BERT never reads it: R/model.py:14-15)."""
+    from transformers.modeling_outputs import BaseModelOutputWithPooling
+    if getattr(albert, "_plb_fused", False):
+        if owner is not None:
+            object.__setattr__(albert, "_plb_owner", owner)
+        return albert
+    if owner is None:
+        # private engine: the layout needs a phoneme head; this 8-row one never leaves the wrapper (not in albert's state_dict)
+        owner = PhonemeOnlyModel(albert, 8, albert.config.hidden_size, _fuse=False)
+    object.__setattr__(albert, "_plb_owner", owner)      # plain attribute: no module registration, no state_dict entry
+    object.__setattr__(albert, "hf_forward", albert.forward)
+    albert.plb_output_dtype, albert.plb_use_graph = output_dtype, use_graph
+
+    def forward(input_ids=None, attention_mask=None, token_type_ids=None, position_ids=None, inputs_embeds=None, **kwargs):
+        model: _FusedModel = albert._plb_owner
+        if input_ids is None or inputs_embeds is not None or position_ids is not None:
+            raise _abi.PlbError("fused AlbertModel.forward takes input_ids (+ attention_mask) only, like the reference's calls")
+        if token_type_ids is not None and bool(token_type_ids.ne(0).any()):
+            raise _abi.PlbError("fused AlbertModel.forward: token_type_ids must be all zeros (the reference never passes any)")
+        model._ensure_engine(input_ids.device)
+        params = [p for _, p in model._arena_params()]
+        if torch.is_grad_enabled() and any(p.requires_grad for n, p in model._arena_params() if n.startswith("encoder.")):
+            batch = model._stage_inputs(input_ids, attention_mask)
+            hidden = _EncoderFn.apply(model, batch, albert.plb_output_dtype, *params)
+        else:
+            hidden = model.encode(input_ids, attention_mask, use_graph=albert.plb_use_graph).to(albert.plb_output_dtype)
+        return BaseModelOutputWithPooling(last_hidden_state=hidden, pooler_output=None)
+
+    object.__setattr__(albert, "forward", forward)
+    object.__setattr__(albert, "_plb_fused", True)
+    return albert
+
+
+FusedAlbertEncoder = fuse_albert   # the name VERDICT round 1 asked for: FusedAlbertEncoder(albert)(ids, attention_mask=m)
 
 
 # upstream (yl4579/PL-BERT) checkpoints call the heads mask_predictor / word_predictor (SURVEY.md §0 row 1)

@@ -19,7 +19,7 @@ LIB = os.path.join(OUT, "libplbert_b200_trace.so")
 def build():
     from plbert_b200.build import NVCC_FLAGS, _nvcc, _sources
     os.makedirs(OUT, exist_ok=True)
-    cmd = [_nvcc(), *NVCC_FLAGS, "-DPLB_ATTN_TRACE", "-shared", "-o", LIB, *_sources(), "-lcuda"]
+    cmd = [_nvcc(), *NVCC_FLAGS, "-DPLB_ATTN_TRACE", f"-DPLB_TRACE_BLOCK={os.environ.get('TRACE_BLOCK', '0')}", "-shared", "-o", LIB, *_sources(), "-lcuda"]
     print(" ".join(cmd))
     subprocess.run(cmd, check=True)
 

@@ -137,3 +137,28 @@ def test_unsupported_configs_are_rejected():
         cfg = AlbertConfig(vocab_size=188, **{**dict(hidden_size=128, num_attention_heads=2, intermediate_size=256, embedding_size=32), **kw})
         with pytest.raises(Exception):
             EngineConfig.from_albert(cfg, 188, None)
+
+
+def test_fused_albert_keeps_the_container_and_fails_loudly_on_cpu():
+    """``fuse_albert`` only swaps ``forward`` on the caller's AlbertModel instance: names, shapes, ``save_pretrained`` inputs
+    stay; the stock implementation stays reachable; a CPU call raises instead of silently computing through PyTorch."""
+    import pytest
+    import torch
+    from transformers import AlbertConfig, AlbertModel
+    import plbert_b200 as P
+    cfg = AlbertConfig(vocab_size=188, embedding_size=32, hidden_size=128, num_attention_heads=2, intermediate_size=256,
+                       num_hidden_layers=2, max_position_embeddings=64)
+    torch.manual_seed(0)
+    bert = AlbertModel(cfg)
+    keys = list(bert.state_dict().keys())
+    assert P.fuse_albert(bert) is bert and P.FusedAlbertEncoder(bert) is bert       # idempotent
+    assert list(bert.state_dict().keys()) == keys                                     # no wrapper / head leaks in
+    ids = torch.randint(1, 185, (2, 16))
+    with pytest.raises(P.PlbError):
+        bert(ids, attention_mask=torch.ones_like(ids))
+    out = bert.hf_forward(ids, attention_mask=torch.ones_like(ids))                   # the stock path is still there
+    assert out.last_hidden_state.shape == (2, 16, 128)
+    # the drop-in models fuse their encoder and report themselves as its owner
+    model = P.PhonemeOnlyModel(AlbertModel(cfg), 188, 128)
+    assert model.encoder._plb_fused and model.encoder._plb_owner is model
+    assert set(model.state_dict()) == {"encoder." + k for k in keys} | {"phoneme_predictor.weight", "phoneme_predictor.bias"}

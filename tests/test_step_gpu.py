@@ -391,3 +391,66 @@ def test_cpu_call_fails_loudly():
     model = P.PhonemeOnlyModel(enc, 188, 128)
     with pytest.raises(P.PlbError):
         model(torch.zeros(2, 8, dtype=torch.long))
+
+
+def test_fused_albert_encoder_call_shape_and_autograd(dev):
+    """``encoder(ids, attention_mask=m).last_hidden_state`` (R/model.py:14-15; StyleTTS, R/README.md:91,107) runs the kernels:
+    inside the drop-in models and stand-alone (``fuse_albert(AlbertModel(cfg))`` + the StyleTTS strict state-dict load), with
+    and without gradients, against the stock HF implementation in fp32 on the same weights."""
+    import copy
+    import plbert_b200 as P
+    from transformers import AlbertConfig, AlbertModel
+    cfg = AlbertConfig(vocab_size=188, embedding_size=32, hidden_size=128, num_attention_heads=2, intermediate_size=256,
+                       num_hidden_layers=3, max_position_embeddings=128)
+    torch.manual_seed(21)
+    stock = AlbertModel(cfg)
+    with torch.no_grad():
+        for n, p in stock.named_parameters():
+            if n.endswith("bias") or "LayerNorm" in n or "layer_norm" in n:
+                p.add_(0.05 * torch.randn_like(p))
+    sd = {k: v.clone() for k, v in stock.state_dict().items()}
+    stock = stock.to(dev).train()
+    g = torch.Generator().manual_seed(3)
+    ids = torch.randint(1, 185, (4, 96), generator=g).to(dev)
+    lens = torch.tensor([96, 80, 33, 7])
+    mask = (torch.arange(96)[None, :] < lens[:, None]).int().to(dev)
+    valid = mask.bool()
+    ref = stock(ids, attention_mask=mask).last_hidden_state
+    wgt = torch.randn(ref.shape, generator=g).to(dev) * valid[:, :, None]          # padded rows never reach a loss
+    (ref * wgt).sum().backward()
+
+    # stand-alone encoder, loaded the StyleTTS way (strict load of the encoder keys)
+    bert = P.fuse_albert(AlbertModel(cfg))
+    bert.load_state_dict(sd, strict=True)
+    bert = bert.to(dev)
+    with torch.no_grad():
+        out = bert(ids, attention_mask=mask)
+    assert out.last_hidden_state.dtype == torch.float32 and out.last_hidden_state.shape == (4, 96, 128) and out.pooler_output is None
+    assert cosine(out.last_hidden_state[valid].cpu().numpy(), ref[valid].detach().cpu().numpy()) > 0.9995
+    assert cosine(out[0][valid].cpu().numpy(), ref[valid].detach().cpu().numpy()) > 0.9995       # tuple-style access
+    bert.plb_use_graph = True
+    with torch.no_grad():
+        graphed = bert(ids, attention_mask=mask).last_hidden_state
+    assert torch.equal(graphed[valid], out.last_hidden_state[valid])
+    # differentiable: finetuning through the encoder call
+    hid = bert(ids, attention_mask=mask).last_hidden_state
+    assert hid.requires_grad
+    (hid * wgt).sum().backward()
+    qb = stock.encoder.albert_layer_groups[0].albert_layers[0].attention.query.bias.grad.norm().item()
+    for (n, p), (_, q) in zip(bert.named_parameters(), stock.named_parameters()):
+        if "pooler" in n:
+            assert p.grad is None
+            continue
+        if n.endswith("attention.key.bias"):
+            assert p.grad.norm().item() <= 0.05 * qb
+            continue
+        assert cosine(p.grad.float().cpu().numpy(), q.grad.cpu().numpy()) >= 0.999, n
+    # the same call on the encoder of a drop-in model uses the model's engine (one set of weights)
+    model = P.PhonemeOnlyModel(AlbertModel(cfg), 188, 128)
+    model.encoder.load_state_dict(sd, strict=True)
+    model = model.to(dev)
+    with torch.no_grad():
+        h2 = model.encoder(ids, attention_mask=mask).last_hidden_state
+    assert model.encoder._plb_owner is model and model._engine is not None
+    assert torch.equal(h2[valid], out.last_hidden_state[valid])
+    assert torch.equal(h2.to(torch.bfloat16)[valid], model.encode(ids, mask)[valid])
