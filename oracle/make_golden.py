@@ -134,7 +134,36 @@ def full_size_case():
                                                                          [len(m) for m in midx]))
 
 
+def dataset_case():
+    """Outputs of the reference's own ``MaskedPhonemeDataset`` + collaters (R/dataloader.py:19-142,200-223,276-297) under
+    fixed ``np.random`` / ``random`` seeds, for the host-side mirror in plbert_b200/data.py.  Records are regenerated by the
+    test from ``plbert_b200.data.synthetic_records`` (same seed), only the outputs are stored."""
+    ref_train, ref_model, ref_data, ref_sym = import_reference()
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+    from plbert_b200.data import synthetic_records as make_records
+    out = {"symbols": np.asarray(ref_sym.symbols)}
+    for name, use_tok, max_len, words in (("short", True, 48, (3, 12)), ("long", False, 512, (100, 150))):
+        recs = make_records(6, seed=5, num_tokens=997, min_words=words[0], max_words=words[1])
+        ds = ref_data.MaskedPhonemeDataset(recs, word_pred_prob=0.3, phoneme_mask_prob=0.8, replace_prob=0.1, word_separator=87,
+                                           max_seq_length=max_len, use_token_ids=use_tok)
+        np.random.seed(99)
+        random.seed(99)
+        items = [ds[i] for i in range(len(ds))]
+        batch = (ref_data.Collater() if use_tok else ref_data.PhonemeOnlyCollater())(items)
+        *tensors, lengths, midx = batch
+        for k, t in enumerate(tensors):
+            out[f"{name}/tensor{k}"] = t.numpy()
+        out[f"{name}/lengths"] = np.asarray(lengths, dtype=np.int64)
+        out[f"{name}/midx_flat"], out[f"{name}/midx_offs"] = ragged([list(m) for m in midx])
+    np.savez_compressed(os.path.join(OUT, "dataset_pipeline.npz"), **out)
+    print("dataset case: lengths", out["short/lengths"].tolist(), out["long/lengths"].tolist())
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "dataset":
+        os.makedirs(OUT, exist_ok=True)
+        dataset_case()
+        return
     if len(sys.argv) > 1 and sys.argv[1] == "D":   # only the full-size case (a minute of float64 CPU work)
         os.makedirs(OUT, exist_ok=True)
         full_size_case()
@@ -312,6 +341,7 @@ def main():
                         mask_id=np.int64(symbols.index(ref_sym.PHONEME_MASK)),
                         sep_id=np.int64(symbols.index(ref_sym.PHONEME_SEPARATOR)), num_symbols=np.int64(Vp))
     full_size_case()
+    dataset_case()
     print("wrote fixtures to", os.path.abspath(OUT))
 
 
