@@ -178,13 +178,34 @@ class _BatchTasks(torch.utils.data.Dataset):
         return self.collate_fn([self.dataset[i] for i in indices])
 
 
+class _TaskSampler:
+    """Sampler over batch tasks.  ``epochs`` = 1: the tasks of the loader's next epoch (advances the epoch counter every time
+    it is iterated); ``epochs`` = None: all epochs back to back, endlessly (keeps the workers busy across epoch boundaries)."""
+
+    def __init__(self, owner: "CollateWorkerLoader", endless: bool):
+        self.owner, self.endless = owner, endless
+
+    def __iter__(self):
+        while True:
+            tasks = self.owner._epoch_tasks(self.owner.epoch)
+            self.owner.epoch += 1
+            yield from tasks
+            if not self.endless:
+                return
+
+    def __len__(self) -> int:
+        return len(self.owner)
+
+
 class CollateWorkerLoader:
     """Epoch-style iterable of collate tuples built by ``num_workers`` background processes (0 = in the calling thread,
     same batches).  ``shuffle`` / ``drop_last`` as in R/dataloader.py:244-273 (train: True / True; validation: False / False).
+    The worker processes are started once and live as long as the loader (``persistent_workers``).
 
         loader = CollateWorkerLoader(MaskedPhonemeDataset(records, **dataset_params, use_token_ids=True), 192, Collater(), 8)
         feed = BatchFeeder(model, loader)            # stages batch i+1 (flatten + pinned H2D) under step i
-    """
+
+    ``endless()`` iterates over all epochs back to back without draining the workers at the epoch boundaries."""
 
     def __init__(self, dataset, batch_size: int, collate_fn, num_workers: int = 4, shuffle: bool = True, drop_last: bool = True,
                  seed: int = 1234, prefetch_factor: int = 2):
@@ -193,7 +214,8 @@ class CollateWorkerLoader:
         self._tasks = _BatchTasks(dataset, collate_fn, seed)
         self._kw = dict(batch_size=None, shuffle=False, num_workers=num_workers)
         if num_workers > 0:
-            self._kw.update(prefetch_factor=prefetch_factor)
+            self._kw.update(prefetch_factor=prefetch_factor, persistent_workers=True)
+        self._dl = None   # created on first use: worker start-up is paid once
         self.epoch = 0
 
     def __len__(self) -> int:
@@ -203,17 +225,17 @@ class CollateWorkerLoader:
     def _epoch_tasks(self, epoch: int):
         n = len(self.dataset)
         order = np.random.default_rng([self.seed, epoch]).permutation(n) if self.shuffle else np.arange(n)
-        tasks = []
-        for k in range(len(self)):
-            tasks.append((epoch, k, order[k * self.batch_size:(k + 1) * self.batch_size].tolist()))
-        return tasks
+        return [(epoch, k, order[k * self.batch_size:(k + 1) * self.batch_size].tolist()) for k in range(len(self))]
 
     def __iter__(self):
-        tasks = self._epoch_tasks(self.epoch)
-        self.epoch += 1
         # the sampler yields whole tasks; with batch_size=None the DataLoader hands each one to dataset.__getitem__ in a worker
         # and returns the results in task order
-        return iter(torch.utils.data.DataLoader(self._tasks, sampler=tasks, **self._kw))
+        if self._dl is None:
+            self._dl = torch.utils.data.DataLoader(self._tasks, sampler=_TaskSampler(self, endless=False), **self._kw)
+        return iter(self._dl)
+
+    def endless(self):
+        return iter(torch.utils.data.DataLoader(self._tasks, sampler=_TaskSampler(self, endless=True), **self._kw))
 
 
 def build_dataloader(df, batch_size, device, dataset_config, use_token_ids, num_workers=4, seed: int = 1234, **kwargs):

@@ -14,8 +14,8 @@ Data parallelism is ``ddp.GradientSynchronizer`` (one process per GPU, the globa
 ``Accelerator(split_batches=True)``, R/train.py:220); mixed precision is the engine's bf16/fp32-master scheme whatever
 ``mixed_precision`` says; wandb is used when importable and not disabled, a JSON-lines file in the run directory
 otherwise.  The dataset is whatever yields the reference's collate tuples: ``training_dataset: synthetic`` selects the
-built-in generator, anything else goes through the reference's own ``dataloader.build_dataloader`` if that module is
-importable (it is data preparation, not part of this path).
+built-in generator, anything else goes through ``plbert_b200.data`` — the reference's masking + collate in background
+worker processes.
 """
 from __future__ import annotations
 
@@ -190,24 +190,32 @@ class SyntheticLoader:
             yield synthetic_collate_batch(self.batch_size, seed=base + i, **self.kw)
 
 
-def setup_dataset_and_dataloader(config, device, use_token_ids: bool = False, num_tokens: int = 64000):
-    """R/train.py:240-257.  Returns ``(train_loader, val_loader)`` yielding GLOBAL collate batches."""
+def setup_dataset_and_dataloader(config, device, use_token_ids: bool = False, num_tokens: int = 64000, num_workers: int = 4):
+    """R/train.py:240-257.  Returns ``(train_loader, val_loader)`` yielding GLOBAL collate batches.
+
+    ``training_dataset``: ``synthetic`` = the built-in tensor generator (no per-sample Python at all); ``synthetic_records`` =
+    synthetic dataset rows through the reference's masking + collate pipeline in ``num_workers`` background processes;
+    anything else = a ``datasets.load_dataset`` name whose rows go through that same pipeline (``plbert_b200.data``: mirrors
+    of R/dataloader.py's classes plus the worker pool — the reference runs them with ``num_workers=0``, R/train.py:253)."""
     tp = config["training_params"]
-    if str(tp.get("training_dataset", "")).lower() == "synthetic":
+    name = str(tp.get("training_dataset", "")).lower()
+    if name == "synthetic":
         n_train = int(tp.get("synthetic_batches_per_epoch", 64))
         n_val = int(tp.get("synthetic_val_batches", 2))
         mk = lambda n, seed, redraw: SyntheticLoader(int(tp["batch_size"]), config["dataset_params"], n, seed, use_token_ids,
                                                      num_tokens, redraw=redraw)
         return mk(n_train, 1234, True), mk(n_val, 987654, False)
-    try:  # the reference's own data pipeline (host-side string/integer work, reused unchanged: SURVEY.md §8 a11)
-        from datasets import load_dataset
-        from dataloader import build_dataloader  # R/dataloader.py:225-274, found on PYTHONPATH
-    except ImportError as e:
-        raise RuntimeError("training_dataset is not 'synthetic' and the reference data pipeline (datasets + the PL-BERT "
-                           "dataloader module on PYTHONPATH) is not importable: " + str(e)) from e
-    dataset = load_dataset(tp["training_dataset"], split=tp["split"])
-    return build_dataloader(dataset, batch_size=tp["batch_size"], num_workers=0, device=device, use_token_ids=use_token_ids,
-                            dataset_config=config["dataset_params"])
+    from .data import build_dataloader, synthetic_records
+    if name == "synthetic_records":
+        dataset = synthetic_records(int(tp.get("synthetic_rows", 4096)), seed=1234, num_tokens=num_tokens)
+    else:
+        try:
+            from datasets import load_dataset
+        except ImportError as e:
+            raise RuntimeError("training_dataset names a datasets.load_dataset source but `datasets` is not importable: " + str(e)) from e
+        dataset = load_dataset(tp["training_dataset"], split=tp["split"])
+    return build_dataloader(dataset, batch_size=tp["batch_size"], device=device, dataset_config=config["dataset_params"],
+                            use_token_ids=use_token_ids, num_workers=num_workers)
 
 
 def _num_symbols() -> int:
@@ -393,11 +401,13 @@ def train(args: Optional[Dict[str, object]] = None) -> Tuple[int, int]:
     print(f"Resuming training from '{log_dir}' with existing config." if resuming else f"Starting new training run in '{log_dir}'.")
     logger = MetricsLogger(log_dir, config, enabled=rank == 0, use_wandb=not args.get("no_wandb", False))
     # optional block of the YAML that only this implementation reads (the reference's keys stay untouched):
-    #   b200_params: {use_token_ids, num_tokens, token_rows: masked|all_valid, pack_sequences, checkpoint_extension, log_lag}
+    #   b200_params: {use_token_ids, num_tokens, token_rows: masked|all_valid, pack_sequences, checkpoint_extension, log_lag,
+    #                 num_workers (input pipeline processes)}
     bp = dict(config.get("b200_params") or {})
     use_tok = bool(args.get("use_token_ids") or bp.get("use_token_ids", False))
     num_tokens = args.get("num_tokens") or bp.get("num_tokens")
-    train_dl, val_dl = setup_dataset_and_dataloader(config, device, use_tok, int(num_tokens or 64000))
+    train_dl, val_dl = setup_dataset_and_dataloader(config, device, use_tok, int(num_tokens or 64000),
+                                                    num_workers=int(bp.get("num_workers", 4)))
     model, optimizer, current_step = initialize_model(config, log_dir, resuming, device, use_tok, num_tokens)
     if "pack_sequences" in bp:
         model.pack_sequences = bool(bp["pack_sequences"])
