@@ -261,11 +261,15 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const AttnTcParam
     uint32_t s_kt = 0;
     uint32_t s_box_uses[MAX_BOXES] = {0, 0, 0, 0};
     auto s_tiles = [&]() { return g == 0 ? (s_it.n_tiles + 1) >> 1 : s_it.n_tiles >> 1; };
+    uint32_t s_issued = 0;                        // S chunks issued so far (the PV stream is at chunk c <= s_issued)
+    bool s_skipped = false;                       // the cursor's last move passed items in which this group has no tile
     auto s_skip_empty = [&]() {  // advance the S cursor past items in which this group has no tile
+      s_skipped = false;
       while (s_item < n_items && s_tiles() == 0) {
         for (int j = 0; j < s_it.n_chunks; ++j) ++s_box_uses[j];
         s_item += gridDim.x;
         if (s_item < n_items) s_it = fwd_item(p, s_item);
+        s_skipped = true;
       }
     };
     auto issue_s = [&]() {  // S_j = Q K_j^T at the cursor, then advance the cursor
@@ -277,6 +281,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const AttnTcParam
 #pragma unroll
       for (int kk = 0; kk < D / 16; ++kk) umma_bf16(tmem_sg, qb + 2 * kk, kb + 2 * kk, idesc_s, kk > 0);
       umma_commit(&gb[S_FULL]);
+      ++s_issued;
       if (s_j == s_it.n_chunks - 1) umma_commit(&gb[Q_EMPTY + sl]);
       PLB_TRACE(1, s_j);
       if (++s_j == s_it.n_chunks) {
@@ -292,15 +297,20 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const AttnTcParam
       }
     };
     s_skip_empty();
-    if (s_item < n_items) issue_s();
     FwdItem nxt = blockIdx.x < n_items ? fwd_item(p, blockIdx.x) : FwdItem{};
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
       const FwdItem it = nxt;
       if (item + static_cast<int>(gridDim.x) < n_items) nxt = fwd_item(p, item + gridDim.x);
       const int my_tiles = g == 0 ? (it.n_tiles + 1) >> 1 : it.n_tiles >> 1;
       if (my_tiles == 0) {
-        // this group has nothing to do in the item: release its share of the K / V boxes right away
+        // this group has nothing to do in the item: release its share of the K / V boxes — but only once the item's boxes
+        // have LANDED.  The producer refills box j only after both groups' arrivals of the previous item, so waiting for the
+        // fill keeps this group's arrivals in item order; arriving right away let a group without tiles in several
+        // consecutive short items run ahead, complete kv_free phases on its own (the other group's K / V overwritten under
+        // it) and push the barrier two phases past the producer's parity wait (deadlock -> trap).
         for (int j = 0; j < it.n_chunks; ++j) {
+          mbar_wait(&k_full[j], box_uses[j] & 1);
+          mbar_wait(&v_full[j], box_uses[j] & 1);
           mbar_arrive(&kv_free[j]);
           ++box_uses[j];
         }
@@ -309,6 +319,13 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const AttnTcParam
       for (int k = 0; k < my_tiles; ++k, ++kt) {
         for (int j = 0; j < it.n_chunks; ++j, ++c) {
           const bool next_in_tile = j + 1 < it.n_chunks;
+          if (s_issued == c) {
+            // S of THIS chunk is still to be issued: the very first chunk of the CTA, or the cursor had passed items without
+            // a tile for this group — their K / V boxes had to be released (above, in item order) before blocking on this
+            // item's loads, because the producer refills a box only after both groups' releases of its previous item
+            if (c > 0) mbar_wait(&gb[S_FREE], (c - 1) & 1);
+            issue_s();
+          }
           if (next_in_tile) {
             mbar_wait(&gb[S_FREE], c & 1);
             issue_s();
@@ -325,7 +342,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const AttnTcParam
           umma_commit(&gb[PV_DONE]);
           if (k == my_tiles - 1) umma_commit(&kv_free[j]);  // this group's last use of K_j / V_j in the item
           PLB_TRACE(2, c);
-          if (!next_in_tile && s_item < n_items) {  // next tile (possibly of the next item): its Q arrives after this tile's last S
+          if (!next_in_tile && s_item < n_items && !s_skipped) {  // next tile (possibly of the next item): its Q arrives after this tile's last S
             mbar_wait(&gb[S_FREE], c & 1);
             issue_s();
           }

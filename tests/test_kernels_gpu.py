@@ -345,6 +345,50 @@ def test_attention_tc_packed_layout(dev, lens):
         assert rel(dqkv[:, sl].float(), qf.grad[:, sl]) < 2e-2, name
 
 
+@pytest.mark.parametrize("seed", [0, 1])
+def test_attention_tc_many_items_per_cta_variable_lengths(dev, seed):
+    """The forward kernel is persistent (one CTA per SM walks several (sequence, head) items): more items than SMs with
+    lengths that give the second softmax group NO tile in runs of consecutive items (<= 128 rows), one, or two tiles.
+    Regression for the run-ahead of a tile-less group (round 2: deadlock -> trap on BASELINE configs[3] batches)."""
+    nh = 6
+    H = nh * 64
+    g = torch.Generator().manual_seed(seed)
+    short = torch.randint(1, 129, (40,), generator=g)
+    mixed = torch.randint(1, 513, (32,), generator=g)
+    lens = torch.cat([short, mixed])[torch.randperm(72, generator=g)].tolist()   # 72 x 6 = 432 items on 148 CTAs
+    starts = [0]
+    for n in lens[:-1]:
+        starts.append(starts[-1] + n)
+    T, B = sum(lens), len(lens)
+    qkv = (torch.randn(T, 3 * H, generator=g) * 1.5).to(dev).to(BF)
+    lens_t = torch.tensor(lens, device=dev, dtype=torch.int32)
+    seq_start = torch.tensor(starts, device=dev, dtype=torch.int32)
+    ctx = torch.full((T, H), float("nan"), device=dev, dtype=BF)
+    lse = torch.zeros(nh, T, device=dev)
+    for _ in range(3):   # the barrier phases of a persistent CTA depend on timing: repeat
+        call("plb_attn_fwd_tc", ptr(qkv), 3 * H, ptr(seq_start), ptr(lens_t), ptr(lens_t), B, nh, 64, max(lens), T, ptr(ctx), H,
+             ptr(lse), S())
+        torch.cuda.synchronize()
+    qf = qkv.float().requires_grad_(True)
+    outs = []
+    for b0, n in zip(starts, lens):
+        q, k, v = [t.view(n, nh, 64).transpose(0, 1) for t in qf[b0:b0 + n].split(H, dim=1)]
+        outs.append((torch.softmax(q @ k.transpose(-1, -2) / 8.0, dim=-1) @ v).transpose(0, 1).reshape(n, H))
+    ref = torch.cat(outs)
+    assert torch.isfinite(ctx.float()).all()
+    worst = max(rel(ctx[b0:b0 + n].float(), ref[b0:b0 + n]) for b0, n in zip(starts, lens))
+    assert worst < 1e-2, worst
+    dctx = torch.randn(T, H, generator=g).to(dev).to(BF)
+    ref.backward(dctx.float())
+    dqkv = torch.full((T, 3 * H), float("nan"), device=dev, dtype=BF)
+    delta = torch.zeros(nh, T, device=dev)
+    call("plb_attn_bwd_tc", ptr(qkv), 3 * H, ptr(seq_start), ptr(lens_t), ptr(lens_t), B, nh, 64, max(lens), T, ptr(ctx),
+         ptr(dctx), H, ptr(lse), ptr(delta), ptr(dqkv), 3 * H, 0, S())
+    assert torch.isfinite(dqkv.float()).all()
+    for name, sl in (("dq", slice(0, H)), ("dk", slice(H, 2 * H)), ("dv", slice(2 * H, 3 * H))):
+        assert rel(dqkv[:, sl].float(), qf.grad[:, sl]) < 2e-2, name
+
+
 # ------------------------------------------------------------------------------------------ masked-row loss path
 def test_gather_scatter_bit_exact(dev):
     T, H, M = 5000, 768, 700
