@@ -516,10 +516,13 @@ def run_b200(args):
         return
 
     # ---------------- N = 1 extras: sub-records, library bar (+ loss check), CPU baseline ----------------
-    del feed, resident, opt, model, eng, stream, loader   # frees ~30 GB and stops the input workers
+    import gc
+    del feed, resident, opt, model, eng, enc, sync, stream, loader   # frees ~30 GB and stops the input workers
+    gc.collect()                                                      # encoder <-> owner model reference cycle (fuse_albert)
     torch.cuda.empty_cache()
     if not args.no_sub_records:
         line["sub_records"] = sub_records(dev, max(4, min(args.steps, 8)))
+        gc.collect()
         torch.cuda.empty_cache()
     ok = True
     if not args.no_library:
