@@ -145,11 +145,11 @@ __global__ void gemm_check_kernel(int op, int epi, int M, int N, int K, const __
   if (bias) acc += bias[n];
   __nv_bfloat16* c = static_cast<__nv_bfloat16*>(C);
   if (epi == PLB_EPI_RESIDUAL) acc += __bfloat162float(aux_in[(size_t)m * ld_in + n]);
-  if (epi == PLB_EPI_GELU_BWD) acc *= gelu_new_grad(__bfloat162float(aux_in[(size_t)m * ld_in + n]));
+  if (epi == PLB_EPI_GELU_BWD) acc *= __bfloat162float(aux_in[(size_t)m * ld_in + n]);
   if (epi == PLB_EPI_GELU) {
-    __nv_bfloat16 u = __float2bfloat16(acc);
-    aux_out[(size_t)m * ld_out + n] = u;
-    acc = gelu_new_fwd(__bfloat162float(u));
+    const float u = __bfloat162float(__float2bfloat16(acc));
+    aux_out[(size_t)m * ld_out + n] = __float2bfloat16(gelu_new_grad(u));
+    acc = gelu_new_fwd(u);
   }
   c[(size_t)m * ldc + n] = __float2bfloat16(acc);
 }

@@ -399,6 +399,19 @@ __device__ __forceinline__ f32x2 gelu_new_grad_x2(f32x2 u) {
   return f2_fma(f2_mul(t, t), nw, base);
 }
 
+// gelu_new and its derivative on a pair from ONE tanh: g = hu (1 + t), g' = t^2 (-w) + (0.5 + 0.5 t + w) with hu = 0.5 u,
+// w = u (0.5 c + 1.5 c k u^2) — 12 packed ops + 2 MUFU (the FFN1 epilogue saves g' for the backward pass instead of u)
+__device__ __forceinline__ void gelu_new_fwd_grad_x2(f32x2 u, f32x2& g, f32x2& gp) {
+  const float c = 0.7978845608028654f, k = 0.044715f;
+  const f32x2 u2 = f2_mul(u, u);
+  const f32x2 t = f2_tanh(f2_mul(u, f2_fma(u2, f2_splat(c * k), f2_splat(c))));
+  const f32x2 hu = f2_mul(u, f2_splat(0.5f));
+  g = f2_fma(hu, t, hu);
+  const f32x2 nw = f2_mul(u, f2_fma(u2, f2_splat(-1.5f * c * k), f2_splat(-0.5f * c)));
+  const f32x2 r = f2_fma(t, f2_splat(0.5f), f2_splat(0.5f));
+  gp = f2_fma(f2_mul(t, t), nw, f2_fma(nw, f2_splat(-1.0f), r));
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -449,20 +449,21 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CU
                 for (int i = 0; i < 4; ++i) {
                   const f32x2 x = f2_from_bf16x2(aw[i]);
                   if (kEpi == kResidual) f[i] = f2_add(f[i], x);
-                  else f[i] = f2_mul(f[i], gelu_new_grad_x2(x));  // kGeluBwd: acc * gelu'(u)
+                  else f[i] = f2_mul(f[i], x);  // kGeluBwd: acc * gelu'(u), the derivative saved by the forward epilogue
                 }
               }
             }
             if (kDual) {
-              // pre-activation u goes to the second buffer of the pair, gelu(u) to the first
-              uint4 pu;
-              pu.x = f2_to_bf16x2(f[0]); pu.y = f2_to_bf16x2(f[1]);
-              pu.z = f2_to_bf16x2(f[2]); pu.w = f2_to_bf16x2(f[3]);
-              sts128(my_row + EPI_BUF_BYTES + ((j ^ (row & 7)) << 4), pu);
-              // gelu is evaluated on the bf16-rounded u so that forward and backward see the same value
-              const uint32_t uw[4] = {pu.x, pu.y, pu.z, pu.w};
+              // gelu'(u) goes to the second buffer of the pair (all the backward pass needs of u: its DGRAD epilogue becomes
+              // one multiply, and this epilogue is bound by its two stores, not by its math), gelu(u) to the first.  Both are
+              // evaluated on the bf16-rounded u, the value a stored pre-activation would have had.
+              f32x2 gp[4];
 #pragma unroll
-              for (int i = 0; i < 4; ++i) f[i] = gelu_new_fwd_x2(f2_from_bf16x2(uw[i]));
+              for (int i = 0; i < 4; ++i) gelu_new_fwd_grad_x2(f2_from_bf16x2(f2_to_bf16x2(f[i])), f[i], gp[i]);
+              uint4 pu;
+              pu.x = f2_to_bf16x2(gp[0]); pu.y = f2_to_bf16x2(gp[1]);
+              pu.z = f2_to_bf16x2(gp[2]); pu.w = f2_to_bf16x2(gp[3]);
+              sts128(my_row + EPI_BUF_BYTES + ((j ^ (row & 7)) << 4), pu);
             }
             uint4 o;
             o.x = f2_to_bf16x2(f[0]); o.y = f2_to_bf16x2(f[1]);

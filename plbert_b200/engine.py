@@ -215,7 +215,7 @@ class Engine:
             self.acts = []
             for _ in range(n_sets):
                 self.acts.append(dict(qkv=mk(3 * H), ctx=mk(H), lse=torch.empty((c.num_attention_heads, cap), dtype=torch.float32, device=dev),
-                                      z1=mk(H), st1=mk(2, torch.float32), a=mk(H), u=mk(I), g=mk(I), z2=mk(H),
+                                      z1=mk(H), st1=mk(2, torch.float32), a=mk(H), dg=mk(I), g=mk(I), z2=mk(H),
                                       st2=mk(2, torch.float32), y=mk(H)))
             if train:
                 # backward scratch, reused by every layer
@@ -278,7 +278,7 @@ class Engine:
             call("plb_ln_fwd", ptr(A["z1"]), T, H, self.pp[att + "LayerNorm.weight"], self.pp[att + "LayerNorm.bias"],
                  c.layer_norm_eps, ptr(A["a"]), ptr(A["st1"]), s)
             self._gemm(GEMM_FWD, EPI_GELU, T, I, H, A["a"], H, self.wp[_LAYER + "ffn.weight"], H, A["g"], I,
-                       bias=self.pp[_LAYER + "ffn.bias"], aux_out=A["u"], ld_out=I)
+                       bias=self.pp[_LAYER + "ffn.bias"], aux_out=A["dg"], ld_out=I)   # g = gelu(u), dg = gelu'(u)
             self._gemm(GEMM_FWD, EPI_RESIDUAL, T, H, I, A["g"], I, self.wp[_LAYER + "ffn_output.weight"], I, A["z2"], H,
                        bias=self.pp[_LAYER + "ffn_output.bias"], aux_in=A["a"], ld_in=H)
             call("plb_ln_fwd", ptr(A["z2"]), T, H, self.pp[_LAYER + "full_layer_layer_norm.weight"],
@@ -458,7 +458,7 @@ class Engine:
                  self.gp[_LAYER + "full_layer_layer_norm.bias"], self.gp[_LAYER + "ffn_output.bias"], s)
             self._gemm(GEMM_WGRAD, EPI_NONE, H, I, T, self.d_z, H, A["g"], I, self.gp[_LAYER + "ffn_output.weight"], I)
             self._gemm(GEMM_DGRAD, EPI_GELU_BWD, T, I, H, self.d_z, H, self.wp[_LAYER + "ffn_output.weight"], I, self.d_u, I,
-                       aux_in=A["u"], ld_in=I)
+                       aux_in=A["dg"], ld_in=I)   # d_u = (d_z W2) o gelu'(u)
             call("plb_colsum", ptr(self.d_u), I, T, I, self.gp[_LAYER + "ffn.bias"], s)
             self._gemm(GEMM_WGRAD, EPI_NONE, I, H, T, self.d_u, I, A["a"], H, self.gp[_LAYER + "ffn.weight"], H)
             self._gemm(GEMM_DGRAD, EPI_RESIDUAL, T, H, I, self.d_u, I, self.wp[_LAYER + "ffn.weight"], H, self.d_a, H,

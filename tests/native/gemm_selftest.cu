@@ -115,7 +115,7 @@ static void run_case(int op, int epi, int M, int N, int K, bool with_bias) {
   if (e != cudaSuccess) { printf("%s: execution failed: %s\n", name, cudaGetErrorString(e)); exit(3); }
   const float atol = 0.02f * sqrtf((float)K) / 3.f + 0.02f;
   compare(name, C1.host(), C2.host(), M, N, ldn, atol, 0.02f);
-  if (epi == PLB_EPI_GELU) compare("    (pre-activation output)", U1.host(), U2.host(), M, N, ldn, atol, 0.02f);
+  if (epi == PLB_EPI_GELU) compare("    (saved gelu derivative)", U1.host(), U2.host(), M, N, ldn, atol, 0.02f);
   if (bias) cudaFree(bias);
 }
 
