@@ -145,6 +145,17 @@ int plb_attn_bwd_tc(const void* qkv, int ld_qkv, const int32_t* seq_start, const
                     const void* ctx, const void* dctx, int ld_ctx, const float* lse2, float* delta,
                     void* dqkv, int ld_dqkv, float* dbias_qkv_accum, plb_stream_t stream);
 
+/* Backward as ONE kernel (attn_bwd_fused.cu): every [128 keys x 128 queries] block is visited once — S^T, dP^T and the
+ * exponentials are computed once instead of once per backward kernel; dK / dV accumulate in tensor memory, the per-key-tile
+ * partials of dQ are summed in `workspace` (fp32, L2-resident, plb_attn_bwd_fused_workspace_bytes(B, heads) bytes,
+ * caller-owned, contents irrelevant before and after the call).  Same arguments and results as plb_attn_bwd_tc. */
+int plb_attn_bwd_fused_workspace_bytes(int B, int heads);
+int plb_attn_bwd_fused(const void* qkv, int ld_qkv, const int32_t* seq_start, const int32_t* q_len,
+                       const int32_t* kv_len, int B, int heads, int head_dim, int max_q_len, int total_rows,
+                       const void* ctx, const void* dctx, int ld_ctx, const float* lse2, float* delta,
+                       void* dqkv, int ld_dqkv, float* dbias_qkv_accum, void* workspace, long long workspace_bytes,
+                       plb_stream_t stream);
+
 /* ---- a8: masked-row loss ----------------------------------------------------------------------------
  * R/train.py:107-131 calculate_phoneme_loss.  The host flattens masked_indices into rows[M] (= b*L + i, in the
  * reference's order) and weights[M] = 1 / (count * n_b); only those rows go through the heads.

@@ -1164,6 +1164,16 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv128, const __gr
 }
 
 }  // namespace
+
+// delta = rowsum(dO o O) per (head, row) for callers that did not fuse it into the O-projection DGRAD (shared with
+// attn_bwd_fused.cu)
+int launch_attn_delta(const void* dctx, const void* ctx, int ld_ctx, int total_rows, int heads, float* delta,
+                      cudaStream_t stream) {
+  const int dgrid = (total_rows + 7) / 8 < sm_count() * 8 ? (total_rows + 7) / 8 : sm_count() * 8;
+  attn_delta_kernel<<<dgrid, 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(dctx), static_cast<const __nv_bfloat16*>(ctx),
+                                               ld_ctx, total_rows, heads, total_rows, delta);
+  return check_launch("plb_attn_bwd(delta)");
+}
 }  // namespace plb
 
 using namespace plb;
@@ -1199,10 +1209,7 @@ extern "C" int plb_attn_bwd_tc(const void* qkv, int ld_qkv, const int32_t* seq_s
                  1.f / sqrtf((float)head_dim)};
   int rc = PLB_OK;
   if (ctx != nullptr) {  // otherwise delta was produced by the O-projection DGRAD (PLB_EPI_ROWDOT)
-    const int dgrid = (total_rows + 7) / 8 < sm_count() * 8 ? (total_rows + 7) / 8 : sm_count() * 8;
-    attn_delta_kernel<<<dgrid, 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(dctx), static_cast<const __nv_bfloat16*>(ctx),
-                                                 ld_ctx, total_rows, heads, total_rows, delta);
-    rc = check_launch("plb_attn_bwd_tc(delta)");
+    rc = launch_attn_delta(dctx, ctx, ld_ctx, total_rows, heads, delta, stream);
     if (rc) return rc;
   }
   attn_bwd_dq_tc_kernel<<<B * heads, BWD_THREADS, DqSmem::kAlloc, stream>>>(tm_qkv128, tm_dctx128, p, lse2, delta,

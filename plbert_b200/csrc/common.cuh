@@ -36,6 +36,10 @@ bool tensor_map_bf16(CUtensorMap* out, const void* base, uint64_t rows, uint64_t
 
 int sm_count();
 
+// attn_tc.cu: delta[h, row] = sum_d dO[row, h*64 + d] * O[row, h*64 + d]  (enqueue only)
+int launch_attn_delta(const void* dctx, const void* ctx, int ld_ctx, int total_rows, int heads, float* delta,
+                      cudaStream_t stream);
+
 // ----------------------------------------------------------------------------------------------
 // Device side
 // ----------------------------------------------------------------------------------------------
@@ -89,6 +93,16 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
   const long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > (1ll << 31)) __trap();
+  }
+}
+
+// Spinning wait (test_wait never suspends the thread): for single-thread roles on a latency-critical hand-off, where the
+// wake-up of a thread suspended inside try_wait was measured at 0.5 - 1.5 k clk (profiles/r2_attn_bwd_fused_timeline.txt).
+__device__ __forceinline__ void mbar_wait_spin(uint64_t* bar, uint32_t parity) {
+  if (mbar_test(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_test(bar, parity)) {
     if (clock64() - t0 > (1ll << 31)) __trap();
   }
 }
@@ -247,6 +261,16 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&v)[32])
       : "r"(taddr)
       : "memory");
 }
+// 32 lanes x 16 consecutive fp32 columns
+__device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const uint32_t (&v)[32]) {
   asm volatile(
@@ -305,6 +329,13 @@ __device__ __forceinline__ void sts128(uint32_t saddr, const uint4& v) {
 __device__ __forceinline__ uint4 lds128(uint32_t saddr) {
   uint4 v;
   asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(saddr) : "memory");
+  return v;
+}
+
+// shared data that other warps rewrite between uses (memory clobber: never merged across barriers, may still be scheduled)
+__device__ __forceinline__ float4 lds128_f4(uint32_t saddr) {
+  float4 v;
+  asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr) : "memory");
   return v;
 }
 

@@ -240,6 +240,14 @@ class Engine:
         self.row_loss = torch.empty(cap, dtype=torch.float32, device=dev)
         self._cap_M = cap
 
+    def _attn_workspace(self, B: int) -> torch.Tensor:
+        """fp32 scratch of the attention backward (per-CTA partial sums of dQ over the key tiles; L2-resident, 19 MB at most)."""
+        need = _abi.load().plb_attn_bwd_fused_workspace_bytes(B, self.cfg.num_attention_heads) // 4
+        ws = getattr(self, "_attn_ws", None)
+        if ws is None or ws.numel() < need:
+            ws = self._attn_ws = torch.empty(need, dtype=torch.float32, device=self.device)
+        return ws
+
     # ------------------------------------------------------------------ kernels
     def _gemm(self, op, epi, M, N, K, A, lda, B, ldb, C, ldc, bias=None, aux_in=None, ld_in=0, aux_out=None, ld_out=0):
         call("plb_gemm_bf16", op, epi, M, N, K, ptr(A), lda, ptr(B), ldb, ptr(C), ldc, ptr(bias), ptr(aux_in), ld_in,
@@ -449,6 +457,7 @@ class Engine:
         wqkv = self.wp[att + "query.weight"]                                        # q|k|v adjacent: [3H, H]
         g_wqkv, g_bqkv = self.gp[att + "query.weight"], self.gp[att + "query.bias"]
         delta_flat = self.delta.view(-1)   # indexed [head * T + row] by the kernels
+        attn_ws = self._attn_workspace(b.B)
         for l in reversed(range(c.num_hidden_layers)):
             A = self.acts[l]
             x_in = self.acts[l - 1]["y"] if l > 0 else self.x0
@@ -472,12 +481,14 @@ class Engine:
             delta_flat[:nh * T].zero_()
             self._gemm(GEMM_DGRAD, EPI_ROWDOT, T, H, H, self.d_z, H, self.wp[att + "dense.weight"], H, self.d_ctx, H,
                        aux_in=A["ctx"], ld_in=H, aux_out=self.delta, ld_out=T)
-            call("plb_attn_bwd_tc", ptr(A["qkv"]), 3 * H, ptr(b.seq_start), ptr(b.q_len), ptr(b.kv_len), b.B, nh, H // nh, b.L,
+            # one kernel: S^T / dP^T and the exponentials are computed once for dQ, dK and dV (attn_bwd_fused.cu).  ctx = NULL:
+            # delta is given; the same kernel accumulates the QKV bias gradient (column sums of dqkv)
+            call("plb_attn_bwd_fused", ptr(A["qkv"]), 3 * H, ptr(b.seq_start), ptr(b.q_len), ptr(b.kv_len), b.B, nh, H // nh, b.L,
                  T, 0, ptr(self.d_ctx), H, ptr(A["lse"]), ptr(self.delta), ptr(self.d_qkv), 3 * H,
-                 ptr(g_bqkv), s)  # ctx = NULL: delta is given; also accumulates the QKV bias gradient (column sums of dqkv)
+                 ptr(g_bqkv), ptr(attn_ws), attn_ws.numel() * 4, s)
             self._gemm(GEMM_WGRAD, EPI_NONE, 3 * H, H, T, self.d_qkv, 3 * H, x_in, H, g_wqkv, H)
             self._gemm(GEMM_DGRAD, EPI_RESIDUAL, T, H, 3 * H, self.d_qkv, 3 * H, wqkv, H, dy, H, aux_in=self.d_z, ld_in=H)
-            self.launches += 5  # 2 ln_bwd, 1 colsum, attention bwd = 2 kernels (dQ, dK/dV); the delta memset is torch's
+            self.launches += 4  # 2 ln_bwd, 1 colsum, 1 attention backward; the delta memset is torch's
 
         # ---- embedding side -----------------------------------------------------------------------
         mp = "encoder.encoder.embedding_hidden_mapping_in."

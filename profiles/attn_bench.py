@@ -48,6 +48,13 @@ def main():
         timeit(lambda: call(n, ptr(qkv), 3 * H, ptr(seq_start), ptr(lens), ptr(lens), B, nh, 64, L, T, ptr(ctx), ptr(dctx), H,
                             ptr(lse), ptr(delta), ptr(dqkv), 3 * H, *extra, S), 2.5 * fwd_flops, n)
 
+    if hasattr(load(), "plb_attn_bwd_fused"):
+        nbytes = load().plb_attn_bwd_fused_workspace_bytes(B, nh)
+        ws = torch.empty(nbytes // 4, device=dev)
+        for use_ctx in (ptr(ctx), 0):   # 0: delta given (the step's configuration: the O-projection DGRAD produced it)
+            timeit(lambda: call("plb_attn_bwd_fused", ptr(qkv), 3 * H, ptr(seq_start), ptr(lens), ptr(lens), B, nh, 64, L, T,
+                                use_ctx, ptr(dctx), H, ptr(lse), ptr(delta), ptr(dqkv), 3 * H, ptr(dbias), ptr(ws), nbytes, S),
+                   2.5 * fwd_flops, "plb_attn_bwd_fused" + ("" if use_ctx else " (delta given)"))
 
     # per-kernel durations of one backward call (CUPTI)
     from torch.profiler import ProfilerActivity, profile

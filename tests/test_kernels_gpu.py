@@ -260,14 +260,30 @@ def _attn_ref(qkv, B, L, nh, lens):
     return (p @ v).transpose(1, 2).reshape(T, H), torch.logsumexp(s, dim=-1)
 
 
+def _attn_bwd(name, *args):
+    """plb_attn_bwd_tc (two kernels) or plb_attn_bwd_fused (one kernel + caller-owned fp32 workspace); `args` are the common
+    arguments up to dbias, in ABI order (ints / device pointers)."""
+    if name == "plb_attn_bwd_fused":
+        B, nh = args[5], args[6]
+        nbytes = _abi.load().plb_attn_bwd_fused_workspace_bytes(B, nh)
+        assert nbytes > 0
+        ws = torch.full((nbytes // 4,), float("nan"), device="cuda")   # contents are irrelevant on entry
+        call(name, *args, ptr(ws), nbytes, S())
+        return ws
+    call(name, *args, S())
+
+
+BWD_IMPLS = ["plb_attn_bwd_tc", "plb_attn_bwd_fused"]
+
+
 @pytest.mark.parametrize("B,L,nh,lens", [(2, 64, 2, [64, 64]), (3, 200, 2, [200, 77, 1]), (2, 512, 12, [512, 300]),
                                          (4, 130, 3, [130, 129, 65, 64]),
                                          # tile / chunk parities of the two-group schedules: 1, 2, 3 query tiles, odd chunk
                                          # counts, fewer key tiles than query tiles, a single valid key
                                          (2, 128, 1, [128, 5]), (2, 256, 2, [256, 130]), (3, 384, 2, [384, 100, 257]),
                                          (4, 512, 2, [1, 128, 129, 511]), (3, 320, 1, [320, 64, 200]), (2, 448, 1, [448, 449 - 64])])
-@pytest.mark.parametrize("fwd,bwd", [("plb_attn_fwd_tc", "plb_attn_bwd_tc")])
-def test_attention_fwd_bwd(dev, B, L, nh, lens, fwd, bwd):
+@pytest.mark.parametrize("bwd", BWD_IMPLS)
+def test_attention_fwd_bwd(dev, B, L, nh, lens, bwd, fwd="plb_attn_fwd_tc"):
     H, T = nh * 64, B * L
     qkv = torch.randn(T, 3 * H, device=dev).to(BF)
     lens_t = torch.tensor(lens, device=dev, dtype=torch.int32)
@@ -290,21 +306,17 @@ def test_attention_fwd_bwd(dev, B, L, nh, lens, fwd, bwd):
     dqkv = torch.full((T, 3 * H), float("nan"), device=dev, dtype=BF)
     delta = torch.zeros(nh, T, device=dev)
     dbias = torch.ones(3 * H, device=dev)
-    if bwd == "plb_attn_bwd_tc":
-        call(bwd, ptr(qkv), 3 * H, ptr(seq_start), ptr(q_len), ptr(lens_t), B, nh, 64, L, T, ptr(ctx), ptr(dctx), H,
-             ptr(lse), ptr(delta), ptr(dqkv), 3 * H, ptr(dbias), S())
-        # fused bias gradient = column sums of the stored (rounded) dqkv, accumulated on top of the initial ones
-        want = dqkv.float().sum(0)
-        assert (dbias - 1 - want).abs().max() <= 1e-3 * want.abs().max() + 1e-4
-        # ctx == NULL: delta is an input (the O-projection DGRAD's ROWDOT epilogue produced it) -> identical gradients
-        d_in = (dctx.float() * ctx.float()).view(T, nh, 64).sum(-1).T.contiguous()
-        dqkv2 = torch.full((T, 3 * H), float("nan"), device=dev, dtype=BF)
-        call(bwd, ptr(qkv), 3 * H, ptr(seq_start), ptr(q_len), ptr(lens_t), B, nh, 64, L, T, 0, ptr(dctx), H,
-             ptr(lse), ptr(d_in), ptr(dqkv2), 3 * H, 0, S())
-        assert rel(dqkv2.float(), dqkv.float()) < 2e-3
-    else:
-        call(bwd, ptr(qkv), 3 * H, ptr(seq_start), ptr(q_len), ptr(lens_t), B, nh, 64, L, T, ptr(ctx), ptr(dctx), H,
-             ptr(lse), ptr(delta), ptr(dqkv), 3 * H, S())
+    _attn_bwd(bwd, ptr(qkv), 3 * H, ptr(seq_start), ptr(q_len), ptr(lens_t), B, nh, 64, L, T, ptr(ctx), ptr(dctx), H,
+              ptr(lse), ptr(delta), ptr(dqkv), 3 * H, ptr(dbias))
+    # fused bias gradient = column sums of the stored (rounded) dqkv, accumulated on top of the initial ones
+    want = dqkv.float().sum(0)
+    assert (dbias - 1 - want).abs().max() <= 1e-3 * want.abs().max() + 1e-4
+    # ctx == NULL: delta is an input (the O-projection DGRAD's ROWDOT epilogue produced it) -> identical gradients
+    d_in = (dctx.float() * ctx.float()).view(T, nh, 64).sum(-1).T.contiguous()
+    dqkv2 = torch.full((T, 3 * H), float("nan"), device=dev, dtype=BF)
+    _attn_bwd(bwd, ptr(qkv), 3 * H, ptr(seq_start), ptr(q_len), ptr(lens_t), B, nh, 64, L, T, 0, ptr(dctx), H,
+              ptr(lse), ptr(d_in), ptr(dqkv2), 3 * H, 0)
+    assert rel(dqkv2.float(), dqkv.float()) < 2e-3
     assert torch.isfinite(dqkv.float()).all()
     for name, sl in (("dq", slice(0, H)), ("dk", slice(H, 2 * H)), ("dv", slice(2 * H, 3 * H))):
         assert rel(dqkv[:, sl].float(), qf.grad[:, sl]) < 2e-2, name
@@ -312,8 +324,9 @@ def test_attention_fwd_bwd(dev, B, L, nh, lens, fwd, bwd):
     assert not dqkv[~valid][:, H:].any()
 
 
+@pytest.mark.parametrize("bwd", BWD_IMPLS)
 @pytest.mark.parametrize("lens", [[512, 300, 1, 77], [65, 64, 130, 129, 128, 127], [200]])
-def test_attention_tc_packed_layout(dev, lens):
+def test_attention_tc_packed_layout(dev, lens, bwd):
     """Packed (cu_seqlens) layout through the same ABI: q_len == kv_len == the sequence length, sequences back to back.
     Rows past a sequence's end belong to its neighbour and must be neither read as keys nor written."""
     nh = 2
@@ -340,15 +353,16 @@ def test_attention_tc_packed_layout(dev, lens):
     ref.backward(dctx.float())
     dqkv = torch.full((T, 3 * H), float("nan"), device=dev, dtype=BF)
     delta = torch.zeros(nh, T, device=dev)
-    call("plb_attn_bwd_tc", ptr(qkv), 3 * H, ptr(seq_start), ptr(lens_t), ptr(lens_t), B, nh, 64, max(lens), T, ptr(ctx),
-         ptr(dctx), H, ptr(lse), ptr(delta), ptr(dqkv), 3 * H, 0, S())
+    _attn_bwd(bwd, ptr(qkv), 3 * H, ptr(seq_start), ptr(lens_t), ptr(lens_t), B, nh, 64, max(lens), T, ptr(ctx),
+              ptr(dctx), H, ptr(lse), ptr(delta), ptr(dqkv), 3 * H, 0)
     assert torch.isfinite(dqkv.float()).all()
     for name, sl in (("dq", slice(0, H)), ("dk", slice(H, 2 * H)), ("dv", slice(2 * H, 3 * H))):
         assert rel(dqkv[:, sl].float(), qf.grad[:, sl]) < 2e-2, name
 
 
+@pytest.mark.parametrize("bwd", BWD_IMPLS)
 @pytest.mark.parametrize("seed", [0, 1])
-def test_attention_tc_many_items_per_cta_variable_lengths(dev, seed):
+def test_attention_tc_many_items_per_cta_variable_lengths(dev, seed, bwd):
     """The forward kernel is persistent (one CTA per SM walks several (sequence, head) items): more items than SMs with
     lengths that give the second softmax group NO tile in runs of consecutive items (<= 128 rows), one, or two tiles.
     Regression for the run-ahead of a tile-less group (round 2: deadlock -> trap on BASELINE configs[3] batches)."""
@@ -384,11 +398,19 @@ def test_attention_tc_many_items_per_cta_variable_lengths(dev, seed):
     ref.backward(dctx.float())
     dqkv = torch.full((T, 3 * H), float("nan"), device=dev, dtype=BF)
     delta = torch.zeros(nh, T, device=dev)
-    call("plb_attn_bwd_tc", ptr(qkv), 3 * H, ptr(seq_start), ptr(lens_t), ptr(lens_t), B, nh, 64, max(lens), T, ptr(ctx),
-         ptr(dctx), H, ptr(lse), ptr(delta), ptr(dqkv), 3 * H, 0, S())
-    assert torch.isfinite(dqkv.float()).all()
-    for name, sl in (("dq", slice(0, H)), ("dk", slice(H, 2 * H)), ("dv", slice(2 * H, 3 * H))):
-        assert rel(dqkv[:, sl].float(), qf.grad[:, sl]) < 2e-2, name
+    dbias = torch.zeros(3 * H, device=dev)
+    for rep in range(3):   # (persistent kernel: the barrier phases depend on timing, and the workspace starts as NaN)
+        dqkv.fill_(float("nan"))
+        dbias.zero_()
+        _attn_bwd(bwd, ptr(qkv), 3 * H, ptr(seq_start), ptr(lens_t), ptr(lens_t), B, nh, 64, max(lens), T, ptr(ctx),
+                  ptr(dctx), H, ptr(lse), ptr(delta), ptr(dqkv), 3 * H, ptr(dbias))
+        torch.cuda.synchronize()
+        assert torch.isfinite(dqkv.float()).all()
+        worst = {name: max(rel(dqkv[b0:b0 + n, sl].float(), qf.grad[b0:b0 + n, sl]) for b0, n in zip(starts, lens))
+                 for name, sl in (("dq", slice(0, H)), ("dk", slice(H, 2 * H)), ("dv", slice(2 * H, 3 * H)))}
+        assert max(worst.values()) < 3e-2, (rep, worst)
+        want = dqkv.float().sum(0)
+        assert (dbias - want).abs().max() <= 1e-3 * want.abs().max() + 1e-3
 
 
 # ------------------------------------------------------------------------------------------ masked-row loss path
