@@ -7,23 +7,30 @@
 // visited once (10 units, 1 L^2 exp):
 //     S^T  = K_t Q_j^T          tcgen05.mma M128 N128 K64  (smem x smem)      -> TMEM [  0,128)
 //     dP^T = V_t dO_j^T         tcgen05.mma M128 N128 K64  (smem x smem)      -> TMEM [128,256)
-//     P^T, dS^T                 8 softmax warps: thread = (key row, 64 query columns); one exp2 per element
+//     P^T, dS^T                 8 softmax warps (32 key rows x 64 query columns each, matrix-fragment register layout);
+//                               one exp2 per element
 //        P^T  -> TMEM [256,320) packed bf16 (A operand of the dV MMA)
-//        dS^T -> shared memory [128 keys x 128 q] bf16, 128-byte swizzled (read by two MMAs under two views)
-//     dV  += P^T  dO_j          M128 N64 K128, A from TMEM, B = dO_j MN-major            -> TMEM [384,448)
-//     dK  += dS^T Q_j           M128 N64 K128, A = dS^T K-major, B = Q_j MN-major        -> TMEM [320,384)
+//        dS^T -> shared memory [128 keys x 128 q] bf16, 128-byte swizzled, DOUBLE-buffered (read by two MMAs under two views)
+//     dV  += P^T  dO_j          M128 N64 K128, A from TMEM, B = dO_j MN-major            -> TMEM [384,448)   (issued first)
 //     dQ_j = dS_j K_t           M128 N64 K128, A = dS^T read MN-major (i.e. transposed), B = K_t MN-major -> TMEM [448,512)
+//     dK  += dS^T Q_j           M128 N64 K128, A = dS^T K-major, B = Q_j MN-major        -> TMEM [320,384)
 // dK / dV accumulate in tensor memory over the query tiles of a key tile.  dQ_j gets one partial per KEY tile (<= 4): the
 // partials are summed in an fp32 scratch of the CTA (128 KB, L2-resident: store for the first tile, red.add for the middle
 // ones, read + add + convert for the last), because 512 queries x 64 fp32 accumulators do not fit beside S^T / dP^T.
 //
-// One persistent CTA per SM walks the (sequence, head) items; Q and dO of the item are resident (4 + 4 tiles of 16 KB),
-// K_t / V_t are double-buffered, so the loads of the next tile / item land under the current one.  16 warps:
-//   warp 0   TMA producer                      warp 1   MMA issuer of the S^T / dP^T stream
-//   warp 2   MMA issuer of dQ / dK / dV        warp 3   stages (-lse2, -delta) of the next query tile in shared memory
+// One persistent CTA per SM walks the (sequence, head) items.  Shared memory (224 KB of tiles): Q of the item resident
+// (4 x 16 KB), dO_j streamed per block through 3 slots, K_t double-buffered, V_t single (its only reader, the dP^T MMA, runs
+// early in a block), dS^T 2 x 32 KB.  16 warps:
+//   warp 0   TMA producer of Q / K / V         warp 1   MMA issuer A: the S^T / dP^T stream
+//   warp 2   MMA issuer B: dV / dQ / dK        warp 3   per-block stager: dO_j (TMA) and (-lse2, -delta) of the query tile
 //   warps 4..11   softmax (P^T, dS^T)          warps 12..15   epilogue (dQ partials, dK / dV tiles, bias column sums)
 // All roles walk the same block sequence n = 0, 1, ... (item-major, then key tile, then query tile); every mbarrier phase
 // is a function of n (or of the running key-tile / slot-use counters), so the pipeline keeps running across items.
+//
+// What bounds it (profiles/r2_attn_bwd_fused.md): not one pipe — tensor 28 %, MUFU 22 %, issue 36 %, and the shared-memory /
+// L1 data pipe, which carries the MMA operand reads (30 % of its wavefronts) AND every LDS / STS / global store of the
+// roles (47 %), at 77 %.  Hence the design rules of this file: no staging of outputs through shared memory, statistics
+// fetched in the fragment layout (a lane loads only its own column pairs), dO streamed instead of kept resident.
 #include "common.cuh"
 
 namespace plb {
@@ -407,15 +414,19 @@ attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_c
   } else if (warp < 12) {
     asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(FB_REGS_SOFTMAX));
     // ====================================== softmax warps: P^T and dS^T of every block ======================================
-    // Thread = (key row, 64 of the block's 128 query columns): quadrant = warp & 3 (the TMEM lanes a warp may touch),
-    // column half ch = (warp - 4) >> 2.  There is no cross-column reduction in the backward pass.  Packed fp32 math.
+    // A warp owns 32 key rows (its TMEM lane quadrant = warp & 3) x 64 of the block's 128 query columns (ch = (warp - 4) >> 2).
+    // S^T / dP^T are pulled out of tensor memory in the MATRIX-FRAGMENT shape (16x256b: thread t holds rows t/4 and t/4 + 8,
+    // column pairs 2(t%4) + 8r), not one row per thread: a lane then needs the (-lse2, -delta) of ITS column pairs only —
+    // 16 eight-byte loads per block instead of 32 sixteen-byte broadcasts at four shared-memory wavefronts each (the kernel is
+    // bound by the shared-memory / L1 data pipe, where those broadcasts were 21 % of all wavefronts).  P^T goes back to tensor
+    // memory with the matching 16x128b shape, dS^T to shared memory with stmatrix.  No cross-column reduction exists in the
+    // backward pass, so the layout is free.  Packed fp32 math.
     const int quad = warp & 3, ch = (warp - 4) >> 2;
-    const int row = quad * 32 + lane;
-    const uint32_t lane_addr = static_cast<uint32_t>(quad * 32) << 16;
-    const uint32_t tS = tmem_base + lane_addr + ch * 64, tDP = tS + 128;
-    const uint32_t tP = tmem_base + lane_addr + 256 + ch * 32;
-    const uint32_t sDS_row = smem_u32(smem + FbSmem::kDS) + ch * TILE16K + row * 128;   // the thread's 64 columns = one swizzled row
-    const uint32_t stat_addr = smem_u32(smem + FbSmem::kStat) + ch * 64 * 4;
+    const uint32_t t_quad = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
+    // stmatrix row address of this lane inside a dS^T sub-tile: matrix m = lane >> 3 -> (row block m & 1, 16-byte chunk m >> 1)
+    const int st_row = quad * 32 + ((lane >> 3) & 1) * 8 + (lane & 7);   // + 16 * half
+    const uint32_t sDS_lane = smem_u32(smem + FbSmem::kDS) + ch * TILE16K + st_row * 128;
+    const uint32_t stat_lane = smem_u32(smem + FbSmem::kStat) + (ch * 64 + 2 * (lane & 3)) * 4;
     const f32x2 sl2 = f2_splat(p.scale_log2);
     uint32_t n = 0;
     FbItem nxt = blockIdx.x < n_items ? fb_item(p, blockIdx.x) : FbItem{};
@@ -424,80 +435,95 @@ attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_c
       if (item + static_cast<int>(gridDim.x) < n_items) nxt = fb_item(p, item + gridDim.x);
       for (int t = 0; t < it.n_kt; ++t) {
         // key rows >= kv_len (last tile only): P = 0 and dS = 0.  Their S^T / dP^T rows are finite (rows of a neighbouring
-        // sequence or TMA zero fill), so the packed results are simply cleared.
+        // sequence or TMA zero fill), so the packed results are simply cleared.  Rows of this thread: r0 + {0, 8, 16, 24}.
         const bool partial = (t + 1) * 128 > it.nk;
-        const uint32_t keep = (t * 128 + row) < it.nk ? 0xffffffffu : 0u;
+        const int r0 = t * 128 + quad * 32 + (lane >> 2);
+        uint32_t keep[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) keep[i] = (r0 + 8 * i) < it.nk ? 0xffffffffu : 0u;
         for (int j = 0; j < it.n_qt; ++j, ++n) {
           const uint32_t b = n & 1;
           FB_WAIT_SOFTMAX(&stat_full[b], (n >> 1) & 1);
           FB_WAIT_SOFTMAX(&pipe[ST_FULL], n & 1);
           tc_fence_after();
           FB_TRACE(10, n);
-          uint32_t pkp[32], pkd[32];
+          // rounds: (32-column chunk c32, lane half h) = (0,0) (0,1) (1,0) (1,1); results pk[c32][h][8]: word 2r + e = repeat r
+          // (columns 8r + 2(t%4), +1 of the chunk), row +0 (e = 0) or +8 (e = 1) — the register order of 16x128b and stmatrix
+          uint32_t pkp[4][8], pkd[4][8];
           uint32_t sv[2][16], dv[2][16];
-          tmem_ld_32x16(tS, sv[0]);
-          tmem_ld_32x16(tDP, dv[0]);
+          tmem_ld_16x256b_x4(t_quad + ch * 64, sv[0]);
+          tmem_ld_16x256b_x4(t_quad + 128 + ch * 64, dv[0]);
+          f32x2 nl[4], nd[4];
 #pragma unroll
-          for (int r = 0; r < 4; ++r) {
-            tmem_ld_wait();   // round r has landed; round r+1 is loaded under this round's math
-            if (r < 3) {
-              tmem_ld_32x16(tS + (r + 1) * 16, sv[(r + 1) & 1]);
-              tmem_ld_32x16(tDP + (r + 1) * 16, dv[(r + 1) & 1]);
+          for (int rd = 0; rd < 4; ++rd) {
+            const int c32 = rd >> 1, h = rd & 1;
+            tmem_ld_wait();   // round rd has landed; round rd + 1 is loaded under this round's math
+            if (rd < 3) {
+              const uint32_t ta = t_quad + (static_cast<uint32_t>(((rd + 1) & 1) * 16) << 16) + ch * 64 + ((rd + 1) >> 1) * 32;
+              tmem_ld_16x256b_x4(ta, sv[(rd + 1) & 1]);
+              tmem_ld_16x256b_x4(ta + 128, dv[(rd + 1) & 1]);
             } else {
               tc_fence_before();
               __syncwarp();
               if (lane == 0) mbar_arrive(&pipe[ST_FREE]);   // S^T / dP^T of block n+1 may overwrite the buffers
               FB_TRACE(11, n);
             }
-            const uint32_t st = stat_addr + b * 1024 + r * 64;
-#ifdef FB_ABL_NOMATH
+            if (h == 0) {   // the statistics of the chunk's column pairs serve both lane halves
+              const uint32_t st = stat_lane + b * 1024 + c32 * 128;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              pkp[r * 8 + i] = sv[r & 1][2 * i] ^ sv[r & 1][2 * i + 1];
-              pkd[r * 8 + i] = dv[r & 1][2 * i] ^ dv[r & 1][2 * i + 1];
+              for (int r = 0; r < 4; ++r) {
+                const float2 l = lds64_f2(st + r * 32), d = lds64_f2(st + 512 + r * 32);
+                nl[r] = f2_pack(l.x, l.y);
+                nd[r] = f2_pack(d.x, d.y);
+              }
             }
-            if (false)
-#endif
 #pragma unroll
-            for (int cc = 0; cc < 4; ++cc) {
-              const float4 l = lds128_f4(st + cc * 16), d = lds128_f4(st + 512 + cc * 16);
+            for (int r = 0; r < 4; ++r) {
 #pragma unroll
-              for (int hh = 0; hh < 2; ++hh) {
-                const int i = cc * 4 + hh * 2;
-                const f32x2 x = f2_fma(f2_pack(__uint_as_float(sv[r & 1][i]), __uint_as_float(sv[r & 1][i + 1])), sl2,
-                                       hh == 0 ? f2_pack(l.x, l.y) : f2_pack(l.z, l.w));
+              for (int e = 0; e < 2; ++e) {
+                const int i = 4 * r + 2 * e;
+                const f32x2 x = f2_fma(f2_pack(__uint_as_float(sv[rd & 1][i]), __uint_as_float(sv[rd & 1][i + 1])), sl2, nl[r]);
                 float x0, x1;
                 f2_unpack(x, x0, x1);
                 const float p0 = ex2_fast(x0), p1 = ex2_fast(x1);
-                const f32x2 tt = f2_add(f2_pack(__uint_as_float(dv[r & 1][i]), __uint_as_float(dv[r & 1][i + 1])),
-                                        hh == 0 ? f2_pack(d.x, d.y) : f2_pack(d.z, d.w));
-                pkp[r * 8 + cc * 2 + hh] = pack_bf16x2(p0, p1);
-                pkd[r * 8 + cc * 2 + hh] = f2_to_bf16x2(f2_mul(f2_pack(p0, p1), tt));
+                const f32x2 tt = f2_add(f2_pack(__uint_as_float(dv[rd & 1][i]), __uint_as_float(dv[rd & 1][i + 1])), nd[r]);
+                pkp[rd][2 * r + e] = pack_bf16x2(p0, p1);
+                pkd[rd][2 * r + e] = f2_to_bf16x2(f2_mul(f2_pack(p0, p1), tt));
+              }
+            }
+            if (partial) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                pkp[rd][i] &= keep[2 * h + (i & 1)];
+                pkd[rd][i] &= keep[2 * h + (i & 1)];
               }
             }
           }
           __syncwarp();
           if (lane == 0) mbar_arrive(&stat_free[b]);
-          if (partial) {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              pkp[i] &= keep;
-              pkd[i] &= keep;
-            }
-          }
           FB_TRACE(12, n);
           // P^T is released right after the dV MMAs of block n - 1 (issued first); dS^T is double-buffered (block n - 2 used
-          // this buffer).  The tensor-memory store is in flight under the shared-memory stores and the proxy fence.
+          // this buffer).  The tensor-memory stores are in flight under the shared-memory stores and the proxy fence.
           if (n >= 1) FB_WAIT_SOFTMAX(&pipe[PV_FREE], (n - 1) & 1);
           tc_fence_after();
           FB_TRACE(13, n);
-          tmem_st_32x32(tP, pkp);
+#pragma unroll
+          for (int rd = 0; rd < 4; ++rd)   // packed columns: 32 per 64-column half, 16 per chunk
+            tmem_st_16x128b_x4(t_quad + (static_cast<uint32_t>((rd & 1) * 16) << 16) + 256 + ch * 32 + (rd >> 1) * 16, pkp[rd]);
           if (n >= 2) FB_WAIT_SOFTMAX(&pipe[DS_FREE0 + b], ((n >> 1) - 1) & 1);
           FB_TRACE(15, n);
-          const uint32_t sDS_mine = sDS_row + b * (2 * TILE16K);
 #pragma unroll
-          for (int c = 0; c < 8; ++c)
-            sts128(sDS_mine + ((c ^ (row & 7)) << 4), make_uint4(pkd[c * 4], pkd[c * 4 + 1], pkd[c * 4 + 2], pkd[c * 4 + 3]));
+          for (int rd = 0; rd < 4; ++rd) {
+            const int c32 = rd >> 1, h = rd & 1;
+            // lane -> row (st_row + 16 h) of matrix m = lane >> 3: chunk 4 c32 + 2 k + (m >> 1) for the k-th instruction
+            const uint32_t base = sDS_lane + b * (2 * TILE16K) + h * (16 * 128);
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+              const int chunk16 = 4 * c32 + 2 * k;
+              stmatrix_x4(base + (((chunk16 + (lane >> 4)) ^ (lane & 7)) << 4), pkd[rd][4 * k], pkd[rd][4 * k + 1], pkd[rd][4 * k + 2],
+                          pkd[rd][4 * k + 3]);
+            }
+          }
           fence_proxy_async_smem();   // generic-proxy stores of dS^T -> visible to the tensor core's async-proxy reads
           FB_TRACE(16, n);
           tmem_st_wait();
@@ -552,24 +578,16 @@ attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_c
             __syncwarp();
             if (lane == 0) mbar_arrive(&pipe[DQ_FREE]);
             FB_TRACE(21, n);
-#ifndef FB_ABL_NORED
 #pragma unroll
             for (int g = 0; g < 16; ++g) {
               float* dst = sp + g * 2048;
               if (first) st_global_f4(dst, __uint_as_float(a[g * 4]), __uint_as_float(a[g * 4 + 1]), __uint_as_float(a[g * 4 + 2]), __uint_as_float(a[g * 4 + 3]));
               else red_global_f4(dst, __uint_as_float(a[g * 4]), __uint_as_float(a[g * 4 + 1]), __uint_as_float(a[g * 4 + 2]), __uint_as_float(a[g * 4 + 3]));
             }
-#else
-            if (a[0] == 0x7fc12345u && a[63] == 0x7fc12345u) sp[0] = 1.f;
-#endif
           } else {
             // last key tile: the partial sums of the earlier tiles come back from L2 while the MMAs of this block run
             float v[64];
-#ifdef FB_ABL_NOFINAL
-            if (false) {
-#else
             if (!first) {
-#endif
 #pragma unroll
               for (int g = 0; g < 16; ++g) {
                 const float4 s4 = ld_global_cg_f4(sp + g * 2048);
@@ -597,9 +615,6 @@ attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_c
 #pragma unroll
               for (int i = 0; i < 32; ++i) v[hf * 32 + i] += __uint_as_float(a[i]);
             }
-#ifdef FB_ABL_NOFINAL
-            if (v[0] == 1.2345e-30f && v[63] == 1.2345e-30f) sp[0] = 1.f;
-#else
             const bool q_ok = q < it.nq;
 #pragma unroll
             for (int pc = 0; pc < 4; ++pc) {
@@ -621,7 +636,6 @@ attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_c
                 colsum16_atomic(cs, dbias + it.h * D + pc * 16, lane);
               }
             }
-#endif
           }
           FB_TRACE(22, n);
           // ---- dK / dV of key tile t, complete after its last query tile ----
@@ -647,10 +661,6 @@ attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_c
                   FB_TRACE(23, n);
                 }
                 const float mul = m == 0 ? p.scale : 1.f;
-#ifdef FB_ABL_NODKV
-                if (a[0] == 0x7fc12345u && a[63] == 0x7fc12345u) sp[0] = 1.f;
-                if (false)
-#endif
 #pragma unroll
                 for (int pc = 0; pc < 4; ++pc) {
                   uint32_t w[8];

@@ -271,6 +271,36 @@ __device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&v)[16])
       : "r"(taddr)
       : "memory");
 }
+// Matrix-fragment shapes (the register layout of an mma accumulator; profiles/probes/tmem_shape_probe.cu prints it):
+// 16 lanes [base, base + 16) x 8 fp32 columns per repeat; thread t holds (lane base + t/4, columns 8r + 2(t%4), +1) in
+// v[4r], v[4r+1] and (lane base + t/4 + 8, same columns) in v[4r+2], v[4r+3].
+__device__ __forceinline__ void tmem_ld_16x256b_x4(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.16x256b.x4.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
+// 16 lanes x 4 32-bit columns per repeat; thread t holds (lane base + t/4, column 4r + t%4) in v[2r] and
+// (lane base + t/4 + 8, same column) in v[2r+1]: the packed-bf16-pair counterpart of the 16x256b fp32 fragment.
+__device__ __forceinline__ void tmem_st_16x128b_x4(uint32_t taddr, const uint32_t (&v)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.16x128b.x4.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(v[0]), "r"(v[1]),
+               "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+               : "memory");
+}
+// Four 8x8 b16 matrices from fragment registers to shared memory: lane i supplies the address of row i % 8 of matrix i / 8
+// (16 bytes per row); register k of thread t holds elements (row t/4, columns 2(t%4), +1) of matrix k.
+__device__ __forceinline__ void stmatrix_x4(uint32_t row_addr, uint32_t r0, uint32_t r1, uint32_t r2, uint32_t r3) {
+  asm volatile("stmatrix.sync.aligned.m8n8.x4.shared.b16 [%0], {%1, %2, %3, %4};" ::"r"(row_addr), "r"(r0), "r"(r1), "r"(r2), "r"(r3)
+               : "memory");
+}
+__device__ __forceinline__ float2 lds64_f2(uint32_t saddr) {
+  float2 v;
+  asm("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(saddr) : "memory");
+  return v;
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const uint32_t (&v)[32]) {
   asm volatile(
