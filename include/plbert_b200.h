@@ -61,7 +61,10 @@ int plb_length_to_mask(const int32_t* lengths, int B, int L, int32_t* attn_mask,
  *   PLB_EPI_RESIDUAL  C = acc (+ bias) + aux_in[m,n]
  *   PLB_EPI_GELU      u = bf16(acc (+ bias));  C = gelu_new(u) (HF/activations.py:66);  aux_out = gelu_new'(u) — the
  *                     derivative is what the backward pass needs of u, saved instead of u itself
- *   PLB_EPI_GELU_BWD  C = acc * aux_in[m,n]   (aux_in = the derivative saved by PLB_EPI_GELU)
+ *   PLB_EPI_GELU_BWD  C = acc * aux_in[m,n]   (aux_in = the derivative saved by PLB_EPI_GELU); if aux_out != NULL it is an
+ *                     fp32 [N] accumulator to which the column sums of the stored (rounded) C are ADDED — the bias
+ *                     gradient of the Linear that produced u (autograd of HF/:239 ffn), fused so that no separate pass
+ *                     reads d_u again
  *   PLB_EPI_ROWDOT    C = acc;  aux_out is FP32: aux_out[(n / 64) * ld_aux_out + m] += sum over the 64-column block of n
  *                     of bf16(C[m, n']) * aux_in[m, n'] — with C = dO (the O-projection DGRAD, HF:198-200) and aux_in = O this
  *                     is attention's delta = rowsum(dO o O) per (head, row), fused into the GEMM

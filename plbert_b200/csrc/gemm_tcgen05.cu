@@ -79,6 +79,7 @@ struct GemmParams {
   int ldc;
   float* rowdot;      // kRowDot: fp32 [N / 64][rowdot_ld] accumulators of sum_n C[m,n] * aux_in[m,n] per 64-column block
   int rowdot_ld;
+  float* colsum;      // kGeluBwd (optional): fp32 [N], column sums of the stored C are ADDED (the producing Linear's bias gradient)
 };
 
 template <int kStages, int kBufs, int kCta>
@@ -290,7 +291,77 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CU
     constexpr bool kHasAuxIn = (kEpi == kResidual || kEpi == kGeluBwd || kEpi == kRowDot);
     constexpr bool kDual = (kEpi == kGelu);
     constexpr int kSlots = kDual ? kBufs / 2 : kBufs;
-    if (kEpi != kAtomicF32 && elect_one_sync()) {
+    if (kEpi == kGeluBwd && p.colsum != nullptr) {
+      // Same walk with all 32 lanes: besides the elected thread's TMA traffic, the warp adds the column sums of every staged
+      // [128 x 64] chunk to p.colsum (d_u's column sums = the FFN1 bias gradient; the separate 62 us pass over [T, 2048] per
+      // layer is gone).  Lane l owns the column pair 2l, 2l+1 and reads it straight from the swizzled staging buffer while the
+      // TMA store reads the same bytes; the sums run over the ROUNDED values, i.e. what the weight-gradient GEMM reads.
+      uint8_t* epi_smem = smem + L::kEpiOff;
+      UnitWalker la(p, unit0, unit_stride);
+      int la_c = 0;
+      uint32_t la_seq = 0;
+      auto la_issue = [&]() {  // aux load of the next not-yet-issued chunk, if any (state kept by every lane, issued by one)
+        while (la.valid(p)) {
+          const int m_blk = la.m_blk;
+          const int n0 = la.n_blk * BN + la_c * EPI_COLS;
+          if (la_c < BN / EPI_COLS && n0 < p.N) {
+            const int slot = la_seq % kSlots;
+            if (elect_one_sync()) {
+              mbar_arrive_expect_tx(&epi_in[slot], EPI_BUF_BYTES);
+              tma_load_2d(epi_smem + slot * EPI_BUF_BYTES, &tm_aux_in, &epi_in[slot], n0, (m_blk * kCta + rank) * BM);
+            }
+            ++la_seq;
+            ++la_c;
+            return;
+          }
+          la.next(p);
+          la_c = 0;
+        }
+      };
+      for (int i = 0; i < kSlots; ++i) la_issue();
+      uint32_t seq = 0;
+      for (UnitWalker w(p, unit0, unit_stride); w.valid(p); w.next(p)) {
+        const int m0 = (w.m_blk * kCta + rank) * BM, n0 = w.n_blk * BN;
+        const int rows = min(BM, p.M - m0);   // rows of the tile inside the matrix (<= 0: the pair's second half is past the end)
+        for (int c = 0; c < BN / EPI_COLS; ++c) {
+          const int nc = n0 + c * EPI_COLS;
+          if (nc >= p.N) break;
+          const int slot = seq % kSlots;
+          uint8_t* buf = epi_smem + slot * EPI_BUF_BYTES;
+          mbar_wait(&chunk_ready[slot], (seq / kSlots) & 1);
+          if (elect_one_sync()) {
+            tma_store_2d(&tm_c, buf, nc, m0);
+            bulk_commit();
+          }
+          float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+          const uint32_t col_addr = smem_u32(buf) + (lane & 3) * 4;
+          int r = 0;
+#pragma unroll 4
+          for (; r + 1 < rows; r += 2) {
+            uint32_t va, vb;
+            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(va) : "r"(col_addr + r * 128 + (((lane >> 2) ^ (r & 7)) << 4)));
+            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(vb) : "r"(col_addr + (r + 1) * 128 + (((lane >> 2) ^ ((r + 1) & 7)) << 4)));
+            s0 += bf16_lo(va); s1 += bf16_hi(va);
+            s2 += bf16_lo(vb); s3 += bf16_hi(vb);
+          }
+          if (r < rows) {
+            uint32_t va;
+            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(va) : "r"(col_addr + r * 128 + (((lane >> 2) ^ (r & 7)) << 4)));
+            s0 += bf16_lo(va); s1 += bf16_hi(va);
+          }
+          if (rows > 0) {
+            const int n = nc + 2 * lane;
+            if (n < p.N) atomicAdd(p.colsum + n, s0 + s2);
+            if (n + 1 < p.N) atomicAdd(p.colsum + n + 1, s1 + s3);
+          }
+          if (elect_one_sync()) bulk_wait_read<0>();   // the slot has left shared memory
+          __syncwarp();                                // ... and every lane has read its column pair
+          la_issue();                                  // chunk seq + kSlots goes into it; epi_in[slot] announces it
+          ++seq;
+        }
+      }
+      if (elect_one_sync()) bulk_wait<0>();  // all stores globally visible before exit
+    } else if (kEpi != kAtomicF32 && elect_one_sync()) {
       uint8_t* epi_smem = smem + L::kEpiOff;
       UnitWalker la(p, unit0, unit_stride);
       int la_c = 0;
@@ -636,6 +707,10 @@ extern "C" int plb_gemm_bf16(int op, int epilogue, int M, int N, int K, const vo
                 "gemm: ROWDOT needs op DGRAD, an fp32 aux_out with ld_aux_out >= M, N %% 64 == 0 and no bias");
     p.rowdot = static_cast<float*>(aux_out);
     p.rowdot_ld = ld_aux_out;
+  }
+  if (epilogue == PLB_EPI_GELU_BWD && aux_out != nullptr) {
+    PLB_REQUIRE(((uintptr_t)aux_out % 4) == 0, PLB_ERR_ARG, "gemm: GELU_BWD column-sum accumulator must be an fp32 array");
+    p.colsum = static_cast<float*>(aux_out);
   }
   if (epilogue == PLB_EPI_RESIDUAL || epilogue == PLB_EPI_GELU_BWD || epilogue == PLB_EPI_ROWDOT) {
     PLB_REQUIRE(aux_in && (ld_aux_in % 8) == 0 && ((uintptr_t)aux_in % 16) == 0, PLB_ERR_ARG,

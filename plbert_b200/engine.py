@@ -467,8 +467,7 @@ class Engine:
                  self.gp[_LAYER + "full_layer_layer_norm.bias"], self.gp[_LAYER + "ffn_output.bias"], s)
             self._gemm(GEMM_WGRAD, EPI_NONE, H, I, T, self.d_z, H, A["g"], I, self.gp[_LAYER + "ffn_output.weight"], I)
             self._gemm(GEMM_DGRAD, EPI_GELU_BWD, T, I, H, self.d_z, H, self.wp[_LAYER + "ffn_output.weight"], I, self.d_u, I,
-                       aux_in=A["dg"], ld_in=I)   # d_u = (d_z W2) o gelu'(u)
-            call("plb_colsum", ptr(self.d_u), I, T, I, self.gp[_LAYER + "ffn.bias"], s)
+                       aux_in=A["dg"], ld_in=I, aux_out=self.gp[_LAYER + "ffn.bias"])   # d_u = (d_z W2) o gelu'(u); b1.grad += colsum(d_u)
             self._gemm(GEMM_WGRAD, EPI_NONE, I, H, T, self.d_u, I, A["a"], H, self.gp[_LAYER + "ffn.weight"], H)
             self._gemm(GEMM_DGRAD, EPI_RESIDUAL, T, H, I, self.d_u, I, self.wp[_LAYER + "ffn.weight"], H, self.d_a, H,
                        aux_in=self.d_z, ld_in=H)
@@ -488,7 +487,7 @@ class Engine:
                  ptr(g_bqkv), ptr(attn_ws), attn_ws.numel() * 4, s)
             self._gemm(GEMM_WGRAD, EPI_NONE, 3 * H, H, T, self.d_qkv, 3 * H, x_in, H, g_wqkv, H)
             self._gemm(GEMM_DGRAD, EPI_RESIDUAL, T, H, 3 * H, self.d_qkv, 3 * H, wqkv, H, dy, H, aux_in=self.d_z, ld_in=H)
-            self.launches += 4  # 2 ln_bwd, 1 colsum, 1 attention backward; the delta memset is torch's
+            self.launches += 3  # 2 ln_bwd, 1 attention backward; the delta memset is torch's
 
         # ---- embedding side -----------------------------------------------------------------------
         mp = "encoder.encoder.embedding_hidden_mapping_in."

@@ -110,6 +110,27 @@ def test_gemm_dgrad(dev, M, N, K, epi):
     assert (C[:, :N].float() - ref).abs().max().item() <= 0.02 * ref.abs().max().item() + 0.05
 
 
+@pytest.mark.parametrize("M,N,K", [(128, 256, 64), (999, 768, 188), (4097, 2048, 768), (30000, 2048, 192), (300, 100, 768)])
+def test_gemm_gelu_bwd_fused_column_sums(dev, M, N, K):
+    """PLB_EPI_GELU_BWD with an fp32 aux_out: the column sums of the STORED d_u (the FFN1 bias gradient) are added to the
+    accumulator by the GEMM's store warp; C itself is unchanged.  Ragged M / N, many tiles per CTA, repeated accumulation."""
+    ldn = (N + 7) // 8 * 8
+    A = torch.randn(M, K + (-K) % 8, device=dev).to(BF)
+    A[:, K:] = 0
+    W = torch.zeros(K, ldn, device=dev, dtype=BF)
+    W[:, :N] = (torch.randn(K, N, device=dev) / math.sqrt(K)).to(BF)
+    X = torch.randn(M, ldn, device=dev).to(BF)
+    C0 = torch.zeros(M, ldn, device=dev, dtype=BF)
+    _gemm(_abi.GEMM_DGRAD, _abi.EPI_GELU_BWD, M, N, K, A, W, C0, None, X)
+    C = torch.zeros(M, ldn, device=dev, dtype=BF)
+    acc = torch.ones(N, device=dev)
+    for _ in range(2):
+        _gemm(_abi.GEMM_DGRAD, _abi.EPI_GELU_BWD, M, N, K, A, W, C, None, X, acc)
+    assert torch.equal(C, C0)
+    want = C[:, :N].float().sum(0)
+    assert (acc - 1 - 2 * want).abs().max().item() <= 2e-3 * want.abs().max().item() + 1e-3
+
+
 @pytest.mark.parametrize("M,N,K", [(128, 64, 64), (1000, 768, 768), (4097, 256, 192), (77, 128, 2048)])
 def test_gemm_rowdot_epilogue(dev, M, N, K):
     """PLB_EPI_ROWDOT: C = A W and, per 64-column block (= attention head), sum_n bf16(C[m,n]) * aux_in[m,n] accumulated
