@@ -127,6 +127,15 @@ int plb_ln_fwd(const void* z, int T, int H, const float* w, const float* b, floa
 int plb_ln_bwd(const void* dy, const void* z, const float* stats, const float* w, int T, int H,
                void* dz, float* dw_accum, float* db_accum, float* colsum_accum, plb_stream_t stream);
 
+/* ---- north star (c): dropout --------------------------------------------------------------------------
+ * HF/:109 (after the embedding LayerNorm) and HF/:201 (attention output projection, before the residual add):
+ * nn.Dropout(hidden_dropout_prob).  y = (residual ? residual : 0) + x * m, m = 0 or 1 / (1 - p) from a counter-based
+ * generator keyed by (seed, stream, element index r * cols + c) (csrc/rng.cuh; numpy replica oracle/dropout_rng.py),
+ * so the SAME call is the backward of the op and no mask tensor exists.  bf16 [rows, cols], cols % 8 == 0, in place
+ * allowed.  The reference itself runs with p = 0. */
+int plb_dropout(const void* x, int ld_x, const void* residual, int ld_res, void* y, int ld_y, int rows, int cols,
+                float p, unsigned long long seed, unsigned int stream, plb_stream_t stream_);
+
 /* ---- a5: fused attention with key padding -----------------------------------------------------------
  * HF/:184-197 (+ HF/integrations/sdpa_attention.py:92, HF/masking_utils.py:495-520).  qkv: bf16 [T, 3*heads*64]
  * = q | k | v as written by the fused QKV GEMM.  Sequence b owns rows [seq_start[b], seq_start[b] + q_len[b]);
@@ -158,6 +167,22 @@ int plb_attn_bwd_fused(const void* qkv, int ld_qkv, const int32_t* seq_start, co
                        const void* ctx, const void* dctx, int ld_ctx, const float* lse2, float* delta,
                        void* dqkv, int ld_dqkv, float* dbias_qkv_accum, void* workspace, long long workspace_bytes,
                        plb_stream_t stream);
+
+/* Attention-probability dropout (HF/:134, :194: dropout(softmax(S)) V, active in training when
+ * attention_probs_dropout_prob > 0; the reference runs with 0).  Same arguments as plb_attn_fwd_tc / plb_attn_bwd_fused plus
+ * (p, seed, rng_stream): the mask of probability (sequence b, head h, query q, key k) comes from the counter-based generator
+ * of csrc/rng.cuh (replica: oracle/dropout_rng.attention_mask, item = b * heads + h), the backward call regenerates it
+ * from the same triple.  At most 32768 (sequence, head) items.  The forward's ctx is computed from the dropped probabilities,
+ * lse2 from the undropped scores. */
+int plb_attn_fwd_tc_dropout(const void* qkv, int ld_qkv, const int32_t* seq_start, const int32_t* q_len,
+                            const int32_t* kv_len, int B, int heads, int head_dim, int max_q_len, int total_rows,
+                            void* ctx, int ld_ctx, float* lse2, float p_drop, unsigned long long seed,
+                            unsigned int rng_stream, plb_stream_t stream);
+int plb_attn_bwd_fused_dropout(const void* qkv, int ld_qkv, const int32_t* seq_start, const int32_t* q_len,
+                               const int32_t* kv_len, int B, int heads, int head_dim, int max_q_len, int total_rows,
+                               const void* ctx, const void* dctx, int ld_ctx, const float* lse2, float* delta,
+                               void* dqkv, int ld_dqkv, float* dbias_qkv_accum, void* workspace, long long workspace_bytes,
+                               float p_drop, unsigned long long seed, unsigned int rng_stream, plb_stream_t stream);
 
 /* ---- a8: masked-row loss ----------------------------------------------------------------------------
  * R/train.py:107-131 calculate_phoneme_loss.  The host flattens masked_indices into rows[M] (= b*L + i, in the

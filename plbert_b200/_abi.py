@@ -7,7 +7,7 @@ from __future__ import annotations
 
 import ctypes
 import os
-from ctypes import c_char_p, c_double, c_float, c_int, c_long, c_longlong, c_void_p
+from ctypes import c_char_p, c_double, c_float, c_int, c_long, c_longlong, c_uint, c_ulonglong, c_void_p
 
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 # PLBERT_B200_LIB points at an alternative build of the same ABI (profiles/ uses it for instrumented / experimental variants)
@@ -41,6 +41,10 @@ SIGNATURES = {
     "plb_attn_bwd_tc": [P, c_int, P, P, P, c_int, c_int, c_int, c_int, c_int, P, P, c_int, P, P, P, c_int, P, P],
     "plb_attn_bwd_fused_workspace_bytes": [c_int, c_int],
     "plb_attn_bwd_fused": [P, c_int, P, P, P, c_int, c_int, c_int, c_int, c_int, P, P, c_int, P, P, P, c_int, P, P, c_longlong, P],
+    "plb_attn_fwd_tc_dropout": [P, c_int, P, P, P, c_int, c_int, c_int, c_int, c_int, P, c_int, P, c_float, c_ulonglong, c_uint, P],
+    "plb_attn_bwd_fused_dropout": [P, c_int, P, P, P, c_int, c_int, c_int, c_int, c_int, P, P, c_int, P, P, P, c_int, P, P, c_longlong,
+                                   c_float, c_ulonglong, c_uint, P],
+    "plb_dropout": [P, c_int, P, c_int, P, c_int, c_int, c_int, c_float, c_ulonglong, c_uint, P],
     "plb_gather_rows": [P, c_int, P, c_int, c_int, P, c_int, P],
     "plb_scatter_add_rows": [P, c_int, P, c_int, c_int, P, c_int, P],
     "plb_masked_ce": [P, c_int, c_int, c_int, P, P, P, P, c_int, P],

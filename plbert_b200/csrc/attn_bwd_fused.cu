@@ -32,6 +32,7 @@
 // roles (47 %), at 77 %.  Hence the design rules of this file: no staging of outputs through shared memory, statistics
 // fetched in the fragment layout (a lane loads only its own column pairs), dO streamed instead of kept resident.
 #include "common.cuh"
+#include "rng.cuh"
 
 namespace plb {
 namespace {
@@ -167,11 +168,20 @@ __device__ unsigned long long g_fb_trace[FB_TRACE_CAP];
 enum { ST_FULL = 0, ST_FREE, PDS_READY, PV_FREE, DQ_FULL, ACC_DONE, DQ_FREE, DKV_FREE /* phase = key-tile counter */,
        DS_FREE0, DS_FREE1 /* one per dS^T buffer: phase = n >> 1 */, NUM_PIPE_BARS };
 
+// multiplier (0 or 1 / (1 - p)) of attention probability (item, query q, key k): the forward kernel's mask, regenerated
+__device__ __forceinline__ float drop_mult(const DropoutParams& d, uint32_t item, uint32_t q, uint32_t k) {
+  const uint32_t x = rng32(d.seed_lo, d.seed_hi, d.stream, attn_dropout_ctr(item, q, k));
+  return ((k & 1u) ? (x >> 16) : (x & 0xffffu)) < d.thresh16 ? d.scale : 0.f;
+}
+
+// kDrop: attention-probability dropout (HF :134 / :194).  With O = (P o m) V the chain rule gives dV = (P o m)^T dO,
+// dP = (dO V^T) o m and dS = P o (dP - delta) with the UNdropped P and delta = rowsum(dO o O) as before.
+template <bool kDrop>
 __global__ void __launch_bounds__(FB_THREADS, 1)
 attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_dctx,
                       const FbParams p, int n_items, const float* __restrict__ lse2, const float* __restrict__ delta,
                       __nv_bfloat16* __restrict__ dqkv, int ld_dqkv, float* __restrict__ dbias,
-                      float* __restrict__ scratch_all) {
+                      float* __restrict__ scratch_all, const DropoutParams drop) {
   extern __shared__ __align__(1024) uint8_t smem[];
   if (smem_u32(smem) & 1023u) __trap();  // 128-byte swizzle needs 1024-byte aligned tiles
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + FbSmem::kBar);
@@ -486,9 +496,20 @@ attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_c
                 float x0, x1;
                 f2_unpack(x, x0, x1);
                 const float p0 = ex2_fast(x0), p1 = ex2_fast(x1);
-                const f32x2 tt = f2_add(f2_pack(__uint_as_float(dv[rd & 1][i]), __uint_as_float(dv[rd & 1][i + 1])), nd[r]);
-                pkp[rd][2 * r + e] = pack_bf16x2(p0, p1);
-                pkd[rd][2 * r + e] = f2_to_bf16x2(f2_mul(f2_pack(p0, p1), tt));
+                const f32x2 dp2 = f2_pack(__uint_as_float(dv[rd & 1][i]), __uint_as_float(dv[rd & 1][i + 1]));
+                if (kDrop) {
+                  const uint32_t q0 = static_cast<uint32_t>(j * 128 + ch * 64 + c32 * 32 + 8 * r + 2 * (lane & 3));
+                  const uint32_t kr = static_cast<uint32_t>(r0 + 16 * h + 8 * e);
+                  const float m0 = drop_mult(drop, static_cast<uint32_t>(item), q0, kr);
+                  const float m1 = drop_mult(drop, static_cast<uint32_t>(item), q0 + 1, kr);
+                  const f32x2 tt = f2_fma(dp2, f2_pack(m0, m1), nd[r]);
+                  pkp[rd][2 * r + e] = pack_bf16x2(p0 * m0, p1 * m1);
+                  pkd[rd][2 * r + e] = f2_to_bf16x2(f2_mul(f2_pack(p0, p1), tt));
+                } else {
+                  const f32x2 tt = f2_add(dp2, nd[r]);
+                  pkp[rd][2 * r + e] = pack_bf16x2(p0, p1);
+                  pkd[rd][2 * r + e] = f2_to_bf16x2(f2_mul(f2_pack(p0, p1), tt));
+                }
               }
             }
             if (partial) {
@@ -705,11 +726,11 @@ extern "C" int plb_attn_bwd_fused_workspace_bytes(int B, int heads) {
   return static_cast<int>(ctas * SCRATCH_FLOATS * static_cast<long long>(sizeof(float)));
 }
 
-extern "C" int plb_attn_bwd_fused(const void* qkv, int ld_qkv, const int32_t* seq_start, const int32_t* q_len,
-                                  const int32_t* kv_len, int B, int heads, int head_dim, int max_q_len, int total_rows,
-                                  const void* ctx, const void* dctx, int ld_ctx, const float* lse2, float* delta,
-                                  void* dqkv, int ld_dqkv, float* dbias_qkv_accum, void* workspace,
-                                  long long workspace_bytes, plb_stream_t stream_) {
+static int attn_bwd_fused_launch(const void* qkv, int ld_qkv, const int32_t* seq_start, const int32_t* q_len,
+                                 const int32_t* kv_len, int B, int heads, int head_dim, int max_q_len, int total_rows,
+                                 const void* ctx, const void* dctx, int ld_ctx, const float* lse2, float* delta,
+                                 void* dqkv, int ld_dqkv, float* dbias_qkv_accum, void* workspace,
+                                 long long workspace_bytes, const DropoutParams& drop, plb_stream_t stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   PLB_REQUIRE(qkv && seq_start && q_len && kv_len && dctx && lse2 && delta && dqkv && workspace, PLB_ERR_ARG,
               "attn_bwd_fused: null pointer");
@@ -724,13 +745,16 @@ extern "C" int plb_attn_bwd_fused(const void* qkv, int ld_qkv, const int32_t* se
   PLB_REQUIRE(workspace_bytes >= plb_attn_bwd_fused_workspace_bytes(B, heads), PLB_ERR_ARG,
               "attn_bwd_fused: workspace of %lld bytes is too small (plb_attn_bwd_fused_workspace_bytes: %d)", workspace_bytes,
               plb_attn_bwd_fused_workspace_bytes(B, heads));
+  PLB_REQUIRE(drop.thresh16 == 0 || static_cast<long long>(B) * heads <= 32768, PLB_ERR_UNSUPPORTED,
+              "attn_bwd_fused: dropout counters cover at most 32768 (sequence, head) items");
   CUtensorMap tm_qkv, tm_dctx;
   if (!tensor_map_bf16(&tm_qkv, qkv, total_rows, 3 * heads * D, ld_qkv, 128, 64) ||
       !tensor_map_bf16(&tm_dctx, dctx, total_rows, heads * D, ld_ctx, 128, 64))
     return PLB_ERR_CUDA;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(attn_bwd_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FbSmem::kAlloc);
+    cudaError_t e = cudaFuncSetAttribute(attn_bwd_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FbSmem::kAlloc);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_bwd_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FbSmem::kAlloc);
     PLB_REQUIRE(e == cudaSuccess, PLB_ERR_CUDA, "attn_bwd_fused: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     configured = true;
   }
@@ -741,10 +765,38 @@ extern "C" int plb_attn_bwd_fused(const void* qkv, int ld_qkv, const int32_t* se
   FbParams p{seq_start, q_len, kv_len, heads, total_rows, 1.4426950408889634f / sqrtf((float)head_dim),
              1.f / sqrtf((float)head_dim)};
   const int n_items = B * heads, sms = sm_count();
-  attn_bwd_fused_kernel<<<n_items < sms ? n_items : sms, FB_THREADS, FbSmem::kAlloc, stream>>>(
-      tm_qkv, tm_dctx, p, n_items, lse2, delta, static_cast<__nv_bfloat16*>(dqkv), ld_dqkv, dbias_qkv_accum,
-      static_cast<float*>(workspace));
+  const int grid = n_items < sms ? n_items : sms;
+  if (drop.thresh16 != 0)
+    attn_bwd_fused_kernel<true><<<grid, FB_THREADS, FbSmem::kAlloc, stream>>>(
+        tm_qkv, tm_dctx, p, n_items, lse2, delta, static_cast<__nv_bfloat16*>(dqkv), ld_dqkv, dbias_qkv_accum,
+        static_cast<float*>(workspace), drop);
+  else
+    attn_bwd_fused_kernel<false><<<grid, FB_THREADS, FbSmem::kAlloc, stream>>>(
+        tm_qkv, tm_dctx, p, n_items, lse2, delta, static_cast<__nv_bfloat16*>(dqkv), ld_dqkv, dbias_qkv_accum,
+        static_cast<float*>(workspace), drop);
   return check_launch("plb_attn_bwd_fused");
+}
+
+extern "C" int plb_attn_bwd_fused(const void* qkv, int ld_qkv, const int32_t* seq_start, const int32_t* q_len,
+                                  const int32_t* kv_len, int B, int heads, int head_dim, int max_q_len, int total_rows,
+                                  const void* ctx, const void* dctx, int ld_ctx, const float* lse2, float* delta,
+                                  void* dqkv, int ld_dqkv, float* dbias_qkv_accum, void* workspace,
+                                  long long workspace_bytes, plb_stream_t stream) {
+  return attn_bwd_fused_launch(qkv, ld_qkv, seq_start, q_len, kv_len, B, heads, head_dim, max_q_len, total_rows, ctx, dctx, ld_ctx,
+                               lse2, delta, dqkv, ld_dqkv, dbias_qkv_accum, workspace, workspace_bytes, make_dropout(0.f, 0, 0),
+                               stream);
+}
+
+extern "C" int plb_attn_bwd_fused_dropout(const void* qkv, int ld_qkv, const int32_t* seq_start, const int32_t* q_len,
+                                          const int32_t* kv_len, int B, int heads, int head_dim, int max_q_len, int total_rows,
+                                          const void* ctx, const void* dctx, int ld_ctx, const float* lse2, float* delta,
+                                          void* dqkv, int ld_dqkv, float* dbias_qkv_accum, void* workspace,
+                                          long long workspace_bytes, float p_drop, unsigned long long seed,
+                                          unsigned int rng_stream, plb_stream_t stream) {
+  PLB_REQUIRE(p_drop >= 0.f && p_drop < 1.f, PLB_ERR_ARG, "attn_bwd_fused_dropout: p = %f outside [0, 1)", p_drop);
+  return attn_bwd_fused_launch(qkv, ld_qkv, seq_start, q_len, kv_len, B, heads, head_dim, max_q_len, total_rows, ctx, dctx, ld_ctx,
+                               lse2, delta, dqkv, ld_dqkv, dbias_qkv_accum, workspace, workspace_bytes,
+                               make_dropout(p_drop, seed, rng_stream), stream);
 }
 
 #ifdef PLB_ATTN_TRACE

@@ -19,6 +19,7 @@
 // The running maximum uses the lazy-rescale rule (only when it grows by more than 2^8); the O accumulator is then
 // rescaled in TMEM by the row's own thread (tcgen05.ld/st).
 #include "common.cuh"
+#include "rng.cuh"
 
 #include <cstdlib>
 
@@ -149,9 +150,13 @@ __device__ __forceinline__ FwdItem fwd_item(const AttnTcParams& p, int item) {
 // barriers keep running across items, and K / V box j is refilled with the NEXT item's rows as soon as both groups'
 // last tiles of the current item have passed chunk j (kv_free[j]), so the load latency, the pipeline fill and the
 // epilogue of one item overlap the tail / head of its neighbours instead of idling the SM once per (sequence, head).
+// kDrop: nn.Dropout on the attention probabilities (HF :134 / SDPA dropout_p, HF :194): the P that multiplies V is
+// P o m with m = 0 or 1 / (1 - p) from the counter-based generator (rng.cuh; pair (k, k + 1) of query row q); the row sum
+// that normalises it is the undropped one, exactly like dropout(softmax(S)) V.
+template <bool kDrop>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const AttnTcParams p, int n_items,
-                   __nv_bfloat16* __restrict__ ctx, int ld_ctx, float* __restrict__ lse2) {
+                   __nv_bfloat16* __restrict__ ctx, int ld_ctx, float* __restrict__ lse2, const DropoutParams drop) {
   extern __shared__ __align__(1024) uint8_t smem[];
   if (smem_u32(smem) & 1023u) __trap();  // 128-byte swizzle needs 1024-byte aligned tiles
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + FwdSmem::kBar);
@@ -445,6 +450,17 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const AttnTcParam
 #pragma unroll
           for (int i = 0; i < 8; ++i) e[i] = ex2_fast(fmaf(__uint_as_float(sv[cc * 8 + i]), p.scale_log2, mneg));
           ls[cc & 1] += ((e[0] + e[1]) + (e[2] + e[3])) + ((e[4] + e[5]) + (e[6] + e[7]));
+          if (kDrop) {
+            const uint32_t ctr0 = attn_dropout_ctr(static_cast<uint32_t>(item), static_cast<uint32_t>(t * QT + row),
+                                                   static_cast<uint32_t>(j * KC + cc * 8));
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              float m0, m1;
+              dropout_pair(drop, ctr0 + i, m0, m1);
+              e[2 * i] *= m0;
+              e[2 * i + 1] *= m1;
+            }
+          }
           pk[cc * 4 + 0] = pack_bf16x2(e[0], e[1]); pk[cc * 4 + 1] = pack_bf16x2(e[2], e[3]);
           pk[cc * 4 + 2] = pack_bf16x2(e[4], e[5]); pk[cc * 4 + 3] = pack_bf16x2(e[6], e[7]);
         }
@@ -517,9 +533,9 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const AttnTcParam
 
 using namespace plb;
 
-extern "C" int plb_attn_fwd_tc(const void* qkv, int ld_qkv, const int32_t* seq_start, const int32_t* q_len,
-                               const int32_t* kv_len, int B, int heads, int head_dim, int max_q_len, int total_rows,
-                               void* ctx, int ld_ctx, float* lse2, plb_stream_t stream) {
+static int attn_fwd_launch(const void* qkv, int ld_qkv, const int32_t* seq_start, const int32_t* q_len, const int32_t* kv_len,
+                           int B, int heads, int head_dim, int max_q_len, int total_rows, void* ctx, int ld_ctx, float* lse2,
+                           const DropoutParams& drop, plb_stream_t stream) {
   PLB_REQUIRE(qkv && seq_start && q_len && kv_len && ctx && lse2, PLB_ERR_ARG, "attn_fwd_tc: null pointer");
   PLB_REQUIRE(head_dim == D, PLB_ERR_UNSUPPORTED, "attn_fwd_tc: head_dim %d not supported (only 64)", head_dim);
   PLB_REQUIRE(B > 0 && heads > 0 && total_rows > 0, PLB_ERR_ARG, "attn_fwd_tc: bad sizes");
@@ -528,20 +544,44 @@ extern "C" int plb_attn_fwd_tc(const void* qkv, int ld_qkv, const int32_t* seq_s
   PLB_REQUIRE(ld_qkv % 8 == 0 && ld_ctx % 8 == 0 && (reinterpret_cast<uintptr_t>(qkv) % 16) == 0 &&
                   (reinterpret_cast<uintptr_t>(ctx) % 16) == 0,
               PLB_ERR_ARG, "attn_fwd_tc: operands must be 16-byte aligned with ld %% 8 == 0");
+  PLB_REQUIRE(drop.thresh16 == 0 || static_cast<long long>(B) * heads <= 32768, PLB_ERR_UNSUPPORTED,
+              "attn_fwd_tc: dropout counters cover at most 32768 (sequence, head) items");
   CUtensorMap tm;
   if (!tensor_map_bf16(&tm, qkv, total_rows, 3 * heads * D, ld_qkv, 128, 64)) return PLB_ERR_CUDA;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(attn_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FwdSmem::kAlloc);
+    cudaError_t e = cudaFuncSetAttribute(attn_fwd_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FwdSmem::kAlloc);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_fwd_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FwdSmem::kAlloc);
     PLB_REQUIRE(e == cudaSuccess, PLB_ERR_CUDA, "attn_fwd_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     configured = true;
   }
   AttnTcParams p{seq_start, q_len, kv_len, heads, total_rows, 1.4426950408889634f / sqrtf((float)head_dim),
                  1.f / sqrtf((float)head_dim)};
   const int n_items = B * heads, sms = sm_count();
-  attn_fwd_tc_kernel<<<n_items < sms ? n_items : sms, NUM_THREADS, FwdSmem::kAlloc, static_cast<cudaStream_t>(stream)>>>(
-      tm, p, n_items, static_cast<__nv_bfloat16*>(ctx), ld_ctx, lse2);
+  const int grid = n_items < sms ? n_items : sms;
+  if (drop.thresh16 != 0)
+    attn_fwd_tc_kernel<true><<<grid, NUM_THREADS, FwdSmem::kAlloc, static_cast<cudaStream_t>(stream)>>>(
+        tm, p, n_items, static_cast<__nv_bfloat16*>(ctx), ld_ctx, lse2, drop);
+  else
+    attn_fwd_tc_kernel<false><<<grid, NUM_THREADS, FwdSmem::kAlloc, static_cast<cudaStream_t>(stream)>>>(
+        tm, p, n_items, static_cast<__nv_bfloat16*>(ctx), ld_ctx, lse2, drop);
   return check_launch("plb_attn_fwd_tc");
+}
+
+extern "C" int plb_attn_fwd_tc(const void* qkv, int ld_qkv, const int32_t* seq_start, const int32_t* q_len,
+                               const int32_t* kv_len, int B, int heads, int head_dim, int max_q_len, int total_rows,
+                               void* ctx, int ld_ctx, float* lse2, plb_stream_t stream) {
+  return attn_fwd_launch(qkv, ld_qkv, seq_start, q_len, kv_len, B, heads, head_dim, max_q_len, total_rows, ctx, ld_ctx, lse2,
+                         make_dropout(0.f, 0, 0), stream);
+}
+
+extern "C" int plb_attn_fwd_tc_dropout(const void* qkv, int ld_qkv, const int32_t* seq_start, const int32_t* q_len,
+                                       const int32_t* kv_len, int B, int heads, int head_dim, int max_q_len, int total_rows,
+                                       void* ctx, int ld_ctx, float* lse2, float p_drop, unsigned long long seed,
+                                       unsigned int rng_stream, plb_stream_t stream) {
+  PLB_REQUIRE(p_drop >= 0.f && p_drop < 1.f, PLB_ERR_ARG, "attn_fwd_tc_dropout: p = %f outside [0, 1)", p_drop);
+  return attn_fwd_launch(qkv, ld_qkv, seq_start, q_len, kv_len, B, heads, head_dim, max_q_len, total_rows, ctx, ld_ctx, lse2,
+                         make_dropout(p_drop, seed, rng_stream), stream);
 }
 
 // =================================================================================================================

@@ -162,3 +162,20 @@ def test_fused_albert_keeps_the_container_and_fails_loudly_on_cpu():
     model = P.PhonemeOnlyModel(AlbertModel(cfg), 188, 128)
     assert model.encoder._plb_fused and model.encoder._plb_owner is model
     assert set(model.state_dict()) == {"encoder." + k for k in keys} | {"phoneme_predictor.weight", "phoneme_predictor.bias"}
+
+
+def test_dropout_rng_replica_statistics():
+    """oracle/dropout_rng.py (the numpy replica of csrc/rng.cuh): keep rate, scale, independence of streams, pair layout."""
+    import numpy as np
+    from oracle import dropout_rng as R
+    m = R.hidden_mask(512, 768, 0.1, 1234, 3)
+    assert set(np.unique(m)) == {0.0, 1 / 0.9}
+    assert abs((m != 0).mean() - 0.9) < 3e-3
+    assert abs(m.mean() - 1.0) < 4e-3
+    m2 = R.hidden_mask(512, 768, 0.1, 1234, 4)
+    agree = ((m != 0) == (m2 != 0)).mean()
+    assert abs(agree - (0.81 + 0.01)) < 5e-3          # independent masks agree with probability 0.9^2 + 0.1^2
+    assert abs(np.corrcoef(m[:, :-1].ravel() != 0, m[:, 1:].ravel() != 0)[0, 1]) < 0.01   # the two halves of a pair are independent
+    a = R.attention_mask(6, 40, 33, 0.25, 99, 1)
+    assert a.shape == (6, 40, 33) and abs((a != 0).mean() - 0.75) < 0.02
+    assert np.array_equal(R.hidden_mask(4, 8, 0.0, 1, 1), np.ones((4, 8)))

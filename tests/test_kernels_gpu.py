@@ -269,6 +269,34 @@ def test_embed_ln_fwd_bwd(dev, T, E, V, P):
     assert rel(g[3], w.grad) < 1e-4 and rel(g[4], b.grad) < 1e-4
 
 
+# ------------------------------------------------------------------------------------------ dropout
+@pytest.mark.parametrize("rows,cols,p", [(1000, 768, 0.1), (77, 128, 0.5), (4096, 2048, 0.25), (5, 8, 0.0)])
+def test_dropout_kernel_matches_replica_mask(dev, rows, cols, p):
+    """plb_dropout == x * mask (+ residual) with the mask of oracle/dropout_rng.py, element for element; keep rate and scale
+    as torch.nn.Dropout (keep with probability 1 - p, scale 1 / (1 - p)); the same call is its own backward."""
+    from oracle import dropout_rng as R
+    seed, stream = 0x1234ABCD5678EF01, 7
+    x = torch.randn(rows, cols, device=dev).to(BF)
+    res = torch.randn(rows, cols, device=dev).to(BF)
+    y = torch.empty_like(x)
+    call("plb_dropout", ptr(x), cols, 0, 0, ptr(y), cols, rows, cols, p, seed, stream, S())
+    mask = torch.from_numpy(R.hidden_mask(rows, cols, p, seed, stream)).to(dev)
+    assert torch.equal(y, (x.float() * mask.float()).to(BF))
+    keep = (mask != 0).double().mean().item()
+    assert abs(keep - (1 - p)) < 4 * math.sqrt(max(p * (1 - p), 1e-12) / (rows * cols)) + 2e-5
+    if p > 0:
+        assert torch.allclose(mask[mask != 0], torch.full_like(mask[mask != 0], 1 / (1 - p)))
+    # residual form (z1 = x + dropout(attn_out), HF :201-202), in place over x
+    y2 = x.clone()
+    call("plb_dropout", ptr(y2), cols, ptr(res), cols, ptr(y2), cols, rows, cols, p, seed, stream, S())
+    want = torch.addcmul(res.float(), x.float(), mask.float()).to(BF)   # one rounding, like the kernel's fma
+    assert (y2.float() - want.float()).abs().max().item() <= 1e-2 * want.float().abs().max().item()
+    # another stream -> another mask
+    if p > 0:
+        call("plb_dropout", ptr(x), cols, 0, 0, ptr(y), cols, rows, cols, p, seed, stream + 1, S())
+        assert not torch.equal(y, (x.float() * mask.float()).to(BF))
+
+
 # ------------------------------------------------------------------------------------------ attention
 def _attn_ref(qkv, B, L, nh, lens):
     T, H3 = qkv.shape
@@ -343,6 +371,59 @@ def test_attention_fwd_bwd(dev, B, L, nh, lens, bwd, fwd="plb_attn_fwd_tc"):
         assert rel(dqkv[:, sl].float(), qf.grad[:, sl]) < 2e-2, name
     # masked keys: exactly zero gradient for K and V
     assert not dqkv[~valid][:, H:].any()
+
+
+@pytest.mark.parametrize("B,L,nh,lens,p", [(2, 200, 2, [200, 77], 0.2), (3, 512, 3, [512, 300, 129], 0.1), (2, 128, 1, [128, 5], 0.5)])
+def test_attention_probability_dropout(dev, B, L, nh, lens, p):
+    """plb_attn_fwd_tc_dropout / plb_attn_bwd_fused_dropout == dropout(softmax(S)) V and its autograd with the SAME mask (HF :134,
+    :194), the mask rebuilt by the numpy replica of the generator; p = 0 through the dropout entry points == the plain kernels."""
+    from oracle import dropout_rng as R
+    seed, stream = 0xC0FFEE1234567, 11
+    H, T = nh * 64, B * L
+    qkv = torch.randn(T, 3 * H, device=dev).to(BF)
+    lens_t = torch.tensor(lens, device=dev, dtype=torch.int32)
+    seq_start = torch.arange(B, device=dev, dtype=torch.int32) * L
+    q_len = torch.full((B,), L, device=dev, dtype=torch.int32)
+    ctx = torch.full((T, H), float("nan"), device=dev, dtype=BF)
+    lse = torch.zeros(nh, T, device=dev)
+    call("plb_attn_fwd_tc_dropout", ptr(qkv), 3 * H, ptr(seq_start), ptr(q_len), ptr(lens_t), B, nh, 64, L, T, ptr(ctx), H, ptr(lse),
+         p, seed, stream, S())
+    mask = torch.from_numpy(R.attention_mask(B * nh, L, L, p, seed, stream)).to(dev).float().view(B, nh, L, L)
+    qf = qkv.float().requires_grad_(True)
+    q, k, v = [t.view(B, L, nh, 64).transpose(1, 2) for t in qf.split(H, dim=1)]
+    sc = q @ k.transpose(-1, -2) / 8.0
+    key_ok = torch.arange(L, device=dev)[None, :] < lens_t[:, None]
+    sc = sc.masked_fill(~key_ok[:, None, None, :], float("-inf"))
+    ref = ((torch.softmax(sc, dim=-1) * mask) @ v).transpose(1, 2).reshape(T, H)
+    assert torch.isfinite(ctx.float()).all()
+    assert rel(ctx.float(), ref) < 1e-2
+    got_lse = lse.view(nh, B, L).permute(1, 0, 2) * math.log(2.0)
+    assert (got_lse - torch.logsumexp(sc, dim=-1)).abs().max() < 2e-3      # the normaliser is the undropped one
+    dctx = torch.randn(T, H, device=dev).to(BF)
+    valid = key_ok.reshape(T)
+    dctx[~valid] = 0
+    ref.backward(dctx.float())
+    nbytes = _abi.load().plb_attn_bwd_fused_workspace_bytes(B, nh)
+    ws = torch.empty(nbytes // 4, device=dev)
+    dqkv = torch.full((T, 3 * H), float("nan"), device=dev, dtype=BF)
+    delta = torch.zeros(nh, T, device=dev)
+    call("plb_attn_bwd_fused_dropout", ptr(qkv), 3 * H, ptr(seq_start), ptr(q_len), ptr(lens_t), B, nh, 64, L, T, ptr(ctx), ptr(dctx),
+         H, ptr(lse), ptr(delta), ptr(dqkv), 3 * H, 0, ptr(ws), nbytes, p, seed, stream, S())
+    assert torch.isfinite(dqkv.float()).all()
+    for name, sl in (("dq", slice(0, H)), ("dk", slice(H, 2 * H)), ("dv", slice(2 * H, 3 * H))):
+        assert rel(dqkv[:, sl].float(), qf.grad[:, sl]) < 3e-2, name
+    assert not dqkv[~valid][:, H:].any()
+    # a different stream must give a different mask (and a clearly different result)
+    ctx2 = torch.empty_like(ctx)
+    call("plb_attn_fwd_tc_dropout", ptr(qkv), 3 * H, ptr(seq_start), ptr(q_len), ptr(lens_t), B, nh, 64, L, T, ptr(ctx2), H, ptr(lse),
+         p, seed, stream + 1, S())
+    assert rel(ctx2.float(), ref) > 5e-2
+    # p = 0 == the plain kernel, bit for bit
+    ctx3, ctx4 = torch.empty_like(ctx), torch.empty_like(ctx)
+    call("plb_attn_fwd_tc_dropout", ptr(qkv), 3 * H, ptr(seq_start), ptr(q_len), ptr(lens_t), B, nh, 64, L, T, ptr(ctx3), H, ptr(lse),
+         0.0, seed, stream, S())
+    call("plb_attn_fwd_tc", ptr(qkv), 3 * H, ptr(seq_start), ptr(q_len), ptr(lens_t), B, nh, 64, L, T, ptr(ctx4), H, ptr(lse), S())
+    assert torch.equal(ctx3, ctx4)
 
 
 @pytest.mark.parametrize("bwd", BWD_IMPLS)
