@@ -204,13 +204,18 @@ def _lin(p: Params, name: str, dtype):
 # encoder forward / backward
 # ----------------------------------------------------------------------------------------------
 def encoder_forward(params: Params, input_ids: np.ndarray, attention_mask: Optional[np.ndarray], cfg: OracleConfig,
-                    dtype=np.float64, keep_cache: bool = True):
+                    dtype=np.float64, keep_cache: bool = True, dropout: Optional[dict] = None):
     """``AlbertModel.forward`` → last_hidden_state (HF :387-423), restated per SURVEY.md §3.2.
 
     embeddings (HF :71-110) → 128→H projection (HF :276) → ``num_hidden_layers`` applications of the ONE shared
     layer (HF :278-286): attention with key-padding mask (HF :170-204, mask semantics HF masking_utils.py:495-520:
     padded KEYS get -inf, padded queries are still computed), post-LN residual blocks (HF :200-202, :235),
     gelu_new FFN (HF :239-241).  The pooler (HF :418) is skipped: PL-BERT never reads it (R/model.py:14-16).
+
+    ``dropout`` (training with hidden_dropout_prob / attention_probs_dropout_prob > 0; the reference config has 0): explicit
+    multiplier arrays (0 or 1/(1-p)) for the three nn.Dropout sites — ``emb`` [B,L,E] after the embedding LayerNorm (HF :109),
+    ``attn`` list per layer application of [B,nh,L,L] on the attention probabilities (HF :134), ``out`` list of [B,L,H] on the
+    attention output projection before the residual add (HF :201).  Tests build them with oracle/dropout_rng.py.
     """
     ids = np.asarray(input_ids)
     B, L = ids.shape
@@ -222,6 +227,8 @@ def encoder_forward(params: Params, input_ids: np.ndarray, attention_mask: Optio
         _EMB + "token_type_embeddings.weight")
     e_sum = (word[ids] + typ[0][None, None, :]) + pos[:L][None, :, :]
     e, e_hat, e_rstd = layer_norm_fwd(e_sum, g(_EMB + "LayerNorm.weight"), g(_EMB + "LayerNorm.bias"), eps)
+    if dropout is not None and dropout.get("emb") is not None:
+        e = e * dropout["emb"]
     Wm, bm = _lin(params, "encoder.encoder.embedding_hidden_mapping_in", dtype)
     x = e @ Wm.T + bm
 
@@ -242,7 +249,9 @@ def encoder_forward(params: Params, input_ids: np.ndarray, attention_mask: Optio
     scale = dtype(1.0 / np.sqrt(d)) if isinstance(dtype, type) else 1.0 / np.sqrt(d)
 
     layers = []
-    for _ in range(cfg.num_hidden_layers):
+    for li in range(cfg.num_hidden_layers):
+        m_attn = dropout["attn"][li] if dropout is not None and dropout.get("attn") is not None else None
+        m_out = dropout["out"][li] if dropout is not None and dropout.get("out") is not None else None
         q = _split_heads(x @ Wq.T + bq, nh)
         k = _split_heads(x @ Wk.T + bk, nh)
         v = _split_heads(x @ Wv.T + bv, nh)
@@ -250,8 +259,9 @@ def encoder_forward(params: Params, input_ids: np.ndarray, attention_mask: Optio
         s_max = s.max(axis=-1, keepdims=True)
         pexp = np.exp(s - s_max)
         prob = pexp / pexp.sum(axis=-1, keepdims=True)
-        ctx = _merge_heads(prob @ v)
-        z1 = x + (ctx @ Wo.T + bo)
+        ctx = _merge_heads((prob if m_attn is None else prob * m_attn) @ v)
+        proj = ctx @ Wo.T + bo
+        z1 = x + (proj if m_out is None else proj * m_out)
         a, a_hat, a_rstd = layer_norm_fwd(z1, ln1w, ln1b, eps)
         u = a @ W1.T + b1
         gact = gelu_new(u)
@@ -259,9 +269,10 @@ def encoder_forward(params: Params, input_ids: np.ndarray, attention_mask: Optio
         y, y_hat, y_rstd = layer_norm_fwd(z2, ln2w, ln2b, eps)
         if keep_cache:
             layers.append(dict(x=x, q=q, k=k, v=v, prob=prob, ctx=ctx, a=a, a_hat=a_hat, a_rstd=a_rstd, u=u, g=gact,
-                               y_hat=y_hat, y_rstd=y_rstd))
+                               y_hat=y_hat, y_rstd=y_rstd, m_attn=m_attn, m_out=m_out))
         x = y
-    cache = dict(ids=ids, e=e, e_hat=e_hat, e_rstd=e_rstd, layers=layers, L=L) if keep_cache else None
+    cache = dict(ids=ids, e=e, e_hat=e_hat, e_rstd=e_rstd, layers=layers, L=L,
+                 m_emb=dropout.get("emb") if dropout is not None else None) if keep_cache else None
     return x, cache
 
 
@@ -301,13 +312,17 @@ def encoder_backward(params: Params, cache: dict, d_last_hidden: np.ndarray, cfg
         dz1, dw, db = layer_norm_bwd(da, c["a_hat"], c["a_rstd"], ln1w)
         acc(_LAYER + "attention.LayerNorm.weight", dw)
         acc(_LAYER + "attention.LayerNorm.bias", db)
-        acc(_LAYER + "attention.dense.weight", flat(dz1).T @ flat(c["ctx"]))
-        acc(_LAYER + "attention.dense.bias", flat(dz1).sum(0))
-        dctx = _split_heads(dz1 @ Wo, nh)
-        # softmax attention
+        dproj = dz1 if c["m_out"] is None else dz1 * c["m_out"]      # z1 = x + dropout(proj)
+        acc(_LAYER + "attention.dense.weight", flat(dproj).T @ flat(c["ctx"]))
+        acc(_LAYER + "attention.dense.bias", flat(dproj).sum(0))
+        dctx = _split_heads(dproj @ Wo, nh)
+        # softmax attention (ctx = dropout(prob) v)
         prob, q, k, v = c["prob"], c["q"], c["k"], c["v"]
-        dv = prob.transpose(0, 1, 3, 2) @ dctx
+        prob_d = prob if c["m_attn"] is None else prob * c["m_attn"]
+        dv = prob_d.transpose(0, 1, 3, 2) @ dctx
         dp = dctx @ v.transpose(0, 1, 3, 2)
+        if c["m_attn"] is not None:
+            dp = dp * c["m_attn"]
         ds = prob * (dp - (dp * prob).sum(axis=-1, keepdims=True))
         dq = (ds @ k) * scale
         dk = (ds.transpose(0, 1, 3, 2) @ q) * scale
@@ -324,6 +339,8 @@ def encoder_backward(params: Params, cache: dict, d_last_hidden: np.ndarray, cfg
     grads["encoder.encoder.embedding_hidden_mapping_in.weight"] = flat(dy).T @ flat(cache["e"])
     grads["encoder.encoder.embedding_hidden_mapping_in.bias"] = flat(dy).sum(0)
     de = dy @ Wm
+    if cache.get("m_emb") is not None:
+        de = de * cache["m_emb"]
     dsum, dw, db = layer_norm_bwd(de, cache["e_hat"], cache["e_rstd"], g(_EMB + "LayerNorm.weight"))
     grads[_EMB + "LayerNorm.weight"] = dw
     grads[_EMB + "LayerNorm.bias"] = db
@@ -388,7 +405,8 @@ def calculate_loss(logits: np.ndarray, labels: np.ndarray, input_lengths: Sequen
 # ----------------------------------------------------------------------------------------------
 def loss_and_grads(params: Params, cfg: OracleConfig, masked_phonemes: np.ndarray, phoneme_labels: np.ndarray,
                    input_lengths: Sequence[int], masked_indices: Sequence[Sequence[int]],
-                   token_labels: Optional[np.ndarray] = None, dtype=np.float64, token_rows: str = "masked"):
+                   token_labels: Optional[np.ndarray] = None, dtype=np.float64, token_rows: str = "masked",
+                   dropout: Optional[dict] = None):
     """One forward+backward of the reference step: R/train.py:381-390 ``process_batch`` followed by
     ``loss.backward()`` (R/train.py:356).  With ``token_labels`` the same loss template is applied to
     ``token_predictor`` and the two losses are summed (unpinned half, see module docstring); ``token_rows="all_valid"``
@@ -396,7 +414,7 @@ def loss_and_grads(params: Params, cfg: OracleConfig, masked_phonemes: np.ndarra
     lengths = [int(x) for x in input_lengths]
     attn = attention_mask_from_lengths(lengths)
     assert attn.shape[1] == np.asarray(masked_phonemes).shape[1], "batch must be padded to max(input_lengths)"
-    hidden, cache = encoder_forward(params, masked_phonemes, attn, cfg, dtype)
+    hidden, cache = encoder_forward(params, masked_phonemes, attn, cfg, dtype, dropout=dropout)
     B, L, H = hidden.shape
     grads: Params = {}
     losses = {}

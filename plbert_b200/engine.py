@@ -71,6 +71,8 @@ class EngineConfig:
     pad_token_id: int
     num_phonemes: int
     num_tokens: Optional[int]
+    hidden_dropout_prob: float = 0.0             # HF :109 (embeddings) and :201 (attention output projection)
+    attention_probs_dropout_prob: float = 0.0    # HF :134 / :194
 
     @classmethod
     def from_albert(cls, cfg, num_phonemes: int, num_tokens: Optional[int]) -> "EngineConfig":
@@ -79,8 +81,9 @@ class EngineConfig:
             problems.append("num_hidden_groups/inner_group_num must be 1 (one shared layer)")
         if cfg.hidden_act != "gelu_new":
             problems.append(f"hidden_act {cfg.hidden_act!r} (only gelu_new)")
-        if cfg.hidden_dropout_prob != 0 or cfg.attention_probs_dropout_prob != 0:
-            problems.append("dropout > 0 (the reference runs with dropout 0, SURVEY.md §0 row 7)")
+        for pname in ("hidden_dropout_prob", "attention_probs_dropout_prob"):
+            if not 0.0 <= float(getattr(cfg, pname)) < 1.0:
+                problems.append(f"{pname} must be in [0, 1)")
         if cfg.hidden_size % cfg.num_attention_heads or cfg.hidden_size // cfg.num_attention_heads != 64:
             problems.append("head_dim must be 64")
         if cfg.hidden_size % 8 or cfg.intermediate_size % 8 or cfg.embedding_size % 8:
@@ -89,7 +92,8 @@ class EngineConfig:
             raise _abi.PlbError("AlbertConfig not supported by the B200 path: " + "; ".join(problems))
         return cls(cfg.vocab_size, cfg.embedding_size, cfg.hidden_size, cfg.num_attention_heads, cfg.intermediate_size,
                    cfg.num_hidden_layers, cfg.max_position_embeddings, cfg.type_vocab_size, float(cfg.layer_norm_eps),
-                   0 if cfg.pad_token_id is None else int(cfg.pad_token_id), num_phonemes, num_tokens)
+                   0 if cfg.pad_token_id is None else int(cfg.pad_token_id), num_phonemes, num_tokens,
+                   float(cfg.hidden_dropout_prob), float(cfg.attention_probs_dropout_prob))
 
 
 class ParamLayout:
@@ -172,6 +176,14 @@ class Engine:
         self._cap_T = 0
         self._cap_M = 0
         self.loss_buf = torch.zeros(1, dtype=torch.float32, device=device)
+        # dropout (identity in the reference: its AlbertConfig has p = 0).  Masks are never stored: every kernel regenerates
+        # them from (seed, stream) with stream = 64 * (training forward number) + site; sites: 0 embeddings, 1 + 2 l attention
+        # probabilities of layer application l, 2 + 2 l its output projection.
+        self.dropout_seed = int(torch.initial_seed()) & 0xFFFFFFFFFFFFFFFF
+        self.dropout_forwards = 0     # training forwards so far (advances the mask stream)
+        self._drop_base = 0           # stream base of the forward whose activations are live (the backward reuses it)
+        self._drop_p = (0.0, 0.0)     # (hidden, attention) probabilities that forward actually applied
+        self.dropout_enabled = True   # the drop-in models mirror nn.Module.training here (eval() -> identity, like HF)
         self.comm_stream: Optional[torch.cuda.Stream] = None
         self.always_reduce = False    # set by ddp.GradientSynchronizer (world > 1): every step ends in the collectives
         # raw addresses of every tensor inside the (never reallocated) arenas: building torch views costs 3-5 us each and
@@ -271,6 +283,18 @@ class Engine:
              self.pp[_EMB + "LayerNorm.weight"], self.pp[_EMB + "LayerNorm.bias"], c.layer_norm_eps,
              ptr(self.e), ptr(self.e_stats), s)
         self.launches += 1
+        on = train and self.dropout_enabled                     # nn.Dropout is the identity outside training (HF modules in eval())
+        p_hid = c.hidden_dropout_prob if on else 0.0
+        p_att = c.attention_probs_dropout_prob if on else 0.0
+        if train:
+            self._drop_p = (p_hid, p_att)
+        if p_hid > 0 or p_att > 0:
+            self._drop_base = (self.dropout_forwards * 64) & 0xFFFFFFFF
+            self.dropout_forwards += 1
+        seed, base = self.dropout_seed, self._drop_base
+        if p_hid > 0:
+            call("plb_dropout", ptr(self.e), E, 0, 0, ptr(self.e), E, T, E, p_hid, seed, base, s)
+            self.launches += 1
         mp = "encoder.encoder.embedding_hidden_mapping_in."
         self._gemm(GEMM_FWD, EPI_NONE, T, H, E, self.e, E, self.wp[mp + "weight"], E, self.x0, H, bias=self.pp[mp + "bias"])
         wqkv, bqkv = self.wp[att + "query.weight"], self.pp[att + "query.bias"]   # q|k|v are adjacent: one [3H, H] matrix
@@ -278,11 +302,21 @@ class Engine:
         for l in range(c.num_hidden_layers):
             A = self.acts[l if train else l % 2]
             self._gemm(GEMM_FWD, EPI_NONE, T, 3 * H, H, x, H, wqkv, H, A["qkv"], 3 * H, bias=bqkv)
-            call("plb_attn_fwd_tc", ptr(A["qkv"]), 3 * H, ptr(b.seq_start), ptr(b.q_len), ptr(b.kv_len), b.B, nh, H // nh,
-                 b.L, T, ptr(A["ctx"]), H, ptr(A["lse"]), s)
+            if p_att > 0:
+                call("plb_attn_fwd_tc_dropout", ptr(A["qkv"]), 3 * H, ptr(b.seq_start), ptr(b.q_len), ptr(b.kv_len), b.B, nh, H // nh,
+                     b.L, T, ptr(A["ctx"]), H, ptr(A["lse"]), p_att, seed, (base + 1 + 2 * l) & 0xFFFFFFFF, s)
+            else:
+                call("plb_attn_fwd_tc", ptr(A["qkv"]), 3 * H, ptr(b.seq_start), ptr(b.q_len), ptr(b.kv_len), b.B, nh, H // nh,
+                     b.L, T, ptr(A["ctx"]), H, ptr(A["lse"]), s)
             self.launches += 1
-            self._gemm(GEMM_FWD, EPI_RESIDUAL, T, H, H, A["ctx"], H, self.wp[att + "dense.weight"], H, A["z1"], H,
-                       bias=self.pp[att + "dense.bias"], aux_in=x, ld_in=H)
+            if p_hid > 0:   # z1 = x + dropout(ctx Wo^T + bo)  (HF :200-202)
+                self._gemm(GEMM_FWD, EPI_NONE, T, H, H, A["ctx"], H, self.wp[att + "dense.weight"], H, A["z1"], H,
+                           bias=self.pp[att + "dense.bias"])
+                call("plb_dropout", ptr(A["z1"]), H, ptr(x), H, ptr(A["z1"]), H, T, H, p_hid, seed, (base + 2 + 2 * l) & 0xFFFFFFFF, s)
+                self.launches += 1
+            else:
+                self._gemm(GEMM_FWD, EPI_RESIDUAL, T, H, H, A["ctx"], H, self.wp[att + "dense.weight"], H, A["z1"], H,
+                           bias=self.pp[att + "dense.bias"], aux_in=x, ld_in=H)
             call("plb_ln_fwd", ptr(A["z1"]), T, H, self.pp[att + "LayerNorm.weight"], self.pp[att + "LayerNorm.bias"],
                  c.layer_norm_eps, ptr(A["a"]), ptr(A["st1"]), s)
             self._gemm(GEMM_FWD, EPI_GELU, T, I, H, A["a"], H, self.wp[_LAYER + "ffn.weight"], H, A["g"], I,
@@ -458,6 +492,8 @@ class Engine:
         g_wqkv, g_bqkv = self.gp[att + "query.weight"], self.gp[att + "query.bias"]
         delta_flat = self.delta.view(-1)   # indexed [head * T + row] by the kernels
         attn_ws = self._attn_workspace(b.B)
+        p_hid, p_att = self._drop_p   # what the forward whose activations are live applied
+        seed, base = self.dropout_seed, self._drop_base
         for l in reversed(range(c.num_hidden_layers)):
             A = self.acts[l]
             x_in = self.acts[l - 1]["y"] if l > 0 else self.x0
@@ -472,19 +508,34 @@ class Engine:
             self._gemm(GEMM_DGRAD, EPI_RESIDUAL, T, H, I, self.d_u, I, self.wp[_LAYER + "ffn.weight"], H, self.d_a, H,
                        aux_in=self.d_z, ld_in=H)
             # a = LN1(z1), z1 = x + ctx Wo^T + bo
-            call("plb_ln_bwd", ptr(self.d_a), ptr(A["z1"]), ptr(A["st1"]), self.pp[att + "LayerNorm.weight"], T, H,
-                 ptr(self.d_z), self.gp[att + "LayerNorm.weight"], self.gp[att + "LayerNorm.bias"],
-                 self.gp[att + "dense.bias"], s)
-            self._gemm(GEMM_WGRAD, EPI_NONE, H, H, T, self.d_z, H, A["ctx"], H, self.gp[att + "dense.weight"], H)
+            d_proj = self.d_z   # gradient of the output projection's result; the residual path takes d_z itself
+            if p_hid > 0:
+                # z1 = x + dropout(proj): d proj = d_z o m (same mask), and the projection's bias gradient is ITS column sum
+                call("plb_ln_bwd", ptr(self.d_a), ptr(A["z1"]), ptr(A["st1"]), self.pp[att + "LayerNorm.weight"], T, H,
+                     ptr(self.d_z), self.gp[att + "LayerNorm.weight"], self.gp[att + "LayerNorm.bias"], 0, s)
+                d_proj = self.d_a   # (consumed by the LayerNorm backward above)
+                call("plb_dropout", ptr(self.d_z), H, 0, 0, ptr(d_proj), H, T, H, p_hid, seed, (base + 2 + 2 * l) & 0xFFFFFFFF, s)
+                call("plb_colsum", ptr(d_proj), H, T, H, self.gp[att + "dense.bias"], s)
+                self.launches += 2
+            else:
+                call("plb_ln_bwd", ptr(self.d_a), ptr(A["z1"]), ptr(A["st1"]), self.pp[att + "LayerNorm.weight"], T, H,
+                     ptr(self.d_z), self.gp[att + "LayerNorm.weight"], self.gp[att + "LayerNorm.bias"],
+                     self.gp[att + "dense.bias"], s)
+            self._gemm(GEMM_WGRAD, EPI_NONE, H, H, T, d_proj, H, A["ctx"], H, self.gp[att + "dense.weight"], H)
             # dO = dz Wo, and in the same epilogue attention's delta[h, row] = sum_d dO o O over each head's 64 columns
             delta_flat[:nh * T].zero_()
-            self._gemm(GEMM_DGRAD, EPI_ROWDOT, T, H, H, self.d_z, H, self.wp[att + "dense.weight"], H, self.d_ctx, H,
+            self._gemm(GEMM_DGRAD, EPI_ROWDOT, T, H, H, d_proj, H, self.wp[att + "dense.weight"], H, self.d_ctx, H,
                        aux_in=A["ctx"], ld_in=H, aux_out=self.delta, ld_out=T)
             # one kernel: S^T / dP^T and the exponentials are computed once for dQ, dK and dV (attn_bwd_fused.cu).  ctx = NULL:
             # delta is given; the same kernel accumulates the QKV bias gradient (column sums of dqkv)
-            call("plb_attn_bwd_fused", ptr(A["qkv"]), 3 * H, ptr(b.seq_start), ptr(b.q_len), ptr(b.kv_len), b.B, nh, H // nh, b.L,
-                 T, 0, ptr(self.d_ctx), H, ptr(A["lse"]), ptr(self.delta), ptr(self.d_qkv), 3 * H,
-                 ptr(g_bqkv), ptr(attn_ws), attn_ws.numel() * 4, s)
+            if p_att > 0:
+                call("plb_attn_bwd_fused_dropout", ptr(A["qkv"]), 3 * H, ptr(b.seq_start), ptr(b.q_len), ptr(b.kv_len), b.B, nh,
+                     H // nh, b.L, T, 0, ptr(self.d_ctx), H, ptr(A["lse"]), ptr(self.delta), ptr(self.d_qkv), 3 * H,
+                     ptr(g_bqkv), ptr(attn_ws), attn_ws.numel() * 4, p_att, seed, (base + 1 + 2 * l) & 0xFFFFFFFF, s)
+            else:
+                call("plb_attn_bwd_fused", ptr(A["qkv"]), 3 * H, ptr(b.seq_start), ptr(b.q_len), ptr(b.kv_len), b.B, nh, H // nh, b.L,
+                     T, 0, ptr(self.d_ctx), H, ptr(A["lse"]), ptr(self.delta), ptr(self.d_qkv), 3 * H,
+                     ptr(g_bqkv), ptr(attn_ws), attn_ws.numel() * 4, s)
             self._gemm(GEMM_WGRAD, EPI_NONE, 3 * H, H, T, self.d_qkv, 3 * H, x_in, H, g_wqkv, H)
             self._gemm(GEMM_DGRAD, EPI_RESIDUAL, T, H, 3 * H, self.d_qkv, 3 * H, wqkv, H, dy, H, aux_in=self.d_z, ld_in=H)
             self.launches += 3  # 2 ln_bwd, 1 attention backward; the delta memset is torch's
@@ -494,6 +545,9 @@ class Engine:
         call("plb_colsum", ptr(dy), H, T, H, self.gp[mp + "bias"], s)
         self._gemm(GEMM_WGRAD, EPI_NONE, H, E, T, dy, H, self.e, E, self.gp[mp + "weight"], E)
         self._gemm(GEMM_DGRAD, EPI_NONE, T, E, H, dy, H, self.wp[mp + "weight"], E, self.d_e, E)
+        if p_hid > 0:   # e = dropout(LN(...)): the LayerNorm backward sees d_e o m
+            call("plb_dropout", ptr(self.d_e), E, 0, 0, ptr(self.d_e), E, T, E, p_hid, seed, base, s)
+            self.launches += 1
         call("plb_embed_ln_bwd", ptr(self.d_e), ptr(b.ids), ptr(b.pos), T, E, c.vocab_size, self.pp[_EMB + "word_embeddings.weight"],
              self.pp[_EMB + "position_embeddings.weight"], self.pp[_EMB + "token_type_embeddings.weight"],
              self.pp[_EMB + "LayerNorm.weight"], ptr(self.e_stats), c.pad_token_id,

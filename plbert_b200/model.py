@@ -208,6 +208,7 @@ class _FusedModel(nn.Module):
                 if versions != self._versions:
                     eng.shadow_valid = False
                     self._versions = versions
+                eng.dropout_enabled = self.training
                 return eng
         named = self._arena_params()
         if eng is None or eng.device != device:
@@ -240,6 +241,7 @@ class _FusedModel(nn.Module):
         if stale or versions != self._versions:
             eng.shadow_valid = False  # someone wrote the fp32 weights through torch (load_state_dict, init, ...)
             self._versions = versions
+        eng.dropout_enabled = self.training
         return eng
 
     def _publish_grads(self) -> None:

@@ -133,10 +133,14 @@ def test_drop_in_constructor_and_state_dict_and_no_cpu_fallback(tmp_path):
 
 def test_unsupported_configs_are_rejected():
     from transformers import AlbertConfig
-    for kw in (dict(hidden_act="gelu"), dict(hidden_dropout_prob=0.1), dict(num_attention_heads=4), dict(num_hidden_groups=2)):
-        cfg = AlbertConfig(vocab_size=188, **{**dict(hidden_size=128, num_attention_heads=2, intermediate_size=256, embedding_size=32), **kw})
+    base = dict(hidden_size=128, num_attention_heads=2, intermediate_size=256, embedding_size=32)
+    for kw in (dict(hidden_act="gelu"), dict(hidden_dropout_prob=1.0), dict(num_attention_heads=4), dict(num_hidden_groups=2)):
+        cfg = AlbertConfig(vocab_size=188, **{**base, **kw})
         with pytest.raises(Exception):
             EngineConfig.from_albert(cfg, 188, None)
+    # dropout is a kernel parameter (identity at the reference's p = 0): probabilities in [0, 1) are carried into the engine
+    ec = EngineConfig.from_albert(AlbertConfig(vocab_size=188, hidden_dropout_prob=0.1, attention_probs_dropout_prob=0.2, **base), 188, None)
+    assert (ec.hidden_dropout_prob, ec.attention_probs_dropout_prob) == (0.1, 0.2)
 
 
 def test_fused_albert_keeps_the_container_and_fails_loudly_on_cpu():

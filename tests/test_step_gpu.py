@@ -150,6 +150,64 @@ def test_step_matches_oracle(dev, two_heads, varlen):
     assert all(set(v) == {"step", "exp_avg", "exp_avg_sq"} for v in sd["state"].values())
 
 
+@pytest.mark.parametrize("varlen", [False, True])
+def test_step_with_dropout_matches_oracle_with_the_same_masks(dev, varlen):
+    """hidden_dropout_prob / attention_probs_dropout_prob > 0 (HF :109, :134, :201; the reference config leaves them at 0): the
+    step must equal the fp64 oracle run with the SAME masks, rebuilt by the numpy replica of the kernels' generator — in the
+    padded and in the packed row layout; a second step draws new masks; eval() switches dropout off."""
+    from transformers import AlbertConfig, AlbertModel
+    from plbert_b200.batch import synthetic_collate_batch
+    from oracle import dropout_rng as R
+    import plbert_b200 as P
+    Vp, E, H, nh, I, nl, L, p_h, p_a = 188, 32, 128, 2, 256, 3, 128, 0.1, 0.15
+    torch.manual_seed(5)
+    enc = AlbertModel(AlbertConfig(vocab_size=Vp, embedding_size=E, hidden_size=H, num_attention_heads=nh, intermediate_size=I,
+                                   num_hidden_layers=nl, max_position_embeddings=L, hidden_dropout_prob=p_h,
+                                   attention_probs_dropout_prob=p_a))
+    model = P.PhonemeOnlyModel(enc, Vp, H).to(dev)
+    model.train()
+    batch = synthetic_collate_batch(4, L, seed=21, variable_length=varlen, min_length=40, word_pred_prob=0.25)
+    labels, masked, lengths, midx = batch
+    B, Lb = masked.shape
+    params = {k: v.detach().cpu().double().numpy() for k, v in model.state_dict().items()}
+    cfg = O.OracleConfig(vocab_size=Vp, embedding_size=E, hidden_size=H, num_attention_heads=nh, intermediate_size=I,
+                         num_hidden_layers=nl, max_position_embeddings=L)
+
+    def masks(step):
+        eng = model._engine
+        seed, base = eng.dropout_seed, 64 * step
+        packed = varlen                                    # loss_and_backward packs variable-length batches
+        starts = np.concatenate([[0], np.cumsum(lengths)[:-1]]) if packed else np.arange(B) * Lb
+        T = int(sum(lengths)) if packed else B * Lb
+
+        def rows(cols, stream):                            # [T, cols] in the engine's row order -> [B, Lb, cols], padding rows = 1
+            m = R.hidden_mask(T, cols, p_h, seed, stream)
+            out = np.ones((B, Lb, cols))
+            for b in range(B):
+                n = lengths[b] if packed else Lb
+                out[b, :n] = m[starts[b]:starts[b] + n]
+            return out
+        attn = [R.attention_mask(B * nh, Lb, Lb, p_a, seed, base + 1 + 2 * l).reshape(B, nh, Lb, Lb) for l in range(nl)]
+        return dict(emb=rows(E, base), out=[rows(H, base + 2 + 2 * l) for l in range(nl)], attn=attn)
+
+    model._ensure_engine(dev)
+    losses = []
+    for step in range(2):
+        total, _, grads, _ = O.loss_and_grads(params, cfg, masked.numpy(), labels.numpy(), lengths, midx, dropout=masks(step))
+        loss = model.loss_and_backward(batch)
+        assert abs(loss.item() - total) <= 2e-2 * abs(total), (step, loss.item(), total)
+        worst = check_grads(model, grads, Lb)
+        losses.append(loss.item())
+        print(f"dropout step {step} (varlen={varlen}): loss {loss.item():.5f} vs {total:.5f}; worst cosine {worst:.6f}")
+    assert abs(losses[0] - losses[1]) > 1e-4               # same weights, same batch, new masks
+    total0, _, _, _ = O.loss_and_grads(params, cfg, masked.numpy(), labels.numpy(), lengths, midx)
+    assert abs(losses[0] - total0) > 1e-3 * abs(total0)   # and dropout really changed the loss
+    model.eval()
+    l_eval = model.loss(batch).item()
+    assert abs(l_eval - total0) <= 2e-2 * abs(total0)
+    model.train()
+
+
 def test_training_trajectory_tracks_oracle(dev):
     """Eight optimizer steps (lr 1e-3 so that the weights really move) on eight different batches: the CUDA path's loss at
     every step stays within the north star's bf16 bar (rel 2e-2) of the fp64 oracle trained on the same batches from the
