@@ -184,6 +184,10 @@ class Engine:
         self._drop_base = 0           # stream base of the forward whose activations are live (the backward reuses it)
         self._drop_p = (0.0, 0.0)     # (hidden, attention) probabilities that forward actually applied
         self.dropout_enabled = True   # the drop-in models mirror nn.Module.training here (eval() -> identity, like HF)
+        # column sums of d_u (FFN1 bias gradient) inside the GELU' DGRAD's store warp instead of a separate plb_colsum pass: same-box
+        # A/B (profiles/ab_step.py) 55.8 vs 55.5 ms per step — the store warp's serial sums slow that GEMM (226 -> 305 us alone) by more
+        # than the 62 us pass costs, so the pass stays the default; the fused form is kept and tested (tests/test_kernels_gpu.py)
+        self.fuse_ffn1_bias_sums = False
         self.comm_stream: Optional[torch.cuda.Stream] = None
         self.always_reduce = False    # set by ddp.GradientSynchronizer (world > 1): every step ends in the collectives
         # raw addresses of every tensor inside the (never reallocated) arenas: building torch views costs 3-5 us each and
@@ -502,8 +506,14 @@ class Engine:
                  ptr(self.d_z), self.gp[_LAYER + "full_layer_layer_norm.weight"],
                  self.gp[_LAYER + "full_layer_layer_norm.bias"], self.gp[_LAYER + "ffn_output.bias"], s)
             self._gemm(GEMM_WGRAD, EPI_NONE, H, I, T, self.d_z, H, A["g"], I, self.gp[_LAYER + "ffn_output.weight"], I)
-            self._gemm(GEMM_DGRAD, EPI_GELU_BWD, T, I, H, self.d_z, H, self.wp[_LAYER + "ffn_output.weight"], I, self.d_u, I,
-                       aux_in=A["dg"], ld_in=I, aux_out=self.gp[_LAYER + "ffn.bias"])   # d_u = (d_z W2) o gelu'(u); b1.grad += colsum(d_u)
+            if self.fuse_ffn1_bias_sums:   # d_u = (d_z W2) o gelu'(u); b1.grad += colsum(d_u) in the same kernel (its store warp)
+                self._gemm(GEMM_DGRAD, EPI_GELU_BWD, T, I, H, self.d_z, H, self.wp[_LAYER + "ffn_output.weight"], I, self.d_u, I,
+                           aux_in=A["dg"], ld_in=I, aux_out=self.gp[_LAYER + "ffn.bias"])
+            else:
+                self._gemm(GEMM_DGRAD, EPI_GELU_BWD, T, I, H, self.d_z, H, self.wp[_LAYER + "ffn_output.weight"], I, self.d_u, I,
+                           aux_in=A["dg"], ld_in=I)
+                call("plb_colsum", ptr(self.d_u), I, T, I, self.gp[_LAYER + "ffn.bias"], s)
+                self.launches += 1
             self._gemm(GEMM_WGRAD, EPI_NONE, I, H, T, self.d_u, I, A["a"], H, self.gp[_LAYER + "ffn.weight"], H)
             self._gemm(GEMM_DGRAD, EPI_RESIDUAL, T, H, I, self.d_u, I, self.wp[_LAYER + "ffn.weight"], H, self.d_a, H,
                        aux_in=self.d_z, ld_in=H)
