@@ -96,6 +96,13 @@ __device__ __forceinline__ void st_global_f4(float* p, float a, float b, float c
 __device__ __forceinline__ void red_global_f4(float* p, float a, float b, float c, float d) {
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
+// 32 bytes per lane (one full L2 sector): the bf16 output rows are 4608 bytes apart, so a warp's store touches 32 lines either
+// way; a 16-byte store leaves every sector half written until its partner arrives
+__device__ __forceinline__ void st_global_b256(void* p, const uint32_t (&w)[8]) {
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]), "r"(w[4]),
+               "r"(w[5]), "r"(w[6]), "r"(w[7])
+               : "memory");
+}
 // L2-only load: the scratch lines are modified by red operations, which bypass L1
 __device__ __forceinline__ float4 ld_global_cg_f4(const float* p) {
   float4 v;
@@ -642,11 +649,7 @@ attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_c
               uint32_t w[8];
 #pragma unroll
               for (int i = 0; i < 8; ++i) w[i] = pack_bf16x2(v[pc * 16 + 2 * i] * p.scale, v[pc * 16 + 2 * i + 1] * p.scale);
-              if (q_ok) {
-                __nv_bfloat16* dst = out_head + static_cast<size_t>(q) * ld_dqkv + pc * 16;
-                *reinterpret_cast<uint4*>(dst) = make_uint4(w[0], w[1], w[2], w[3]);
-                *reinterpret_cast<uint4*>(dst + 8) = make_uint4(w[4], w[5], w[6], w[7]);
-              }
+              if (q_ok) st_global_b256(out_head + static_cast<size_t>(q) * ld_dqkv + pc * 16, w);
               if (dbias != nullptr) {   // column sums of the ROUNDED values: exactly what the weight-gradient GEMM reads
                 float cs[16];
 #pragma unroll
@@ -688,10 +691,7 @@ attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_c
 #pragma unroll
                   for (int i = 0; i < 8; ++i) w[i] = pack_bf16x2(__uint_as_float(a[pc * 16 + 2 * i]) * mul, __uint_as_float(a[pc * 16 + 2 * i + 1]) * mul);
                   const int col = (m + 1) * H + pc * 16;
-                  if (k_ok) {
-                    *reinterpret_cast<uint4*>(dst_row + col) = make_uint4(w[0], w[1], w[2], w[3]);
-                    *reinterpret_cast<uint4*>(dst_row + col + 8) = make_uint4(w[4], w[5], w[6], w[7]);
-                  }
+                  if (k_ok) st_global_b256(dst_row + col, w);
                   if (dbias != nullptr) {
                     float cs[16];
 #pragma unroll
@@ -740,8 +740,8 @@ static int attn_bwd_fused_launch(const void* qkv, int ld_qkv, const int32_t* seq
               "attn_bwd_fused: sequences longer than %d rows are not supported (got %d)", MAX_TILES * 128, max_q_len);
   PLB_REQUIRE(ld_qkv % 8 == 0 && ld_ctx % 8 == 0 && ld_dqkv % 8 == 0 && (reinterpret_cast<uintptr_t>(qkv) % 16) == 0 &&
                   (reinterpret_cast<uintptr_t>(ctx) % 16) == 0 && (reinterpret_cast<uintptr_t>(dctx) % 16) == 0 &&  /* NULL ctx passes */
-                  (reinterpret_cast<uintptr_t>(dqkv) % 16) == 0 && (reinterpret_cast<uintptr_t>(workspace) % 16) == 0,
-              PLB_ERR_ARG, "attn_bwd_fused: operands must be 16-byte aligned with ld %% 8 == 0");
+                  (reinterpret_cast<uintptr_t>(dqkv) % 32) == 0 && ld_dqkv % 16 == 0 && (reinterpret_cast<uintptr_t>(workspace) % 16) == 0,
+              PLB_ERR_ARG, "attn_bwd_fused: operands must be 16-byte aligned with ld %% 8 == 0 (dqkv: 32 bytes, ld %% 16 == 0)");
   PLB_REQUIRE(workspace_bytes >= plb_attn_bwd_fused_workspace_bytes(B, heads), PLB_ERR_ARG,
               "attn_bwd_fused: workspace of %lld bytes is too small (plb_attn_bwd_fused_workspace_bytes: %d)", workspace_bytes,
               plb_attn_bwd_fused_workspace_bytes(B, heads));
