@@ -56,7 +56,7 @@ struct FbSmem {
   static constexpr int kStat = kDS + 4 * TILE16K;            // 2 buffers x (128 x -lse2 | 128 x -delta) fp32
   static constexpr int kBar = kStat + 2 * 256 * 4;
   // q_full[4], q_free[4], k_full[2], k_free[2], v_full, v_free, do_full[3], do_free[3], pipeline, stat_full[2], stat_free[2]
-  static constexpr int kNumBars = 4 + 4 + 2 + 2 + 2 + 3 + 3 + 10 + 4;
+  static constexpr int kNumBars = 4 + 4 + 2 + 2 + 2 + 3 + 3 + 11 + 4;
   static constexpr int kAlloc = kBar + kNumBars * 8 + 16;
 };
 static_assert(FbSmem::kAlloc <= 232448, "fused attention backward exceeds the 227 KB shared-memory limit");
@@ -172,7 +172,7 @@ __device__ unsigned long long g_fb_trace[FB_TRACE_CAP];
 #endif
 
 // pipeline barriers (phase = block counter n unless noted)
-enum { ST_FULL = 0, ST_FREE, PDS_READY, PV_FREE, DQ_FULL, ACC_DONE, DQ_FREE, DKV_FREE /* phase = key-tile counter */,
+enum { ST_FULL = 0, ST_FREE, PDS_READY, PV_FREE, DQ_FULL, ACC_DONE, DQ_FREE, DV_FREE, DK_FREE /* phase = key-tile counter */,
        DS_FREE0, DS_FREE1 /* one per dS^T buffer: phase = n >> 1 */, NUM_PIPE_BARS };
 
 // multiplier (0 or 1 / (1 - p)) of attention probability (item, query q, key k): the forward kernel's mask, regenerated
@@ -223,7 +223,8 @@ attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_c
     mbar_init(&pipe[DQ_FULL], 1);
     mbar_init(&pipe[ACC_DONE], 1);
     mbar_init(&pipe[DQ_FREE], 4);       // one arrive per epilogue warp
-    mbar_init(&pipe[DKV_FREE], 4);
+    mbar_init(&pipe[DV_FREE], 4);
+    mbar_init(&pipe[DK_FREE], 4);
     mbar_init(&pipe[DS_FREE0], 1);
     mbar_init(&pipe[DS_FREE1], 1);
     for (int i = 0; i < 2; ++i) {
@@ -354,7 +355,7 @@ attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_c
               const uint64_t ds_off = static_cast<uint64_t>((n & 1) * ((2 * TILE16K) >> 4));
               FB_WAIT_ISSUER(&pipe[PDS_READY], n & 1);                    // P^T in tensor memory, dS^T in shared memory
               FB_TRACE(2, n);
-              if (j == 0 && T >= 1) FB_WAIT_ISSUER(&pipe[DKV_FREE], (T - 1) & 1);   // new key tile: the previous dK / dV are out of TMEM
+              if (j == 0 && T >= 1) FB_WAIT_ISSUER(&pipe[DV_FREE], (T - 1) & 1);   // new key tile: the previous dV is out of TMEM
               tc_fence_after();
               // (rolled loops: 24 unrolled MMAs keep 48 descriptors live and spill the issuer's registers)
               // dV first: P^T is single-buffered in tensor memory, so it is released as early as possible
@@ -373,6 +374,10 @@ attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_c
                 umma_bf16(tmem_base + 448, dDSm + ds_off + 128 * kk, dKm + kv_off + 128 * kk, idesc_dq, kk > 0);
               umma_commit(&pipe[DQ_FULL]);                           // the epilogue drains dQ under the dK MMAs
               FB_TRACE(6, n);
+              if (j == 0 && T >= 1) {   // ... and the previous dK (the epilogue converts dV first, then dK: by now both are out)
+                FB_WAIT_ISSUER(&pipe[DK_FREE], (T - 1) & 1);
+                tc_fence_after();
+              }
 #pragma unroll 1
               for (int kk = 0; kk < 8; ++kk)
                 umma_bf16(tmem_base + 320, dDSk + ds_off + static_cast<uint64_t>((kk >> 2) * (TILE16K >> 4) + 2 * (kk & 3)),
@@ -667,23 +672,21 @@ attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_c
             mbar_wait(&pipe[ACC_DONE], n & 1);
             tc_fence_after();
             {
-              // dK is converted and stored before dV is pulled out of tensor memory: releasing the accumulators earlier (both loads
-              // first) was measured slower, 710 vs 670 us — it only moves more traffic onto the saturated shared-memory / L1 data pipe
+              // one accumulator at a time: pulling both out before converting (earlier release) was measured slower, 710 vs 670 us
               const int key = t * 128 + row;
               const bool k_ok = key < it.nq;
               __nv_bfloat16* dst_row = out_head + static_cast<size_t>(key) * ld_dqkv;
 #pragma unroll
-              for (int m = 0; m < 2; ++m) {   // 0: dK (x scale), 1: dV
+              for (int mm = 0; mm < 2; ++mm) {   // dV first (the next tile's MMAs need its accumulator first), then dK (x scale)
+                const int m = 1 - mm;
                 uint32_t a[64];
 #pragma unroll
                 for (int pc = 0; pc < 4; ++pc) tmem_ld_32x16(t_row + 320 + m * 64 + pc * 16, *reinterpret_cast<uint32_t(*)[16]>(&a[pc * 16]));
                 tmem_ld_wait();
-                if (m == 1) {
-                  tc_fence_before();
-                  __syncwarp();
-                  if (lane == 0) mbar_arrive(&pipe[DKV_FREE]);
-                  FB_TRACE(23, n);
-                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&pipe[m == 1 ? DV_FREE : DK_FREE]);   // the accumulator is in registers
+                if (m == 0) FB_TRACE(23, n);
                 const float mul = m == 0 ? p.scale : 1.f;
 #pragma unroll
                 for (int pc = 0; pc < 4; ++pc) {
