@@ -535,14 +535,8 @@ attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_c
           __syncwarp();
           if (lane == 0) mbar_arrive(&stat_free[b]);
           FB_TRACE(12, n);
-          // P^T is released right after the dV MMAs of block n - 1 (issued first); dS^T is double-buffered (block n - 2 used
-          // this buffer).  The tensor-memory stores are in flight under the shared-memory stores and the proxy fence.
-          if (n >= 1) FB_WAIT_SOFTMAX(&pipe[PV_FREE], (n - 1) & 1);
-          tc_fence_after();
-          FB_TRACE(13, n);
-#pragma unroll
-          for (int rd = 0; rd < 4; ++rd)   // packed columns: 32 per 64-column half, 16 per chunk
-            tmem_st_16x128b_x4(t_quad + (static_cast<uint32_t>((rd & 1) * 16) << 16) + 256 + ch * 32 + (rd >> 1) * 16, pkp[rd]);
+          // dS^T is double-buffered (block n - 2 used this buffer): its stmatrix stores and the proxy fence run first, so that
+          // the wait for P^T's release (the dV MMAs of block n - 1, issued first by issuer B) hides under them
           if (n >= 2) FB_WAIT_SOFTMAX(&pipe[DS_FREE0 + b], ((n >> 1) - 1) & 1);
           FB_TRACE(15, n);
 #pragma unroll
@@ -559,6 +553,12 @@ attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_c
           }
           fence_proxy_async_smem();   // generic-proxy stores of dS^T -> visible to the tensor core's async-proxy reads
           FB_TRACE(16, n);
+          if (n >= 1) FB_WAIT_SOFTMAX(&pipe[PV_FREE], (n - 1) & 1);
+          tc_fence_after();
+          FB_TRACE(13, n);
+#pragma unroll
+          for (int rd = 0; rd < 4; ++rd)   // packed columns: 32 per 64-column half, 16 per chunk
+            tmem_st_16x128b_x4(t_quad + (static_cast<uint32_t>((rd & 1) * 16) << 16) + 256 + ch * 32 + (rd >> 1) * 16, pkp[rd]);
           tmem_st_wait();
           tc_fence_before();
           __syncwarp();
