@@ -15,9 +15,17 @@ def main():
     dev = torch.device("cuda:0")
     B, L, nh = 192, 512, 12
     H, T = nh * 64, B * L
+    if os.environ.get("VARLEN"):   # BASELINE configs[3]: lengths U[32, 512], sorted by length like the collate functions, packed rows
+        g = torch.Generator().manual_seed(int(os.environ["VARLEN"]))
+        lens_l = sorted(torch.randint(32, 513, (B,), generator=g).tolist(), reverse=True)
+        T = sum(lens_l)
+        lens = torch.tensor(lens_l, device=dev, dtype=torch.int32)
+        seq_start = torch.tensor([0] + torch.tensor(lens_l).cumsum(0).tolist()[:-1], device=dev, dtype=torch.int32)
+    else:
+        lens_l = [L] * B
+        lens = torch.full((B,), L, device=dev, dtype=torch.int32)
+        seq_start = torch.arange(B, device=dev, dtype=torch.int32) * L
     qkv = torch.randn(T, 3 * H, device=dev).to(torch.bfloat16)
-    lens = torch.full((B,), L, device=dev, dtype=torch.int32)
-    seq_start = torch.arange(B, device=dev, dtype=torch.int32) * L
     ctx = torch.empty(T, H, device=dev, dtype=torch.bfloat16)
     dctx = torch.randn(T, H, device=dev).to(torch.bfloat16)
     dqkv = torch.empty(T, 3 * H, device=dev, dtype=torch.bfloat16)
@@ -25,7 +33,7 @@ def main():
     delta = torch.empty(nh, T, device=dev)
     dbias = None if os.environ.get("NO_DBIAS") else torch.zeros(3 * H, device=dev)  # NO_DBIAS=1: skip the fused bias sums
     S = torch.cuda.current_stream().cuda_stream
-    fwd_flops = 4.0 * B * nh * L * L * 64
+    fwd_flops = 4.0 * nh * sum(n * n for n in lens_l) * 64
 
     def timeit(fn, flops, label, iters=10):
         for _ in range(3):
