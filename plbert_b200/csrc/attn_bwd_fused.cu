@@ -164,13 +164,6 @@ __device__ unsigned long long g_fb_trace[FB_TRACE_CAP];
 #define FB_TRACE(code, idx) do { } while (0)
 #endif
 
-#ifndef FB_WAIT_ISSUER
-#define FB_WAIT_ISSUER mbar_wait_spin
-#endif
-#ifndef FB_WAIT_SOFTMAX
-#define FB_WAIT_SOFTMAX mbar_wait
-#endif
-
 // pipeline barriers (phase = block counter n unless noted)
 enum { ST_FULL = 0, ST_FREE, PDS_READY, PV_FREE, DQ_FULL, ACC_DONE, DQ_FREE, DV_FREE, DK_FREE /* phase = key-tile counter */,
        DS_FREE0, DS_FREE1 /* one per dS^T buffer: phase = n >> 1 */, NUM_PIPE_BARS };
@@ -301,14 +294,14 @@ attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_c
             const uint64_t kv_off = static_cast<uint64_t>((T & 1) * (TILE16K >> 4));
             for (int j = 0; j < it.n_qt; ++j, ++n) {
               const int qs = (qbase + j) & 3;
-              if (t == 0) FB_WAIT_ISSUER(&q_full[qs], slot_count(quse, qs) & 1);
+              if (t == 0) mbar_wait(&q_full[qs], slot_count(quse, qs) & 1);
               if (j == 0) {
-                FB_WAIT_ISSUER(&k_full[T & 1], (T >> 1) & 1);
-                FB_WAIT_ISSUER(v_full, T & 1);
+                mbar_wait(&k_full[T & 1], (T >> 1) & 1);
+                mbar_wait(v_full, T & 1);
               }
-              FB_WAIT_ISSUER(&do_full[dslot], dphase);
+              mbar_wait(&do_full[dslot], dphase);
               FB_TRACE(7, n);
-              if (n >= 1) FB_WAIT_ISSUER(&pipe[ST_FREE], (n - 1) & 1);   // every softmax warp has pulled block n-1 out of TMEM
+              if (n >= 1) mbar_wait(&pipe[ST_FREE], (n - 1) & 1);   // every softmax warp has pulled block n-1 out of TMEM
               tc_fence_after();
               FB_TRACE(8, n);
               const uint64_t q_off = static_cast<uint64_t>(qs * (TILE16K >> 4)), do_off = static_cast<uint64_t>(dslot * (TILE16K >> 4));
@@ -353,9 +346,9 @@ attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_c
               const uint64_t q_off = static_cast<uint64_t>(qs * (TILE16K >> 4));
               const uint64_t do_off = static_cast<uint64_t>(dslot * (TILE16K >> 4));
               const uint64_t ds_off = static_cast<uint64_t>((n & 1) * ((2 * TILE16K) >> 4));
-              FB_WAIT_ISSUER(&pipe[PDS_READY], n & 1);                    // P^T in tensor memory, dS^T in shared memory
+              mbar_wait(&pipe[PDS_READY], n & 1);                    // P^T in tensor memory, dS^T in shared memory
               FB_TRACE(2, n);
-              if (j == 0 && T >= 1) FB_WAIT_ISSUER(&pipe[DV_FREE], (T - 1) & 1);   // new key tile: the previous dV is out of TMEM
+              if (j == 0 && T >= 1) mbar_wait(&pipe[DV_FREE], (T - 1) & 1);   // new key tile: the previous dV is out of TMEM
               tc_fence_after();
               // (rolled loops: 24 unrolled MMAs keep 48 descriptors live and spill the issuer's registers)
               // dV first: P^T is single-buffered in tensor memory, so it is released as early as possible
@@ -366,7 +359,7 @@ attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_c
               umma_commit(&do_free[dslot]);
               if (++dslot == 3) dslot = 0;
               FB_TRACE(5, n);
-              if (n >= 1) FB_WAIT_ISSUER(&pipe[DQ_FREE], (n - 1) & 1);    // the epilogue has pulled the previous dQ partial out of TMEM
+              if (n >= 1) mbar_wait(&pipe[DQ_FREE], (n - 1) & 1);    // the epilogue has pulled the previous dQ partial out of TMEM
               tc_fence_after();
               FB_TRACE(3, n);
 #pragma unroll 1
@@ -375,7 +368,7 @@ attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_c
               umma_commit(&pipe[DQ_FULL]);                           // the epilogue drains dQ under the dK MMAs
               FB_TRACE(6, n);
               if (j == 0 && T >= 1) {   // ... and the previous dK (the epilogue converts dV first, then dK: by now both are out)
-                FB_WAIT_ISSUER(&pipe[DK_FREE], (T - 1) & 1);
+                mbar_wait(&pipe[DK_FREE], (T - 1) & 1);
                 tc_fence_after();
               }
 #pragma unroll 1
@@ -465,8 +458,8 @@ attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_c
         for (int i = 0; i < 4; ++i) keep[i] = (r0 + 8 * i) < it.nk ? 0xffffffffu : 0u;
         for (int j = 0; j < it.n_qt; ++j, ++n) {
           const uint32_t b = n & 1;
-          FB_WAIT_SOFTMAX(&stat_full[b], (n >> 1) & 1);
-          FB_WAIT_SOFTMAX(&pipe[ST_FULL], n & 1);
+          mbar_wait(&stat_full[b], (n >> 1) & 1);
+          mbar_wait(&pipe[ST_FULL], n & 1);
           tc_fence_after();
           FB_TRACE(10, n);
           // rounds: (32-column chunk c32, lane half h) = (0,0) (0,1) (1,0) (1,1); results pk[c32][h][8]: word 2r + e = repeat r
@@ -537,7 +530,7 @@ attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_c
           FB_TRACE(12, n);
           // dS^T is double-buffered (block n - 2 used this buffer): its stmatrix stores and the proxy fence run first, so that
           // the wait for P^T's release (the dV MMAs of block n - 1, issued first by issuer B) hides under them
-          if (n >= 2) FB_WAIT_SOFTMAX(&pipe[DS_FREE0 + b], ((n >> 1) - 1) & 1);
+          if (n >= 2) mbar_wait(&pipe[DS_FREE0 + b], ((n >> 1) - 1) & 1);
           FB_TRACE(15, n);
 #pragma unroll
           for (int rd = 0; rd < 4; ++rd) {
@@ -553,7 +546,7 @@ attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_c
           }
           fence_proxy_async_smem();   // generic-proxy stores of dS^T -> visible to the tensor core's async-proxy reads
           FB_TRACE(16, n);
-          if (n >= 1) FB_WAIT_SOFTMAX(&pipe[PV_FREE], (n - 1) & 1);
+          if (n >= 1) mbar_wait(&pipe[PV_FREE], (n - 1) & 1);
           tc_fence_after();
           FB_TRACE(13, n);
 #pragma unroll

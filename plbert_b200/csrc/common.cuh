@@ -97,16 +97,6 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
-// Spinning wait (test_wait never suspends the thread): for single-thread roles on a latency-critical hand-off, where the
-// wake-up of a thread suspended inside try_wait was measured at 0.5 - 1.5 k clk (profiles/r2_attn_bwd_fused_timeline.txt).
-__device__ __forceinline__ void mbar_wait_spin(uint64_t* bar, uint32_t parity) {
-  if (mbar_test(bar, parity)) return;
-  const long long t0 = clock64();
-  while (!mbar_test(bar, parity)) {
-    if (clock64() - t0 > (1ll << 31)) __trap();
-  }
-}
-
 // ---- async-proxy fences / bulk groups ----------------------------------------------------------
 __device__ __forceinline__ void fence_proxy_async_smem() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
