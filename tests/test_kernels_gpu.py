@@ -316,8 +316,11 @@ def _attn_bwd(name, *args):
         B, nh = args[5], args[6]
         nbytes = _abi.load().plb_attn_bwd_fused_workspace_bytes(B, nh)
         assert nbytes > 0
-        ws = torch.full((nbytes // 4,), float("nan"), device="cuda")   # contents are irrelevant on entry
+        guard = 4096
+        ws = torch.full((nbytes // 4 + guard,), float("nan"), device="cuda")   # contents are irrelevant on entry
+        ws[nbytes // 4:] = 1234.5                                               # ... and nothing past the declared size is touched
         call(name, *args, ptr(ws), nbytes, S())
+        assert bool((ws[nbytes // 4:] == 1234.5).all()), "attention backward wrote past its workspace"
         return ws
     call(name, *args, S())
 
