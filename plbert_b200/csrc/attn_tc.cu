@@ -8,16 +8,16 @@
 // Warp roles (12 warps = 3 warpgroups): warp 0 = TMA producer, warps 1 / 2 = MMA issuer of softmax group 0 / 1 (one elected
 // thread each, blocking on the barrier that is due next; warp 3 idle; the warpgroup gives its registers away with
 // setmaxnreg), warps 4..7 = softmax group 0, warps 8..11 = softmax group 1 (each softmax thread keeps a whole 128-score
-// row in registers).  The two groups work on DIFFERENT query tiles (tile t goes to group t & 1) and take turns on the
-// MUFU-bound exp2 phase (turn_acquire / turn_release), so one group's exponentials overlap the other's latency-bound
-// phase (TMEM load, row maximum, barriers) and MMAs.  Thread r of a group owns row r of its tile = TMEM lane r.
-// Per 128-query tile and 128-key chunk c:
+// row in registers).  The two groups work on DIFFERENT query tiles (tile t goes to group t & 1), so one group's exponentials
+// overlap the other's latency-bound phases (TMEM load, row maximum, barriers) and MMAs.  Thread r of a group owns row r of its
+// tile = TMEM lane r.  Per 128-query tile and 128-key chunk c:
 //     S_c  = Q K_c^T                 tcgen05.mma  M128 N128 K64  -> TMEM (one S buffer per group)
 //     regs = tcgen05.ld(S_c)         the S buffer is released right here, so S_{c+1} is computed during the exp2 phase
 //     P_c  = exp2(S_c*k - m)         fp32 softmax, bf16 pairs -> TENSOR MEMORY (tcgen05.st), no shared-memory round trip
 //     O   += P_c V_c                 tcgen05.mma  M128 N64 K128, A = P_c from TMEM, B = V as MN-major smem (no transpose)
 // The running maximum uses the lazy-rescale rule (only when it grows by more than 2^8); the O accumulator is then
-// rescaled in TMEM by the row's own thread (tcgen05.ld/st).
+// rescaled in TMEM by the row's own thread (tcgen05.ld/st).  A finished tile's O is taken out of TMEM inside the group's NEXT
+// chunk (deferred epilogue) and leaves the SM as one 4 KB TMA store per warp.
 #include "common.cuh"
 #include "rng.cuh"
 
@@ -48,8 +48,7 @@ struct FwdSmem {
   static constexpr int kBar = kP + 2 * TILE16K;
   // k_full[4], v_full[4], then per group: q_full, q_empty, s_full, s_free, p_ready, pv_done, o_free
   static constexpr int kNumBars = 2 * MAX_BOXES + 2 * BARS_PER_GROUP_FWD + MAX_BOXES;   // ... then kv_free[4]
-  static constexpr int kTurn = kBar + kNumBars * 8 + 16;  // 9 words for the exponential-phase turn-taking
-  static constexpr int kBytes = kTurn + 48;
+  static constexpr int kBytes = kBar + kNumBars * 8 + 16;  // (+ the TMEM base address word)
   static constexpr int kAlloc = kBytes;  // no slack: the dynamic window is 1024-byte aligned (checked at run time)
 };
 static_assert(FwdSmem::kAlloc <= 232448, "forward attention exceeds the 227 KB shared-memory limit");
@@ -88,16 +87,6 @@ __device__ __forceinline__ float turn_acquire(int grp, int quad, uint32_t c, uin
   if (grp == 0 ? (c >= 1 && c - 1 < steps1) : true)
     asm volatile("bar.sync %1, %3;\n\tld.volatile.shared.f32 %0, [%2];" : "=f"(z) : "r"(3 + grp * 4 + quad), "r"(turn_addr), "n"(kPair) : "memory");
   return z;
-}
-// The same two halves with the decision made by the caller (persistent forward kernel: the alternation runs across items).
-__device__ __forceinline__ float turn_wait(int grp, int quad, uint32_t turn_addr) {
-  float z;
-  asm volatile("bar.sync %1, 64;\n\tld.volatile.shared.f32 %0, [%2];" : "=f"(z) : "r"(3 + grp * 4 + quad), "r"(turn_addr) : "memory");
-  return z;
-}
-__device__ __forceinline__ void turn_signal(int grp, int quad, uint32_t turn_addr, uint32_t result_bits) {
-  asm volatile("st.volatile.shared.b32 [%0], %1;\n\tbar.arrive %2, 64;" ::"r"(turn_addr + 4 + ((threadIdx.x >> 5) - 4) * 4), "r"(result_bits),
-               "r"(3 + (grp ^ 1) * 4 + quad) : "memory");
 }
 template <int kPair = 64>
 __device__ __forceinline__ void turn_release(int grp, int quad, uint32_t c, uint32_t steps0, uint32_t steps1, uint32_t turn_addr,
@@ -155,7 +144,7 @@ __device__ __forceinline__ FwdItem fwd_item(const AttnTcParams& p, int item) {
 // that normalises it is the undropped one, exactly like dropout(softmax(S)) V.
 template <bool kDrop>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
-attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const AttnTcParams p, int n_items,
+attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_ctx, const AttnTcParams p, int n_items,
                    __nv_bfloat16* __restrict__ ctx, int ld_ctx, float* __restrict__ lse2, const DropoutParams drop) {
   extern __shared__ __align__(1024) uint8_t smem[];
   if (smem_u32(smem) & 1023u) __trap();  // 128-byte swizzle needs 1024-byte aligned tiles
@@ -173,7 +162,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const AttnTcParam
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tm_qkv);
-    *reinterpret_cast<volatile float*>(smem + FwdSmem::kTurn) = 0.f;
+    tma_prefetch_desc(&tm_ctx);
     for (int i = 0; i < 2 * MAX_BOXES; ++i) mbar_init(&bars[i], 1);
     for (int g = 0; g < 2; ++g) {
       uint64_t* gb = gbar + g * BARS_PER_GROUP;
@@ -362,36 +351,83 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const AttnTcParam
     const int grp = (warp - 4) >> 2;
     const int quad = warp & 3;
     const int row = quad * 32 + lane;
-    const int gtid = threadIdx.x - 128 - grp * 128;  // 0..127 within the group
     const uint32_t lane_addr = static_cast<uint32_t>(quad * 32) << 16;
     const uint32_t tmem_s = tmem_base + lane_addr + grp * 256;
     const uint32_t tmem_o = tmem_s + 128, tmem_p = tmem_s + 192;
     uint64_t* gb = gbar + grp * BARS_PER_GROUP;
-    const uint32_t sPg = smem_u32(smem + FwdSmem::kP + grp * TILE16K);  // output staging of the group
-    const uint32_t sP_row = sPg + row * 128;
     uint32_t c = 0;  // chunk counter of this group over all items (phase of s_full / s_free / p_ready / pv_done)
-    const uint32_t turn_zero = smem_u32(smem + FwdSmem::kTurn);  // one zero word, then one sink word per softmax warp
-    bool prev_even = false;  // the previous item gave both groups the same number of chunks (so group 1 ran last)
+    // Deferred tile epilogue: the finished tile's O stays in TMEM while the group already runs the load / maximum / exponentials of
+    // its NEXT tile's first chunk (whose S the issuer computed right after the tile's last PV); O is pulled out just before that
+    // chunk's P goes to tensor memory and is converted / stored while the chunk's PV MMA runs.
+    bool pend = false;
+    int pend_grow = -1, pend_h = 0;  // this thread's output row (global row index, -1: beyond the sequence) and head
+    bool pend_wfull = false;         // all 32 rows of the warp are rows of the sequence: they leave with one TMA store
+    float pend_inv = 0.f, pend_lse = 0.f;
+    const uint32_t sP_warp = smem_u32(smem + FwdSmem::kP + grp * TILE16K + quad * 4096);  // the warp's 32 staging rows (1024-byte aligned)
+    auto pend_take = [&](uint32_t (&o)[64]) {  // the caller has waited for PV_DONE of the tile's last chunk
+      tc_fence_after();
+      tmem_ld_32x32(tmem_o, *reinterpret_cast<uint32_t(*)[32]>(&o[0]));
+      tmem_ld_32x32(tmem_o + 32, *reinterpret_cast<uint32_t(*)[32]>(&o[32]));
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&gb[O_FREE]);
+    };
+    auto pend_store = [&](const uint32_t (&o)[64]) {
+      pend = false;
+      if (pend_wfull) {
+        // bf16 rows -> the warp's swizzled staging rows -> ONE 4 KB TMA store (32 rows x 128 bytes).  Per-lane global stores of the
+        // rows (32 different lines per instruction) keep the SM's load/store pipe busy for ~300 clk each and every mbarrier operation
+        // of the CTA queues behind them: 253 -> 240 us per launch at 192 x 512 x 12 (profiles/r2_attn_fwd.md)
+        if (lane == 0) bulk_wait_read<0>();  // the warp's previous store has read the staging rows
+        __syncwarp();
+#pragma unroll
+        for (int cc = 0; cc < 8; ++cc) {
+          uint4 v;
+          v.x = pack_bf16x2(__uint_as_float(o[cc * 8 + 0]) * pend_inv, __uint_as_float(o[cc * 8 + 1]) * pend_inv);
+          v.y = pack_bf16x2(__uint_as_float(o[cc * 8 + 2]) * pend_inv, __uint_as_float(o[cc * 8 + 3]) * pend_inv);
+          v.z = pack_bf16x2(__uint_as_float(o[cc * 8 + 4]) * pend_inv, __uint_as_float(o[cc * 8 + 5]) * pend_inv);
+          v.w = pack_bf16x2(__uint_as_float(o[cc * 8 + 6]) * pend_inv, __uint_as_float(o[cc * 8 + 7]) * pend_inv);
+          sts128(sP_warp + lane * 128 + ((cc ^ (lane & 7)) << 4), v);
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {  // lane 0's row is the warp's first
+          tma_store_2d(&tm_ctx, smem + FwdSmem::kP + grp * TILE16K + quad * 4096, pend_h * D, pend_grow);
+          bulk_commit();
+        }
+        lse2[static_cast<size_t>(pend_h) * p.total_rows + pend_grow] = pend_lse;
+      } else if (pend_grow >= 0) {
+        // ragged end of a sequence: the thread writes its own row (128 contiguous bytes) as four 32-byte stores
+        __nv_bfloat16* orow = ctx + static_cast<size_t>(pend_grow) * ld_ctx + pend_h * D;
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc) {
+          uint32_t w[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            w[i] = pack_bf16x2(__uint_as_float(o[cc * 16 + 2 * i]) * pend_inv, __uint_as_float(o[cc * 16 + 2 * i + 1]) * pend_inv);
+          asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(orow + cc * 16), "r"(w[0]), "r"(w[1]),
+                       "r"(w[2]), "r"(w[3]), "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7]) : "memory");
+        }
+        lse2[static_cast<size_t>(pend_h) * p.total_rows + pend_grow] = pend_lse;
+      }
+    };
     FwdItem nxt = blockIdx.x < n_items ? fwd_item(p, blockIdx.x) : FwdItem{};
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
      const FwdItem it = nxt;
-     const bool has_next_item = item + static_cast<int>(gridDim.x) < n_items;
-     if (has_next_item) nxt = fwd_item(p, item + gridDim.x);  // its three scalar loads are in flight during this item
+     if (item + static_cast<int>(gridDim.x) < n_items) nxt = fwd_item(p, item + gridDim.x);  // its three scalar loads are in flight during this item
      const int h = it.h, row_base = it.row_base, nq = it.nq, nk = it.nk, n_chunks = it.n_chunks, n_tiles = it.n_tiles;
-     const uint32_t steps0 = ((n_tiles + 1) >> 1) * n_chunks, steps1 = (n_tiles >> 1) * n_chunks;  // chunks per group in this item
-     uint32_t ci = 0;  // chunk counter within the item
-     // Exponential phases alternate g0, g1, g0, g1, ... within an item (g0 has the extra ones of an odd tile) and the
-     // alternation continues across items: g0's first step waits for g1's last step of the previous item when that item
-     // ended on g1, which g1 signals only if a next item exists.
      for (int t = grp; t < n_tiles; t += 2) {
       float m_used = -INFINITY, l_run = 0.f;
-      for (int j = 0; j < n_chunks; ++j, ++c, ++ci) {
+      for (int j = 0; j < n_chunks; ++j, ++c) {
         mbar_wait(&gb[S_FULL], c & 1);
         tc_fence_after();
         PLB_TRACE(10, c);
         // pull the 128 scores of this row out of TMEM and hand the S buffer straight back to the MMA warp, so that
         // S_{c+1} is computed while this group is busy with the exponentials of chunk c
         uint32_t sv[KC];
+        const int valid = nk - j * KC;  // only the last chunk can hold keys >= kv_len -> -inf
+        float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
         for (int q = 0; q < KC / 32; ++q) tmem_ld_32x32(tmem_s + q * 32, *reinterpret_cast<uint32_t(*)[32]>(&sv[q * 32]));
         tmem_ld_wait();
@@ -399,13 +435,11 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const AttnTcParam
         __syncwarp();
         if (lane == 0) mbar_arrive(&gb[S_FREE]);
         PLB_TRACE(11, c);
-        const int valid = nk - j * KC;  // only the last chunk can hold keys >= kv_len -> -inf
         if (valid < KC) {
 #pragma unroll
           for (int i = 0; i < KC; ++i)
             if (i >= valid) sv[i] = 0xff800000u;
         }
-        float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
         for (int i = 0; i < KC; i += 4) {
           mx[0] = fmaxf(mx[0], __uint_as_float(sv[i]));
@@ -439,18 +473,29 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const AttnTcParam
         // P = exp2(S*k - m) -> bf16, packed in registers FIRST: the exponentials then overlap the previous PV MMA,
         // which still reads the group's P columns; only the TMEM stores wait for it.
         float ls[2] = {0.f, 0.f};
-        float mneg = -m_used;
-        PLB_TRACE(12, c);
-        uint32_t pk[KC / 2];
-        if (grp == 0 ? (ci >= 1 ? ci - 1 < steps1 : prev_even) : true) mneg += turn_wait(grp, quad, turn_zero);
+        const float mneg = -m_used;
         PLB_TRACE(13, c);
+        uint32_t pk[KC / 2];
+        if constexpr (!kDrop) {
+          // on register pairs (FFMA2 / FADD2: half the issue slots of the scale and of the row sum)
+          const f32x2 sc2 = f2_splat(p.scale_log2), mn2 = f2_splat(mneg);
+          f32x2 acc[4] = {f2_splat(0.f), f2_splat(0.f), f2_splat(0.f), f2_splat(0.f)};
 #pragma unroll
-        for (int cc = 0; cc < KC / 8; ++cc) {  // sixteen 16-byte pieces = 128 keys (masked keys: exp2(-inf) = 0)
-          float e[8];
+          for (int i = 0; i < KC; i += 2) {  // masked keys: exp2(-inf) = 0
+            float lo, hi;
+            f2_unpack(f2_fma(f2_pack(__uint_as_float(sv[i]), __uint_as_float(sv[i + 1])), sc2, mn2), lo, hi);
+            const float e0 = ex2_fast(lo), e1 = ex2_fast(hi);
+            acc[(i >> 1) & 3] = f2_add(acc[(i >> 1) & 3], f2_pack(e0, e1));
+            pk[i >> 1] = pack_bf16x2(e0, e1);
+          }
+          f2_unpack(f2_add(f2_add(acc[0], acc[1]), f2_add(acc[2], acc[3])), ls[0], ls[1]);
+        } else {
 #pragma unroll
-          for (int i = 0; i < 8; ++i) e[i] = ex2_fast(fmaf(__uint_as_float(sv[cc * 8 + i]), p.scale_log2, mneg));
-          ls[cc & 1] += ((e[0] + e[1]) + (e[2] + e[3])) + ((e[4] + e[5]) + (e[6] + e[7]));
-          if (kDrop) {
+          for (int cc = 0; cc < KC / 8; ++cc) {  // sixteen 16-byte pieces = 128 keys
+            float e[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) e[i] = ex2_fast(fmaf(__uint_as_float(sv[cc * 8 + i]), p.scale_log2, mneg));
+            ls[cc & 1] += ((e[0] + e[1]) + (e[2] + e[3])) + ((e[4] + e[5]) + (e[6] + e[7]));
             const uint32_t ctr0 = attn_dropout_ctr(static_cast<uint32_t>(item), static_cast<uint32_t>(t * QT + row),
                                                    static_cast<uint32_t>(j * KC + cc * 8));
 #pragma unroll
@@ -460,67 +505,53 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const AttnTcParam
               e[2 * i] *= m0;
               e[2 * i + 1] *= m1;
             }
+            pk[cc * 4 + 0] = pack_bf16x2(e[0], e[1]); pk[cc * 4 + 1] = pack_bf16x2(e[2], e[3]);
+            pk[cc * 4 + 2] = pack_bf16x2(e[4], e[5]); pk[cc * 4 + 3] = pack_bf16x2(e[6], e[7]);
           }
-          pk[cc * 4 + 0] = pack_bf16x2(e[0], e[1]); pk[cc * 4 + 1] = pack_bf16x2(e[2], e[3]);
-          pk[cc * 4 + 2] = pack_bf16x2(e[4], e[5]); pk[cc * 4 + 3] = pack_bf16x2(e[6], e[7]);
         }
-        if (grp == 0 ? (ci < steps1) : (ci + 1 < steps0 || (steps1 == steps0 && has_next_item)))
-          turn_signal(grp, quad, turn_zero, __float_as_uint(ls[0] + ls[1]));
         PLB_TRACE(14, c);
         if (c >= 1) mbar_wait(&gb[PV_DONE], (c - 1) & 1);  // the previous PV has finished reading the P columns
         PLB_TRACE(15, c);
         // P goes to tensor memory (the A operand of O += P V is read from there): no shared-memory round trip
-        tc_fence_after();
-        tmem_st_32x32(tmem_p, *reinterpret_cast<uint32_t(*)[32]>(&pk[0]));
-        tmem_st_32x32(tmem_p + 32, *reinterpret_cast<uint32_t(*)[32]>(&pk[32]));
-        l_run += ls[0] + ls[1];
-        tmem_st_wait();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&gb[P_READY]);
-        PLB_TRACE(16, c);
-      }
-      // ---- epilogue of the tile: O / l -> bf16 -> staging -> global; LSE ----
-      mbar_wait(&gb[PV_DONE], (c - 1) & 1);  // all PV MMAs of the tile are complete: O final
-      tc_fence_after();
-      PLB_TRACE(20, t);
-      const float inv = 1.f / l_run;
-#pragma unroll
-      for (int q = 0; q < 2; ++q) {
-        uint32_t o[32];
-        tmem_ld_32x32(tmem_o + q * 32, o);
-        tmem_ld_wait();
-#pragma unroll
-        for (int cc = 0; cc < 4; ++cc) {
-          uint4 v;
-          v.x = pack_bf16x2(__uint_as_float(o[cc * 8 + 0]) * inv, __uint_as_float(o[cc * 8 + 1]) * inv);
-          v.y = pack_bf16x2(__uint_as_float(o[cc * 8 + 2]) * inv, __uint_as_float(o[cc * 8 + 3]) * inv);
-          v.z = pack_bf16x2(__uint_as_float(o[cc * 8 + 4]) * inv, __uint_as_float(o[cc * 8 + 5]) * inv);
-          v.w = pack_bf16x2(__uint_as_float(o[cc * 8 + 6]) * inv, __uint_as_float(o[cc * 8 + 7]) * inv);
-          sts128(sP_row + (((q * 4 + cc) ^ (row & 7)) << 4), v);
+        auto store_p = [&]() {
+          tc_fence_after();
+          tmem_st_32x32(tmem_p, *reinterpret_cast<uint32_t(*)[32]>(&pk[0]));
+          tmem_st_32x32(tmem_p + 32, *reinterpret_cast<uint32_t(*)[32]>(&pk[32]));
+          l_run += ls[0] + ls[1];
+          tmem_st_wait();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&gb[P_READY]);
+          PLB_TRACE(16, c);
+        };
+        if (pend) {  // (only at j == 0: the wait above covered the previous tile's last PV, its O is final)
+          uint32_t o[64];
+          pend_take(o);
+          store_p();
+          pend_store(o);
+          PLB_TRACE(21, t);
+        } else {
+          store_p();
         }
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&gb[O_FREE]);
+      // the tile's epilogue (O / l -> bf16 -> global, LSE) is deferred into the group's next chunk
       const int qrow = t * QT + row;
-      if (qrow < nq) lse2[static_cast<size_t>(h) * p.total_rows + row_base + qrow] = m_used + log2f(l_run);
-      group_bar_sync(grp);
-      // coalesced copy-out: 128 rows x 8 pieces, guarded by the sequence's row count
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int idx = gtid + i * 128;
-        const int r = idx >> 3, cc = idx & 7;
-        if (t * QT + r < nq) {
-          const uint4 v = lds128(sPg + r * 128 + ((cc ^ (r & 7)) << 4));
-          *reinterpret_cast<uint4*>(ctx + static_cast<size_t>(row_base + t * QT + r) * ld_ctx + h * D + cc * 8) = v;
-        }
-      }
-      group_bar_sync(grp);  // staging fully read before the next tile overwrites it
-      PLB_TRACE(21, t);
+      pend = true;
+      pend_grow = qrow < nq ? row_base + qrow : -1;
+      pend_wfull = t * QT + quad * 32 + 32 <= nq;
+      pend_h = h;
+      pend_inv = 1.f / l_run;
+      pend_lse = m_used + log2f(l_run);
      }
-     prev_even = steps1 == steps0;
     }
+    if (pend) {  // the group's last tile
+      mbar_wait(&gb[PV_DONE], (c - 1) & 1);
+      PLB_TRACE(20, 0);
+      uint32_t o[64];
+      pend_take(o);
+      pend_store(o);
+    }
+    if (lane == 0) bulk_wait_read<0>();  // staging rows read before the CTA's shared memory goes away
   }
   tc_fence_before();
   __syncthreads();
@@ -548,6 +579,8 @@ static int attn_fwd_launch(const void* qkv, int ld_qkv, const int32_t* seq_start
               "attn_fwd_tc: dropout counters cover at most 32768 (sequence, head) items");
   CUtensorMap tm;
   if (!tensor_map_bf16(&tm, qkv, total_rows, 3 * heads * D, ld_qkv, 128, 64)) return PLB_ERR_CUDA;
+  CUtensorMap tm_ctx;   // output rows leave as [32 rows x 64 columns] boxes, one per softmax warp
+  if (!tensor_map_bf16(&tm_ctx, ctx, total_rows, heads * D, ld_ctx, 32, 64)) return PLB_ERR_CUDA;
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(attn_fwd_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FwdSmem::kAlloc);
@@ -561,10 +594,10 @@ static int attn_fwd_launch(const void* qkv, int ld_qkv, const int32_t* seq_start
   const int grid = n_items < sms ? n_items : sms;
   if (drop.thresh16 != 0)
     attn_fwd_tc_kernel<true><<<grid, NUM_THREADS, FwdSmem::kAlloc, static_cast<cudaStream_t>(stream)>>>(
-        tm, p, n_items, static_cast<__nv_bfloat16*>(ctx), ld_ctx, lse2, drop);
+        tm, tm_ctx, p, n_items, static_cast<__nv_bfloat16*>(ctx), ld_ctx, lse2, drop);
   else
     attn_fwd_tc_kernel<false><<<grid, NUM_THREADS, FwdSmem::kAlloc, static_cast<cudaStream_t>(stream)>>>(
-        tm, p, n_items, static_cast<__nv_bfloat16*>(ctx), ld_ctx, lse2, drop);
+        tm, tm_ctx, p, n_items, static_cast<__nv_bfloat16*>(ctx), ld_ctx, lse2, drop);
   return check_launch("plb_attn_fwd_tc");
 }
 

@@ -318,6 +318,23 @@ __device__ __forceinline__ float ex2_fast(float x) {
   return y;
 }
 
+// volatile twins: the compiler keeps them in source order (software-pipelined exponentials, attn_tc.cu)
+__device__ __forceinline__ float ex2_fast_v(float x) {
+  float y;
+  asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ uint32_t pack_bf16x2_v(float lo, float hi) {
+  uint32_t r;
+  asm volatile("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+__device__ __forceinline__ float max3(float a, float b, float c) {
+  float r;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+  return r;
+}
+
 // Shared-memory matrix descriptor (sm_100 "version 1" format), 128-byte swizzle.
 //   K-major : rows of 64 bf16 (128 B); 8-row atoms 1024 B apart (SBO); LBO unused.
 //   MN-major: 64 contiguous MN elements (128 B) per K row; 8 K rows = one 1024 B atom (SBO);
@@ -417,6 +434,11 @@ __device__ __forceinline__ f32x2 f2_mul(f32x2 a, f32x2 b) {
 __device__ __forceinline__ f32x2 f2_add(f32x2 a, f32x2 b) {
   f32x2 d;
   asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ f32x2 f2_add_v(f32x2 a, f32x2 b) {
+  f32x2 d;
+  asm volatile("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
   return d;
 }
 __device__ __forceinline__ f32x2 f2_from_bf16x2(uint32_t w) { return f2_pack(bf16_lo(w), bf16_hi(w)); }
