@@ -482,9 +482,28 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
           f32x2 acc[4] = {f2_splat(0.f), f2_splat(0.f), f2_splat(0.f), f2_splat(0.f)};
 #pragma unroll
           for (int i = 0; i < KC; i += 2) {  // masked keys: exp2(-inf) = 0
-            float lo, hi;
+            float lo, hi, e0, e1;
             f2_unpack(f2_fma(f2_pack(__uint_as_float(sv[i]), __uint_as_float(sv[i + 1])), sc2, mn2), lo, hi);
-            const float e0 = ex2_fast(lo), e1 = ex2_fast(hi);
+            if (((i >> 1) & 3) == 3) {
+              // Every 4th pair on the FMA pipe instead of the MUFU (16 ex2 per clock and SM, the busiest pipe of this kernel):
+              // 2^x = 2^n p(f), n = round(x), f = x - n in [-0.5, 0.5], cubic p with relative error 8e-5 (bf16 rounding of P: 2e-3);
+              // x >= -126 keeps the exponent arithmetic in range (masked keys: 2^-126 instead of 0, far below one bf16 ulp of O).
+              // Measured at 192 x 512 x 12: 0 / 12.5 / 25 / 37.5 / 50 % of the pairs -> 235 / 228 / 217 / 234 / 260 us.
+              const f32x2 xc = f2_pack(fmaxf(lo, -126.f), fmaxf(hi, -126.f));
+              const f32x2 tt = f2_add(xc, f2_splat(12582912.f));                 // low mantissa bits = n
+              const f32x2 ff = f2_add(xc, f2_mul(f2_add(tt, f2_splat(-12582912.f)), f2_splat(-1.f)));
+              f32x2 pp = f2_fma(ff, f2_splat(0.05508868396282196f), f2_splat(0.24260404706001282f));
+              pp = f2_fma(pp, ff, f2_splat(0.6932762265205383f));
+              pp = f2_fma(pp, ff, f2_splat(0.9999289512634277f));
+              float p0, p1, t0, t1;
+              f2_unpack(pp, p0, p1);
+              f2_unpack(tt, t0, t1);
+              e0 = __uint_as_float(__float_as_uint(p0) + (__float_as_uint(t0) << 23));
+              e1 = __uint_as_float(__float_as_uint(p1) + (__float_as_uint(t1) << 23));
+            } else {
+              e0 = ex2_fast(lo);
+              e1 = ex2_fast(hi);
+            }
             acc[(i >> 1) & 3] = f2_add(acc[(i >> 1) & 3], f2_pack(e0, e1));
             pk[i >> 1] = pack_bf16x2(e0, e1);
           }
