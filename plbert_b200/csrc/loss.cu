@@ -90,7 +90,268 @@ __global__ void masked_ce_kernel(__nv_bfloat16* __restrict__ logits, int ld, int
   }
 }
 
-// Large vocabularies (the 64 k token head): one CTA per row, 16-byte accesses.  Pass 1 streams the row from HBM, passes 2
+// Large vocabularies, ld > 8192 (the 64 k token head): ONE ROW PER CLUSTER of 8 CTAs x 4 warps, persistent.  Every warp owns
+// a contiguous piece of the row (kVec x 512 bytes) and streams its pieces of the cluster's rows through a private ring of
+// CE_BUFS shared-memory slots: 1-D bulk copies in (cp.async.bulk + mbarrier, issued by lane 0 one row ahead), three passes
+// over the slot from shared memory (maximum, sum of exponentials, gradient written back in place), one bulk copy out — so
+// the logits cross HBM exactly once each way, nothing is re-read from L2, and the bytes in flight do not depend on
+// registers.  Per row every warp reduces its own (max, sum) with shuffles, lane 0 writes the pair into slot
+// [rank * 4 + warp] of all eight CTAs (st.shared::cluster), ONE cluster barrier publishes the 32 pairs and every warp merges
+// them itself (one pair per lane).  The pair slots alternate between two sets by row parity, so that one barrier per row is
+// enough: a CTA writes set p again only after every peer has passed the barrier of the row in between, i.e. has read set p.
+// What this replaces: one CTA per row, three passes with one 16-byte load per thread in flight (816 us for the 2.92 GB of
+// the 64 000-wide head = 3.6 TB/s).  Measured on the way (profiles/ce_bench.py, -D variants, same box): a register-resident
+// one-shot cluster per row 580 - 645 us (each generation of CTAs loads, computes and stores in lock-step; made persistent
+// its spills fell out of L1: 1.1 ms); this kernel 594 us = 4.9 TB/s; refilling the ring at the top of the row / before the
+// barrier instead of after it 641 / 690; 256-thread CTAs 641; three slots with 4 resident CTAs 720; 1 / 2 / 3 of 4 gradient
+// exponentials on the FMA pipe 583 / 595 / 627; with NO exponentials at all 530 — the skeleton (bulk copies both ways + one
+// cluster barrier per row), not the MUFU, sets the time.
+#ifndef PLB_CE_THREADS
+#define PLB_CE_THREADS 128
+#endif
+constexpr int CE_CLUSTER = 8, CE_THREADS = PLB_CE_THREADS, CE_WARPS = CE_THREADS / 32;
+#ifndef PLB_CE_BUFS
+#define PLB_CE_BUFS 2      // ring slots per warp (16 KB per CTA and slot at kVec = 8)
+#endif
+#ifndef PLB_CE_ISSUE_AT
+#define PLB_CE_ISSUE_AT 2  // where lane 0 refills the ring: 0 = top of the row, 1 = before the cluster barrier, 2 = after it
+#endif
+#ifndef PLB_CE_MINB
+#define PLB_CE_MINB 6      // resident CTAs per SM the register budget is cut for (6 x 33 KB of shared memory fit)
+#endif
+constexpr int CE_BUFS = PLB_CE_BUFS;
+__device__ __forceinline__ void st_cluster_f32x2(uint32_t cluster_addr, float a, float b) {
+  asm volatile("st.shared::cluster.v2.f32 [%0], {%1, %2};" ::"r"(cluster_addr), "f"(a), "f"(b) : "memory");
+}
+#ifndef PLB_CE_POLY
+#define PLB_CE_POLY 0      // pairs per 16-byte word (of 4) whose GRADIENT exponentials run on the FMA pipe instead of the MUFU
+#endif
+// 2^x on a pair without the MUFU: 2^n p(f), n = round(x), f = x - n in [-0.5, 0.5], cubic p (relative error 8e-5; the
+// result is rounded to bf16, 2e-3); x clamped to >= -126 so that the exponent arithmetic stays in range
+__device__ __forceinline__ f32x2 ex2_poly3_x2(f32x2 x) {
+  float lo, hi;
+  f2_unpack(x, lo, hi);
+  const f32x2 xc = f2_pack(fmaxf(lo, -126.f), fmaxf(hi, -126.f));
+  const f32x2 tt = f2_add(xc, f2_splat(12582912.f));                 // low mantissa bits = n
+  const f32x2 ff = f2_add(xc, f2_mul(f2_add(tt, f2_splat(-12582912.f)), f2_splat(-1.f)));
+  f32x2 pp = f2_fma(ff, f2_splat(0.05508868396282196f), f2_splat(0.24260404706001282f));
+  pp = f2_fma(pp, ff, f2_splat(0.6932762265205383f));
+  pp = f2_fma(pp, ff, f2_splat(0.9999289512634277f));
+  float p0, p1, t0, t1;
+  f2_unpack(pp, p0, p1);
+  f2_unpack(tt, t0, t1);
+  return f2_pack(__uint_as_float(__float_as_uint(p0) + (__float_as_uint(t0) << 23)),
+                 __uint_as_float(__float_as_uint(p1) + (__float_as_uint(t1) << 23)));
+}
+// e[q] = 2^(z log2e + nm2) on pairs; the last kPoly pairs of the word on the FMA pipe
+template <int kPoly = 0>
+__device__ __forceinline__ void ce_word_exp(const uint4& v, f32x2 l2e, f32x2 nm2, f32x2 (&e)[4]) {
+  const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const f32x2 x = f2_fma(f2_from_bf16x2(w[q]), l2e, nm2);
+    if (q >= 4 - kPoly) {
+      e[q] = ex2_poly3_x2(x);
+    } else {
+      float lo, hi;
+      f2_unpack(x, lo, hi);
+      e[q] = f2_pack(ex2_fast(lo), ex2_fast(hi));
+    }
+  }
+}
+
+template <int kVec>   // 16-byte words per lane and row
+__global__ void __cluster_dims__(CE_CLUSTER, 1, 1) __launch_bounds__(CE_THREADS, kVec * CE_WARPS <= 32 ? PLB_CE_MINB : 3)
+masked_ce_cluster_kernel(__nv_bfloat16* __restrict__ logits, int ld, int M, int V, const int32_t* __restrict__ labels,
+                         const float* __restrict__ weights, float* __restrict__ row_loss) {
+  extern __shared__ __align__(128) uint8_t ce_smem[];             // [warp][slot][kVec * 512 bytes]
+  __shared__ uint64_t bars[CE_WARPS][CE_BUFS];
+  __shared__ float2 s_part[2][CE_CLUSTER * CE_WARPS];
+  constexpr float kLog2e = 1.4426950408889634f;
+  constexpr int kPiece = kVec * 32;                               // 16-byte words per warp and row
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t rank = cluster_ctarank();
+  const int nclusters = gridDim.x / CE_CLUSTER;
+  const int first_row = blockIdx.x / CE_CLUSTER;
+  const int nvec = ld >> 3;                                       // ld % 8 == 0 (checked by the caller)
+  const int w0 = (static_cast<int>(rank) * CE_WARPS + warp) * kPiece;            // the warp's first word of a row
+  const int nwords = nvec - w0 < 0 ? 0 : (nvec - w0 < kPiece ? nvec - w0 : kPiece);   // ... and how many exist (<= kPiece)
+  const int j_first = w0 * 8;                                     // first column of the piece
+  const bool full = j_first + kPiece * 8 <= V;                    // no column of the piece is padding (warp-uniform)
+  const uint32_t ring = smem_u32(ce_smem) + static_cast<uint32_t>(warp) * CE_BUFS * kPiece * 16;
+  uint64_t* bar = bars[warp];
+  auto issue = [&](int it) {   // lane 0: slot it % CE_BUFS <- the warp's piece of the cluster's it-th row
+    const long m = first_row + static_cast<long>(it) * nclusters;
+    if (m < M && nwords > 0) {
+      const int st = it % CE_BUFS;
+      mbar_arrive_expect_tx(&bar[st], static_cast<uint32_t>(nwords) * 16);
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                       ring + st * kPiece * 16),
+                   "l"(reinterpret_cast<const uint4*>(logits + m * ld) + w0), "r"(nwords * 16), "r"(smem_u32(&bar[st]))
+                   : "memory");
+    }
+  };
+  if (lane == 0) {
+    for (int i = 0; i < CE_BUFS; ++i) mbar_init(&bar[i], 1);
+    fence_mbar_init();
+    for (int i = 0; i < CE_BUFS - 1; ++i) issue(i);
+  }
+  __syncwarp();
+  const f32x2 l2e = f2_splat(kLog2e);
+  int it = 0;
+  for (int m = first_row; m < M; m += nclusters, ++it) {
+    const int st = it % CE_BUFS;
+    const uint32_t piece = ring + st * kPiece * 16;               // column k of the piece: piece + 2 k
+    const uint32_t slot = piece + lane * 16;                      // word i of this lane: slot + i * 512 (conflict-free)
+    int y = labels[m];
+    const bool y_ok = y >= 0 && y < V;
+    const float wgt = y_ok ? weights[m] : 0.f;   // a label outside [0, V): no loss and no gradient for the row
+    if (!y_ok && rank == 0 && tid == 0) row_loss[m] = 0.f;
+    const int ky = y_ok ? y - j_first : -1;      // the label's column inside this warp's piece, if it is there
+    const bool mine = ky >= 0 && ky < nwords * 8;
+    auto refill = [&]() {
+      // the slot the row after this one goes to was handed to a bulk store CE_BUFS - 1 iterations ago: wait until it has been read
+      if (lane == 0) {
+        bulk_wait_read<CE_BUFS - 2>();
+        issue(it + CE_BUFS - 1);
+      }
+      __syncwarp();
+    };
+    if (PLB_CE_ISSUE_AT == 0) refill();
+    if (nwords > 0) mbar_wait(&bar[st], static_cast<uint32_t>(it / CE_BUFS) & 1);
+    float zy = 0.f;
+    if (mine && lane == 0) {
+      uint16_t bits;
+      asm volatile("ld.shared.u16 %0, [%1];" : "=h"(bits) : "r"(piece + 2 * ky));
+      zy = __uint_as_float(static_cast<uint32_t>(bits) << 16);
+    }
+    // ---- warp-local maximum ----
+    float mx = -INFINITY;
+    if (full) {
+#pragma unroll
+      for (int i = 0; i < kVec; ++i) {
+        const uint4 v = lds128(slot + i * 512);
+        mx = max3(mx, bf16_lo(v.x), bf16_hi(v.x));
+        mx = max3(mx, bf16_lo(v.y), bf16_hi(v.y));
+        mx = max3(mx, bf16_lo(v.z), bf16_hi(v.z));
+        mx = max3(mx, bf16_lo(v.w), bf16_hi(v.w));
+      }
+    } else {
+      for (int i = 0; i < kVec; ++i) {
+        const int j0 = j_first + (lane + 32 * i) * 8;
+        if (j0 >= V) break;
+        const uint4 v = lds128(slot + i * 512);
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          if (j0 + 2 * q < V) mx = fmaxf(mx, bf16_lo(w[q]));
+          if (j0 + 2 * q + 1 < V) mx = fmaxf(mx, bf16_hi(w[q]));
+        }
+      }
+    }
+    mx = warp_max(mx);
+    const float nm2s = mx == -INFINITY ? 0.f : -mx * kLog2e;       // a warp without a valid column contributes (-inf, 0)
+    // ---- warp-local sum of exponentials (relative to the warp's maximum) ----
+    float se;
+    {
+      const f32x2 nm2 = f2_splat(nm2s);
+      f32x2 acc[2] = {f2_splat(0.f), f2_splat(0.f)};
+      if (full) {
+#pragma unroll
+        for (int i = 0; i < kVec; ++i) {
+          f32x2 e[4];
+          ce_word_exp(lds128(slot + i * 512), l2e, nm2, e);
+          acc[0] = f2_add(acc[0], f2_add(e[0], e[1]));
+          acc[1] = f2_add(acc[1], f2_add(e[2], e[3]));
+        }
+      } else {
+        for (int i = 0; i < kVec; ++i) {
+          const int j0 = j_first + (lane + 32 * i) * 8;
+          if (j0 >= V) break;
+          f32x2 e[4];
+          ce_word_exp(lds128(slot + i * 512), l2e, nm2, e);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            float lo, hi;
+            f2_unpack(e[q], lo, hi);
+            acc[q & 1] = f2_add(acc[q & 1], f2_pack(j0 + 2 * q < V ? lo : 0.f, j0 + 2 * q + 1 < V ? hi : 0.f));
+          }
+        }
+      }
+      float s0, s1;
+      f2_unpack(f2_add(acc[0], acc[1]), s0, s1);
+      se = warp_sum(s0 + s1);
+    }
+    if (lane == 0) {
+      const uint32_t own = smem_u32(&s_part[it & 1][rank * CE_WARPS + warp]);
+#pragma unroll
+      for (uint32_t r = 0; r < CE_CLUSTER; ++r) st_cluster_f32x2(mapa_u32(own, r), mx, se);
+    }
+    if (PLB_CE_ISSUE_AT == 1) refill();
+    cluster_sync_all();   // release / acquire: the 32 pairs of this row are visible everywhere
+    if (PLB_CE_ISSUE_AT == 2) refill();
+    float row_max = -INFINITY, row_se = 0.f;
+    {
+      float2 part[CE_CLUSTER * CE_WARPS / 32];
+#pragma unroll
+      for (int i = 0; i < CE_CLUSTER * CE_WARPS / 32; ++i) {
+        part[i] = s_part[it & 1][lane + 32 * i];
+        row_max = fmaxf(row_max, part[i].x);
+      }
+      row_max = warp_max(row_max);                                 // finite: V >= 1
+#pragma unroll
+      for (int i = 0; i < CE_CLUSTER * CE_WARPS / 32; ++i) row_se += part[i].y * ex2_fast((part[i].x - row_max) * kLog2e);
+      row_se = warp_sum(row_se);
+    }
+    if (nwords > 0) {
+      // ---- gradient, in place in the slot: w * (softmax - onehot); columns [V, ld) are zeroed for the GEMMs that read them ----
+      const float invs = wgt / row_se, nrm2s = -row_max * kLog2e;
+      const f32x2 inv = f2_splat(invs), nrm2 = f2_splat(nrm2s);
+      if (full) {
+#pragma unroll
+        for (int i = 0; i < kVec; ++i) {
+          f32x2 e[4];
+          ce_word_exp<PLB_CE_POLY>(lds128(slot + i * 512), l2e, nrm2, e);
+          sts128(slot + i * 512, make_uint4(f2_to_bf16x2(f2_mul(e[0], inv)), f2_to_bf16x2(f2_mul(e[1], inv)),
+                                            f2_to_bf16x2(f2_mul(e[2], inv)), f2_to_bf16x2(f2_mul(e[3], inv))));
+        }
+      } else {
+        for (int i = 0; i < kVec; ++i) {
+          const int j0 = j_first + (lane + 32 * i) * 8;
+          if (lane + 32 * i >= nwords) break;
+          f32x2 e[4];
+          ce_word_exp(lds128(slot + i * 512), l2e, nrm2, e);
+          uint32_t o[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            float lo, hi;
+            f2_unpack(f2_mul(e[q], inv), lo, hi);
+            o[q] = pack_bf16x2(j0 + 2 * q < V ? lo : 0.f, j0 + 2 * q + 1 < V ? hi : 0.f);
+          }
+          sts128(slot + i * 512, make_uint4(o[0], o[1], o[2], o[3]));
+        }
+      }
+      __syncwarp();
+      if (mine && lane == 0) {   // the label's entry: w * (softmax - 1); the loss from the logit read before the overwrite
+        row_loss[m] = wgt * (__logf(row_se) + row_max - zy);
+        const float gy = ex2_fast(fmaf(zy, kLog2e, nrm2s)) * invs - wgt;
+        asm volatile("st.shared.u16 [%0], %1;" ::"r"(piece + 2 * ky), "h"(__bfloat16_as_ushort(__float2bfloat16(gy))) : "memory");
+      }
+      fence_proxy_async_smem();   // every lane: its writes to the slot become visible to the bulk-copy engine
+      __syncwarp();
+      if (lane == 0) {
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(
+                         reinterpret_cast<uint4*>(logits + static_cast<size_t>(m) * ld) + w0),
+                     "r"(piece), "r"(nwords * 16)
+                     : "memory");
+        bulk_commit();
+      }
+    }
+  }
+  if (lane == 0) bulk_wait<0>();   // the last stores have left shared memory and are performed before the CTA retires
+}
+
+// Wide rows the cluster kernel does not take (ld <= 8192, ld > 131072 or an unaligned buffer): one CTA per row, 16-byte accesses.  Pass 1 streams the row from HBM, passes 2
 // and 3 re-read it from L1/L2 (a 64 k row is 128 KB), so the traffic is one read and one write of the logits.
 __global__ void __launch_bounds__(256)
 masked_ce_wide_kernel(__nv_bfloat16* __restrict__ logits, int ld, int M, int V, const int32_t* __restrict__ labels,
@@ -270,7 +531,36 @@ extern "C" int plb_masked_ce(void* logits, int ld, int M, int V, const int32_t* 
   __nv_bfloat16* z = static_cast<__nv_bfloat16*>(logits);
   if (V <= 2048)
     masked_ce_kernel<32><<<(M + 7) / 8, 256, 0, stream>>>(z, ld, M, V, labels, weights, row_loss);
-  else
+  else if (ld > 8192 && ld <= 16 * 8192 && ld % 8 == 0 && (reinterpret_cast<uintptr_t>(z) & 15) == 0) {
+    const int per_thread = (ld / 8 + CE_CLUSTER * CE_THREADS - 1) / (CE_CLUSTER * CE_THREADS);   // 16-byte words per thread
+    auto kern = per_thread <= 2 ? masked_ce_cluster_kernel<2> : per_thread <= 4 ? masked_ce_cluster_kernel<4>
+              : per_thread <= 8 ? masked_ce_cluster_kernel<8> : masked_ce_cluster_kernel<16>;
+    const int kv = per_thread <= 2 ? 2 : per_thread <= 4 ? 4 : per_thread <= 8 ? 8 : 16;
+    const int smem = CE_WARPS * CE_BUFS * kv * 512;
+    static int cached[4] = {0, 0, 0, 0};   // resident clusters per kernel instantiation (a property of the device + binary)
+    int& resident = cached[kv == 2 ? 0 : kv == 4 ? 1 : kv == 8 ? 2 : 3];
+    if (resident == 0) {
+      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+      PLB_REQUIRE(e == cudaSuccess, PLB_ERR_CUDA, "masked_ce: cudaFuncSetAttribute(smem=%d): %s", smem, cudaGetErrorString(e));
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(CE_CLUSTER * sm_count(), 1, 1);
+      cfg.blockDim = dim3(CE_THREADS, 1, 1);
+      cfg.dynamicSmemBytes = smem;
+      cudaLaunchAttribute attr;
+      attr.id = cudaLaunchAttributeClusterDimension;
+      attr.val.clusterDim.x = CE_CLUSTER;
+      attr.val.clusterDim.y = attr.val.clusterDim.z = 1;
+      cfg.attrs = &attr;
+      cfg.numAttrs = 1;
+      int n = 0;
+      e = cudaOccupancyMaxActiveClusters(&n, kern, &cfg);
+      PLB_REQUIRE(e == cudaSuccess && n >= 1, PLB_ERR_CUDA, "masked_ce: cluster occupancy query failed: %s", cudaGetErrorString(e));
+      resident = n;
+    }
+    int nclusters = resident;
+    if (nclusters > M) nclusters = M;
+    kern<<<nclusters * CE_CLUSTER, CE_THREADS, smem, stream>>>(z, ld, M, V, labels, weights, row_loss);
+  } else
     masked_ce_wide_kernel<<<M, 256, 0, stream>>>(z, ld, M, V, labels, weights, row_loss);
   int rc = check_launch("plb_masked_ce");
   if (rc) return rc;
