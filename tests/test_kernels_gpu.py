@@ -539,7 +539,8 @@ def test_gather_scatter_bit_exact(dev):
     assert (acc[0] == 4).all() and not acc[1:].any()
 
 
-@pytest.mark.parametrize("M,V", [(1000, 188), (37, 97), (300, 5000), (300, 5003), (200, 64000), (151, 65536), (40, 70000)])
+@pytest.mark.parametrize("M,V", [(1000, 188), (37, 97), (300, 5000), (300, 5003), (200, 64000), (151, 65536), (40, 70000),
+                                 (5, 9001), (300, 40003), (1, 64000), (1300, 16385), (3, 131072), (2, 131075)])
 def test_masked_ce(dev, M, V):
     ld = (V + 7) // 8 * 8
     z = torch.zeros(M, ld, device=dev, dtype=BF)
@@ -562,6 +563,28 @@ def test_masked_ce(dev, M, V):
     assert abs(loss.item() - (ref_rows.sum().item() + (w * math.log(V)).sum().item())) < 1e-4
     call("plb_masked_ce", ptr(z2), ld, 0, V, ptr(labels), ptr(w), ptr(row_loss), ptr(loss), 0, S())  # empty -> 0
     assert loss.item() == 0.0
+
+
+@pytest.mark.parametrize("M,V", [(64, 188), (64, 5003), (130, 64000), (9, 9001)])
+def test_masked_ce_label_outside_vocabulary(dev, M, V):
+    """A label outside [0, V) contributes neither loss nor gradient (every kernel variant: warp-per-row, CTA-per-row, cluster)."""
+    ld = (V + 7) // 8 * 8
+    z = torch.zeros(M, ld, device=dev, dtype=BF)
+    z[:, :V] = (torch.randn(M, V, device=dev) * 2).to(BF)
+    labels = torch.randint(0, V, (M,), device=dev, dtype=torch.int32)
+    bad = torch.arange(M, device=dev) % 3 == 1
+    labels[bad] = torch.where(torch.arange(M, device=dev)[bad] % 2 == 0, torch.tensor(V, device=dev), torch.tensor(-1, device=dev)).int()
+    w = torch.rand(M, device=dev) / M
+    zf = z[:, :V].float().requires_grad_(True)
+    safe = labels.long().clamp(0, V - 1)
+    ref_rows = torch.nn.functional.cross_entropy(zf, safe, reduction="none") * w * (~bad)
+    ref_rows.sum().backward()
+    row_loss = torch.full((M,), 9.0, device=dev)
+    loss = torch.zeros(1, device=dev)
+    call("plb_masked_ce", ptr(z), ld, M, V, ptr(labels), ptr(w), ptr(row_loss), ptr(loss), 0, S())
+    assert rel(row_loss, ref_rows) < 1e-5
+    assert (row_loss[bad] == 0).all() and not z[bad].any()
+    assert rel(z[:, :V].float(), zf.grad) < 6e-3
 
 
 @pytest.mark.parametrize("T,N", [(3000, 2304), (100, 188), (98304, 768)])
