@@ -41,6 +41,11 @@ int plb_abi_version(void);
 const char* plb_last_error_string(void);
 /* Number of SMs of the current device (148 on B200); <0 on error. */
 int plb_device_sm_count(void);
+/* Programmatic dependent launch for the kernels of one stream (default: enabled).  The reference's step is a chain of
+ * ~1000 stream-ordered library kernels (R/train.py:353-357); here the ~260 kernels of a step are launched so that the
+ * next kernel's CTAs take over an SM the moment the previous kernel's CTA leaves it (their prologue runs before
+ * griddepcontrol.wait).  Results are identical either way.  Process-wide; returns PLB_OK. */
+int plb_set_launch_overlap(int enable);
 
 /* ---- a1: key-padding mask --------------------------------------------------------------------
  * R/train.py:34-44 length_to_mask + R/train.py:386 `(~mask).int()`:

@@ -70,6 +70,10 @@ int check_launch(const char* what) {
   return PLB_OK;
 }
 
+static int g_launch_overlap = 1;
+bool launch_overlap_enabled() { return g_launch_overlap != 0; }
+void set_launch_overlap(int on) { g_launch_overlap = on ? 1 : 0; }
+
 int sm_count() {
   static int n = 0;
   if (n == 0) {
@@ -168,6 +172,11 @@ using namespace plb;
 
 extern "C" int plb_abi_version(void) { return PLB_ABI_VERSION; }
 extern "C" const char* plb_last_error_string(void) { return g_error; }
+extern "C" int plb_set_launch_overlap(int enable) {
+  plb::set_launch_overlap(enable);
+  return PLB_OK;
+}
+
 extern "C" int plb_device_sm_count(void) {
   int dev = 0, n = 0;
   if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) {

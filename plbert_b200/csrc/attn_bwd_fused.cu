@@ -231,6 +231,7 @@ attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_c
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  pdl_grid_sync();   // the prologue above is CTA-local; everything below reads / writes global memory
   // TMEM columns: S^T [0,128)  dP^T [128,256)  P^T bf16 pairs [256,320)  dK [320,384)  dV [384,448)  dQ [448,512)
 
   if (warp < 4) {
@@ -762,14 +763,10 @@ static int attn_bwd_fused_launch(const void* qkv, int ld_qkv, const int32_t* seq
              1.f / sqrtf((float)head_dim)};
   const int n_items = B * heads, sms = sm_count();
   const int grid = n_items < sms ? n_items : sms;
-  if (drop.thresh16 != 0)
-    attn_bwd_fused_kernel<true><<<grid, FB_THREADS, FbSmem::kAlloc, stream>>>(
-        tm_qkv, tm_dctx, p, n_items, lse2, delta, static_cast<__nv_bfloat16*>(dqkv), ld_dqkv, dbias_qkv_accum,
-        static_cast<float*>(workspace), drop);
-  else
-    attn_bwd_fused_kernel<false><<<grid, FB_THREADS, FbSmem::kAlloc, stream>>>(
-        tm_qkv, tm_dctx, p, n_items, lse2, delta, static_cast<__nv_bfloat16*>(dqkv), ld_dqkv, dbias_qkv_accum,
-        static_cast<float*>(workspace), drop);
+  cudaError_t le = launch_kernel(drop.thresh16 != 0 ? attn_bwd_fused_kernel<true> : attn_bwd_fused_kernel<false>, dim3(grid),
+                                 dim3(FB_THREADS), FbSmem::kAlloc, stream, tm_qkv, tm_dctx, p, n_items, lse2, delta,
+                                 static_cast<__nv_bfloat16*>(dqkv), ld_dqkv, dbias_qkv_accum, static_cast<float*>(workspace), drop);
+  PLB_REQUIRE(le == cudaSuccess, PLB_ERR_CUDA, "plb_attn_bwd_fused: launch failed: %s", cudaGetErrorString(le));
   return check_launch("plb_attn_bwd_fused");
 }
 

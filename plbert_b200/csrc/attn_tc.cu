@@ -184,6 +184,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  pdl_grid_sync();   // the prologue above is CTA-local; everything below reads / writes global memory
   // TMEM columns per group g (stride 256): S [+0, +128), O [+128, +64), P as packed bf16 pairs [+192, +64)
 
   if (warp < 4) {
@@ -611,12 +612,10 @@ static int attn_fwd_launch(const void* qkv, int ld_qkv, const int32_t* seq_start
                  1.f / sqrtf((float)head_dim)};
   const int n_items = B * heads, sms = sm_count();
   const int grid = n_items < sms ? n_items : sms;
-  if (drop.thresh16 != 0)
-    attn_fwd_tc_kernel<true><<<grid, NUM_THREADS, FwdSmem::kAlloc, static_cast<cudaStream_t>(stream)>>>(
-        tm, tm_ctx, p, n_items, static_cast<__nv_bfloat16*>(ctx), ld_ctx, lse2, drop);
-  else
-    attn_fwd_tc_kernel<false><<<grid, NUM_THREADS, FwdSmem::kAlloc, static_cast<cudaStream_t>(stream)>>>(
-        tm, tm_ctx, p, n_items, static_cast<__nv_bfloat16*>(ctx), ld_ctx, lse2, drop);
+  cudaError_t le = launch_kernel(drop.thresh16 != 0 ? attn_fwd_tc_kernel<true> : attn_fwd_tc_kernel<false>, dim3(grid),
+                                 dim3(NUM_THREADS), FwdSmem::kAlloc, static_cast<cudaStream_t>(stream), tm, tm_ctx, p, n_items,
+                                 static_cast<__nv_bfloat16*>(ctx), ld_ctx, lse2, drop);
+  PLB_REQUIRE(le == cudaSuccess, PLB_ERR_CUDA, "plb_attn_fwd_tc: launch failed: %s", cudaGetErrorString(le));
   return check_launch("plb_attn_fwd_tc");
 }
 

@@ -36,6 +36,31 @@ bool tensor_map_bf16(CUtensorMap* out, const void* base, uint64_t rows, uint64_t
 
 int sm_count();
 
+// Programmatic dependent launch (include/plbert_b200.h: plb_set_launch_overlap).  When enabled, the hot kernels are launched
+// with cudaLaunchAttributeProgrammaticStreamSerialization: a kernel's CTAs may become resident while the previous kernel of
+// the stream drains, run their prologue (barrier init, TMEM allocation, descriptor prefetch) and then block in
+// griddepcontrol.wait until that kernel has COMPLETED and its writes are visible.  Every kernel launched this way executes
+// pdl_grid_sync() before its first global access; kernels launched without the attribute treat it as a no-op.
+bool launch_overlap_enabled();
+void set_launch_overlap(int on);
+
+#if defined(__CUDACC__)
+template <typename... KArgs, typename... Args>
+cudaError_t launch_kernel(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = launch_overlap_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+#endif
+
 // attn_tc.cu: delta[h, row] = sum_d dO[row, h*64 + d] * O[row, h*64 + d]  (enqueue only)
 int launch_attn_delta(const void* dctx, const void* ctx, int ld_ctx, int total_rows, int heads, float* delta,
                       cudaStream_t stream);
@@ -44,6 +69,14 @@ int launch_attn_delta(const void* dctx, const void* ctx, int ld_ctx, int total_r
 // Device side
 // ----------------------------------------------------------------------------------------------
 #if defined(__CUDACC__)
+
+// ---- programmatic dependent launch ------------------------------------------------------------
+// launch_dependents first: the next kernel of the stream may be scheduled as soon as every CTA of this grid has got here
+// (it still blocks in ITS griddepcontrol.wait until this grid has completed); then wait for the previous grid.
+__device__ __forceinline__ void pdl_grid_sync() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+}
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));

@@ -194,6 +194,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CU
   if (kCta == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  pdl_grid_sync();   // everything above touched only this CTA's shared / tensor memory; operands and outputs are global
 
   if (warp == 0) {
     // =========================== TMA producer ===========================
@@ -604,13 +605,15 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, 
   cfg.blockDim = dim3(NUM_THREADS);
   cfg.dynamicSmemBytes = L::kAlloc;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = kCta;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = launch_overlap_enabled() ? 2 : 1;
   cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ta, tb, tc, tin, tout, p);
   PLB_REQUIRE(e == cudaSuccess, PLB_ERR_CUDA, "plb_gemm_bf16: launch failed: %s", cudaGetErrorString(e));
   return check_launch("plb_gemm_bf16");

@@ -444,6 +444,7 @@ __global__ void sum_rows_kernel(const float* __restrict__ v, int n, float* __res
 __global__ void __launch_bounds__(256) colsum_kernel(const __nv_bfloat16* __restrict__ x, int ld, int T, int N,
                                                      float* __restrict__ out) {
   __shared__ float s[8][256];
+  pdl_grid_sync();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int col = blockIdx.x * 256 + lane * 8;
   float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
@@ -575,7 +576,8 @@ extern "C" int plb_colsum(const void* x, int ld, int T, int N, float* out_accum,
   const int gx = (N + 255) / 256;
   int gy = (8 * sm_count() + gx - 1) / gx;
   if (gy > (T + 7) / 8) gy = (T + 7) / 8;
-  colsum_kernel<<<dim3(gx, gy), 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const __nv_bfloat16*>(x), ld, T, N,
-                                                                            out_accum);
+  cudaError_t e = launch_kernel(colsum_kernel, dim3(gx, gy), dim3(256), 0, static_cast<cudaStream_t>(stream),
+                                static_cast<const __nv_bfloat16*>(x), ld, T, N, out_accum);
+  PLB_REQUIRE(e == cudaSuccess, PLB_ERR_CUDA, "plb_colsum: launch failed: %s", cudaGetErrorString(e));
   return check_launch("plb_colsum");
 }

@@ -36,6 +36,7 @@ __global__ void __launch_bounds__(WARPS * 32) ln_fwd_kernel(const __nv_bfloat16*
                                                             float eps, __nv_bfloat16* __restrict__ y,
                                                             float* __restrict__ stats) {
   extern __shared__ __align__(128) uint8_t ln_smem[];
+  pdl_grid_sync();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int nchunk = H >> 3;
   const uint32_t row_bytes = static_cast<uint32_t>(H) * 2;
@@ -146,6 +147,7 @@ ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restr
               __nv_bfloat16* __restrict__ dz, float* __restrict__ dw_acc, float* __restrict__ db_acc,
               float* __restrict__ colsum_acc) {
   extern __shared__ __align__(128) uint8_t ln_smem[];
+  pdl_grid_sync();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int nchunk = H >> 3;
   const uint32_t row_bytes = static_cast<uint32_t>(H) * 2;
@@ -480,8 +482,9 @@ extern "C" int plb_ln_fwd(const void* z, int T, int H, const float* w, const flo
   int per_sm = 1;   // resident CTAs per SM (registers and shared memory): the grid is persistent
   e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, WARPS * 32, smem);
   PLB_REQUIRE(e == cudaSuccess && per_sm >= 1, PLB_ERR_CUDA, "ln_fwd: occupancy query failed: %s", cudaGetErrorString(e));
-  kern<<<row_grid(T, per_sm), WARPS * 32, smem, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const __nv_bfloat16*>(z), T, H, w, b, eps, static_cast<__nv_bfloat16*>(y), stats);
+  e = launch_kernel(kern, dim3(row_grid(T, per_sm)), dim3(WARPS * 32), smem, static_cast<cudaStream_t>(stream),
+                    static_cast<const __nv_bfloat16*>(z), T, H, w, b, eps, static_cast<__nv_bfloat16*>(y), stats);
+  PLB_REQUIRE(e == cudaSuccess, PLB_ERR_CUDA, "plb_ln_fwd: launch failed: %s", cudaGetErrorString(e));
   return check_launch("plb_ln_fwd");
 }
 
@@ -506,9 +509,10 @@ extern "C" int plb_ln_bwd(const void* dy, const void* z, const float* stats, con
   e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, BWD_WARPS * 32, smem);
   PLB_REQUIRE(e == cudaSuccess && per_sm >= 1, PLB_ERR_CUDA, "ln_bwd: occupancy query failed: %s", cudaGetErrorString(e));
   const int need = (T + BWD_WARPS - 1) / BWD_WARPS, cap = sm_count() * per_sm;
-  kern<<<need < cap ? need : cap, BWD_WARPS * 32, smem, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const __nv_bfloat16*>(dy), static_cast<const __nv_bfloat16*>(z), stats, w, T, H,
-      static_cast<__nv_bfloat16*>(dz), dw_accum, db_accum, colsum_accum);
+  e = launch_kernel(kern, dim3(need < cap ? need : cap), dim3(BWD_WARPS * 32), smem, static_cast<cudaStream_t>(stream),
+                    static_cast<const __nv_bfloat16*>(dy), static_cast<const __nv_bfloat16*>(z), stats, w, T, H,
+                    static_cast<__nv_bfloat16*>(dz), dw_accum, db_accum, colsum_accum);
+  PLB_REQUIRE(e == cudaSuccess, PLB_ERR_CUDA, "plb_ln_bwd: launch failed: %s", cudaGetErrorString(e));
   return check_launch("plb_ln_bwd");
 }
 

@@ -271,6 +271,40 @@ def test_token_head_over_all_valid_positions(dev, packed):
     assert abs(got - t2) <= 2e-2 * abs(t2) and abs(t2 - l2["token_predictor"]) < 1e-12
 
 
+def test_launch_overlap_does_not_change_results(dev):
+    """plb_set_launch_overlap: with programmatic dependent launch the next kernel's CTAs start under the previous kernel's tail
+    and block in griddepcontrol.wait before their first global access — same loss, same gradients, same weights after AdamW
+    as with plain stream-ordered launches (only the fp32 atomics' summation order may differ)."""
+    import plbert_b200 as P
+    from plbert_b200._abi import call
+    from plbert_b200.batch import synthetic_collate_batch
+    cfgv = [188, 32, 128, 2, 256, 4, 128, 211]
+    batches = [synthetic_collate_batch(6, 128, seed=30 + i, variable_length=bool(i), min_length=9, with_token_ids=True,
+                                       num_tokens=211, word_pred_prob=0.25) for i in range(2)]
+    out = {}
+    try:
+        for on in (0, 1):
+            call("plb_set_launch_overlap", on)
+            model = build_model(cfgv, True, dev, seed=5)
+            opt = P.FusedAdamW(model.parameters(), lr=1e-5)   # small steps: elements at the summation-noise floor may step either way
+            losses = []
+            for step in range(4):
+                losses.append(model.loss_and_backward(batches[step % 2]).item())
+                if step == 0:
+                    grads = {n: p.grad.detach().float().clone() for n, p in model.named_parameters() if p.grad is not None}
+                opt.step()
+            torch.cuda.synchronize()
+            out[on] = (losses, grads, {n: p.detach().float().clone() for n, p in model.named_parameters()})
+    finally:
+        call("plb_set_launch_overlap", 1)
+    for a, b in zip(out[0][0], out[1][0]):
+        assert abs(a - b) <= 1e-4 * abs(a), (out[0][0], out[1][0])
+    for n, g in out[0][1].items():
+        assert (out[1][1][n] - g).abs().max().item() <= 2e-3 * g.abs().max().item() + 1e-7, n
+    for n, w in out[0][2].items():
+        assert (out[1][2][n] - w).abs().max().item() <= 5e-3 * w.abs().max().item() + 1e-6, n
+
+
 def test_packed_layout_equals_padded_layout(dev):
     """Variable-length batches run without their padding rows.  The reference computes the padded
     rows and never reads them, so loss and gradients must not change; only the fp32 summation order of the weight
