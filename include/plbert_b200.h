@@ -93,6 +93,21 @@ int plb_gemm_bf16(int op, int epilogue, int M, int N, int K,
                   void* aux_out, int ld_aux_out,
                   plb_stream_t stream);
 
+/* ---- (e): weight gradient + its data-parallel all-reduce in ONE kernel -------------------------
+ * R/train.py:160,218-221: DistributedDataParallel all-reduces every gradient bucket with NCCL after the
+ * kernels that produced it.  For the large head (64 000 x 768 fp32 = 197 MB) this call IS the collective:
+ * the same WGRAD as plb_gemm_bf16(PLB_GEMM_WGRAD, ...), but C_multicast is the NVSwitch MULTICAST address of
+ * a buffer that every rank of the node has mapped (CUDA multicast object / torch symmetric memory), and the
+ * epilogue accumulates with multimem.red.add.v4.f32 — the switch adds each tile into ALL ranks' copies, so
+ * when every rank's kernel has completed each copy holds the SUM over ranks (no NCCL kernel, no second pass
+ * over the gradient).  The caller orders the ranks (no rank may start adding before every rank has consumed
+ * and zeroed the previous step's sum; readers wait for every rank's kernel).  N % 4 == 0, ldc % 4 == 0,
+ * C_multicast 16-byte aligned. */
+int plb_gemm_wgrad_allreduce(int M, int N, int K,
+                             const void* A, int lda, const void* B, int ldb,
+                             float* C_multicast, int ldc,
+                             plb_stream_t stream);
+
 /* Plain CUDA-core GEMM with the same signature and semantics as plb_gemm_bf16 (fp32 math,
  * one thread per output element).  TEST INFRASTRUCTURE: used by tests/ to cross-check the
  * tensor-core kernel on the device; never called by the product path. */

@@ -34,6 +34,7 @@ SIGNATURES = {
     "plb_length_to_mask": [P, c_int, c_int, P, P],
     "plb_gemm_bf16": _GEMM_ARGS,
     "plb_gemm_bf16_check": _GEMM_ARGS,
+    "plb_gemm_wgrad_allreduce": [c_int, c_int, c_int, P, c_int, P, c_int, P, c_int, P],
     "plb_embed_ln_fwd": [P, P, c_int, c_int, P, P, P, P, P, c_float, P, P, P],
     "plb_embed_ln_bwd": [P, P, P, c_int, c_int, c_int, P, P, P, P, P, c_int, P, P, P, P, P, P],
     "plb_ln_fwd": [P, c_int, c_int, P, P, c_float, P, P, P],

@@ -76,6 +76,7 @@ struct GemmParams {
   int num_units;      // m_tiles * n_tiles * splits (m_tiles counts 128*kCta-row tiles)
   const float* bias;  // [N] or null
   float* c_f32;       // WGRAD output
+  int c_multimem;     // WGRAD: c_f32 is a MULTICAST address (NVSwitch): every add lands in all peers' copies (multimem.red)
   int ldc;
   float* rowdot;      // kRowDot: fp32 [N / 64][rowdot_ld] accumulators of sum_n C[m,n] * aux_in[m,n] per 64-column block
   int rowdot_ld;
@@ -462,7 +463,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CU
 #pragma unroll
             for (int i = 0; i < 32; i += 4) {
               const int n = n0 + c * 32 + i;
-              if (n + 3 < p.N && ((reinterpret_cast<uintptr_t>(dst + i) & 15) == 0)) {
+              if (p.c_multimem) {
+                // gradient all-reduce fused into the WGRAD epilogue: the switch adds the four values into EVERY rank's copy
+                // of the arena (the host checked N % 4 == 0 and the 16-byte alignment for this mode)
+                asm volatile("multimem.red.relaxed.sys.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + i),
+                             "f"(__uint_as_float(v[i])), "f"(__uint_as_float(v[i + 1])),
+                             "f"(__uint_as_float(v[i + 2])), "f"(__uint_as_float(v[i + 3]))
+                             : "memory");
+              } else if (n + 3 < p.N && ((reinterpret_cast<uintptr_t>(dst + i) & 15) == 0)) {
                 asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + i),
                              "f"(__uint_as_float(v[i])), "f"(__uint_as_float(v[i + 1])),
                              "f"(__uint_as_float(v[i + 2])), "f"(__uint_as_float(v[i + 3]))
@@ -629,9 +637,9 @@ using namespace plb;
 // fewer than two 128-row tiles.
 static int pick_ctas(int M) { return M > BM ? 2 : 1; }
 
-extern "C" int plb_gemm_bf16(int op, int epilogue, int M, int N, int K, const void* A, int lda, const void* B,
-                             int ldb, void* C, int ldc, const float* bias, const void* aux_in, int ld_aux_in,
-                             void* aux_out, int ld_aux_out, plb_stream_t stream_) {
+static int gemm_dispatch(int op, int epilogue, int M, int N, int K, const void* A, int lda, const void* B,
+                         int ldb, void* C, int ldc, const float* bias, const void* aux_in, int ld_aux_in,
+                         void* aux_out, int ld_aux_out, plb_stream_t stream_, int c_multimem) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   PLB_REQUIRE(M > 0 && N > 0 && K > 0, PLB_ERR_ARG, "gemm: bad shape M=%d N=%d K=%d", M, N, K);
   PLB_REQUIRE(A && B && C, PLB_ERR_ARG, "gemm: null operand");
@@ -696,6 +704,9 @@ extern "C" int plb_gemm_bf16(int op, int epilogue, int M, int N, int K, const vo
     p.num_units = tiles * p.splits;
     p.c_f32 = static_cast<float*>(C);
     p.ldc = ldc;
+    p.c_multimem = c_multimem;
+    PLB_REQUIRE(!c_multimem || ((N % 4) == 0 && (ldc % 4) == 0 && ((uintptr_t)C % 16) == 0), PLB_ERR_ARG,
+                "gemm: the multicast WGRAD needs N %% 4 == 0, ldc %% 4 == 0 and a 16-byte aligned C");
     tc = tin = tout = ta;
     PLB_LAUNCH(true, true, kAtomicF32, 4, 2, 6, 2);
   }
@@ -749,6 +760,19 @@ extern "C" int plb_gemm_bf16(int op, int epilogue, int M, int N, int K, const vo
 #undef PLB_LAUNCH
   set_error("gemm: op %d does not support epilogue %d", op, epilogue);
   return PLB_ERR_UNSUPPORTED;
+}
+
+extern "C" int plb_gemm_bf16(int op, int epilogue, int M, int N, int K, const void* A, int lda, const void* B,
+                             int ldb, void* C, int ldc, const float* bias, const void* aux_in, int ld_aux_in,
+                             void* aux_out, int ld_aux_out, plb_stream_t stream) {
+  return gemm_dispatch(op, epilogue, M, N, K, A, lda, B, ldb, C, ldc, bias, aux_in, ld_aux_in, aux_out, ld_aux_out, stream, 0);
+}
+
+extern "C" int plb_gemm_wgrad_allreduce(int M, int N, int K, const void* A, int lda, const void* B, int ldb,
+                                        float* C_multicast, int ldc, plb_stream_t stream) {
+  PLB_REQUIRE(C_multicast != nullptr, PLB_ERR_ARG, "gemm_wgrad_allreduce: null multicast address");
+  return gemm_dispatch(PLB_GEMM_WGRAD, PLB_EPI_NONE, M, N, K, A, lda, B, ldb, C_multicast, ldc, nullptr, nullptr, 0, nullptr, 0,
+                       stream, 1);
 }
 
 #ifdef PLB_GEMM_TRACE

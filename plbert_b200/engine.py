@@ -198,6 +198,23 @@ class Engine:
         self.wp = {n: self.shadow.data_ptr() + 2 * o for n, o in lay.offsets.items()}   # bf16 shadow
         self.name_of_ptr = {v: k for k, v in self.pp.items()}                           # fp32 master address -> name
         self.grad_views = {n: self.view(self.grads, n) for n in lay.offsets}            # what p.grad points at
+        # ddp.GradientSynchronizer (NVSwitch multicast available): head weight name -> MULTICAST address of its gradient; the
+        # head's WGRAD then adds into every rank's arena at once (plb_gemm_wgrad_allreduce) and needs no NCCL all-reduce
+        self.grad_multicast: Dict[str, int] = {}
+
+    def rebind_grads(self, arena: torch.Tensor) -> None:
+        """Move the gradient arena into ``arena`` (same size / dtype / device; e.g. a symmetric-memory allocation).  Only
+        legal while no gradient is live (before the first step or right after an optimizer step)."""
+        if arena.shape != self.grads.shape or arena.dtype != self.grads.dtype or arena.device != self.grads.device:
+            raise _abi.PlbError("rebind_grads: the new arena must match the old one")
+        if self.have_grads:
+            raise _abi.PlbError("rebind_grads: gradients are live")
+        arena.zero_()
+        self.grads = arena
+        self.grads_clean = True
+        lay = self.layout
+        self.gp = {n: self.grads.data_ptr() + 4 * o for n, o in lay.offsets.items()}
+        self.grad_views = {n: self.view(self.grads, n) for n in lay.offsets}
 
     # ------------------------------------------------------------------ parameter views
     def view(self, arena: torch.Tensor, name: str) -> torch.Tensor:
@@ -269,6 +286,15 @@ class Engine:
         call("plb_gemm_bf16", op, epi, M, N, K, ptr(A), lda, ptr(B), ldb, ptr(C), ldc, ptr(bias), ptr(aux_in), ld_in,
              ptr(aux_out), ld_out, _stream())
         self.launches += 1
+
+    def _head_wgrad(self, head: str, V: int, H: int, m: int, logits, ldv: int) -> None:
+        """dW_head += dz^T h_rows — into this rank's arena, or (data parallel on NVSwitch) into every rank's at once."""
+        mc = self.grad_multicast.get(head + ".weight")
+        if mc is None:
+            self._gemm(GEMM_WGRAD, EPI_NONE, V, H, m, logits, ldv, self.h_rows, H, self.gp[head + ".weight"], H)
+        else:
+            call("plb_gemm_wgrad_allreduce", V, H, m, ptr(logits), ldv, ptr(self.h_rows), H, mc, H, _stream())
+            self.launches += 1
 
     def forward(self, b: DeviceBatch, train: bool) -> torch.Tensor:
         """Encoder forward; returns last_hidden_state as bf16 [T, H] (a workspace view)."""
@@ -361,7 +387,7 @@ class Engine:
         self.launches += 2
         if backward:
             call("plb_colsum", ptr(logits), ldv, m, V, self.gp[head + ".bias"], s)
-            self._gemm(GEMM_WGRAD, EPI_NONE, V, H, m, logits, ldv, self.h_rows, H, self.gp[head + ".weight"], H)
+            self._head_wgrad(head, V, H, m, logits, ldv)
             self._gemm(GEMM_DGRAD, EPI_NONE, m, H, V, logits, ldv, self.wp[head + ".weight"], H, self.dh_rows, H)
             call("plb_scatter_add_rows", ptr(self.dh_rows), H, ptr(rows), m, H, ptr(self.d_y), H, s)
             self.launches += 2
@@ -399,6 +425,7 @@ class Engine:
         dy[:T].zero_()
         loss_started = False
 
+        self._before_head_backward()
         # ---- heads on the masked rows only: one gather, the heads' row gradients summed, one scatter -------------------
         if M > 0 and masked_heads:
             call("plb_gather_rows", ptr(hidden), H, ptr(b.rows), M, H, ptr(self.h_rows), H, s)
@@ -414,7 +441,7 @@ class Engine:
                 loss_started = True
                 call("plb_colsum", ptr(logits), ldv, M, V, self.gp[head + ".bias"], s)
                 self.launches += 3
-                self._gemm(GEMM_WGRAD, EPI_NONE, V, H, M, logits, ldv, self.h_rows, H, self.gp[head + ".weight"], H)
+                self._head_wgrad(head, V, H, M, logits, ldv)
                 if k == 0:
                     self._gemm(GEMM_DGRAD, EPI_NONE, M, H, V, logits, ldv, self.wp[head + ".weight"], H, self.dh_rows, H)
                 else:
@@ -444,6 +471,7 @@ class Engine:
             self.have_grads = False
             return
         self.have_grads = True
+        self._before_head_backward()
         self._after_head_backward()
         self._after_encoder_backward()
 
@@ -568,6 +596,9 @@ class Engine:
         self._after_encoder_backward()
 
     # ------------------------------------------------------------------ data parallel hooks (ddp.py overrides)
+    def _before_head_backward(self) -> None:   # every step, every rank, before the first head gradient is written
+        pass
+
     def _after_head_backward(self) -> None:
         pass
 

@@ -3,7 +3,10 @@
 into FusedAdamW) == one-rank step on the concatenated batch (R/train.py:160-162,218-221 DDP semantics).
 
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 \
-        profiles/ddp_equivalence.py > profiles/r2_ddp_equivalence.json
+        profiles/ddp_equivalence.py [--fuse] > profiles/r2_ddp_equivalence.json
+
+--fuse: GradientSynchronizer(fuse_head_allreduce=True) — the token head's WGRAD adds into every rank's arena through the
+NVSwitch multicast mapping (plb_gemm_wgrad_allreduce) instead of the NCCL head bucket.
 
 Every rank takes its contiguous share of each global batch (train.shard_batch), runs 3 optimizer steps; rank 0 then repeats
 the 3 steps alone on the whole batches from the same initial weights and compares
@@ -67,8 +70,9 @@ def main():
         model, opt = build(dev)
         init = {k: v.detach().cpu().clone() for k, v in model.state_dict().items()}
         eng = model._ensure_engine(dev)
-        sync = GradientSynchronizer(eng)
+        sync = GradientSynchronizer(eng, fuse_head_allreduce="--fuse" in sys.argv)
         opt.grad_scale = sync.grad_scale
+        report["fused_head_allreduce"] = {"heads": sync.fused_heads, "why_not": sync.fuse_error}
         grads1, losses = None, []
         for i, gb in enumerate(batches):
             loss = model.loss_and_backward(shard_batch(gb, rank, world))

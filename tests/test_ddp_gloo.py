@@ -104,13 +104,16 @@ def _sync_worker(rank, world, port, out):
         eng = types.SimpleNamespace(layout=layout, device=torch.device("cpu"), shadow_valid=True, always_reduce=False,
                                     have_grads=False, loss_buf=torch.ones(1),
                                     params=torch.full((layout.total,), float(rank)), grads=torch.zeros(layout.total),
-                                    _after_head_backward=lambda: None, _after_encoder_backward=lambda: None)
+                                    _before_head_backward=lambda: None, _after_head_backward=lambda: None,
+                                    _after_encoder_backward=lambda: None)
         sync = ddp.GradientSynchronizer(eng)
         assert eng.always_reduce and not eng.shadow_valid and sync.grad_scale == 0.5
         assert not eng.params.any()                                    # rank 0's weights everywhere
-        if rank == 0:   # a normal step: gradients, then the two hooks in backward order
+        assert sync.symm is None and not sync.fused_heads             # CPU tensors: the NCCL / gloo bucket path
+        if rank == 0:   # a normal step: gradients, then the hooks in backward order
             eng.grads[:layout.trainable_end] = 2.0
             eng.have_grads = True
+            eng._before_head_backward()
             eng._after_head_backward()
             eng._after_encoder_backward()
         else:           # empty shard (R/train.py:129): must still enter both collectives with zeros, and step
