@@ -437,6 +437,65 @@ def test_reference_style_forward_backward(dev):
     opt.step()
 
 
+def test_styletts_style_finetuning_with_a_stock_torch_optimizer(dev):
+    """R/README.md:46-117 (StyleTTS second-stage training): ``bert`` is finetuned through ``bert(texts, attention_mask=...)
+    .last_hidden_state`` -> ``bert_encoder = nn.Linear(768, 512)`` with a STOCK ``torch.optim.AdamW`` whose param group is edited
+    in place (betas (0.9, 0.99), lr 1e-5, weight_decay 0.01).  The fused encoder must follow the weights such an optimizer writes
+    through torch (the bf16 shadow is refreshed when the parameters' version counters move) — compared with the stock HF
+    encoder taking the same steps on the same data."""
+    import plbert_b200 as P
+    from transformers import AlbertConfig, AlbertModel
+    cfg = AlbertConfig(vocab_size=188, embedding_size=32, hidden_size=128, num_attention_heads=2, intermediate_size=256,
+                       num_hidden_layers=3, max_position_embeddings=128)
+    torch.manual_seed(4)
+    stock = AlbertModel(cfg)
+    sd = {k: v.clone() for k, v in stock.state_dict().items()}
+    proj0 = torch.nn.Linear(128, 64)
+    g = torch.Generator().manual_seed(9)
+    ids = torch.randint(1, 185, (4, 96), generator=g).to(dev)
+    lens = torch.tensor([96, 70, 41, 12])
+    text_mask = (torch.arange(96)[None, :] >= lens[:, None]).to(dev)                  # StyleTTS: True = padding
+    target = torch.randn(4, 96, 64, generator=g).to(dev)
+    outs = {}
+    for kind in ("stock", "fused"):
+        bert = AlbertModel(cfg) if kind == "stock" else P.fuse_albert(AlbertModel(cfg))
+        bert.load_state_dict(sd, strict=True)
+        bert = bert.to(dev).train()
+        proj = torch.nn.Linear(128, 64)
+        proj.load_state_dict(proj0.state_dict())
+        proj = proj.to(dev)
+        params = [p for n, p in bert.named_parameters() if "pooler" not in n]
+        opt = torch.optim.AdamW(params, lr=1e-4)
+        for grp in opt.param_groups:                                                   # R/README.md:79-86
+            grp["betas"], grp["lr"], grp["weight_decay"] = (0.9, 0.99), 2e-3, 0.01     # large lr: three steps must move the output
+        opt_p = torch.optim.AdamW(proj.parameters(), lr=1e-3)
+        losses = []
+        for step in range(3):
+            hid = bert(ids, attention_mask=(~text_mask).int()).last_hidden_state       # R/README.md:91
+            d_en = proj(hid.float())
+            loss = ((d_en - target) ** 2 * (~text_mask)[:, :, None]).mean()
+            opt.zero_grad()
+            opt_p.zero_grad()
+            loss.backward()
+            opt_p.step()                                                               # R/README.md:116-117
+            opt.step()
+            losses.append(loss.item())
+        with torch.no_grad():
+            final = bert(ids, attention_mask=(~text_mask).int()).last_hidden_state.float()
+        outs[kind] = (losses, final[~text_mask].cpu().numpy(), {n: p.detach().float().cpu().numpy() for n, p in bert.named_parameters()})
+    for a, b in zip(outs["stock"][0], outs["fused"][0]):
+        assert abs(a - b) <= 2e-2 * abs(a), (outs["stock"][0], outs["fused"][0])
+    assert outs["stock"][0][2] < outs["stock"][0][0]                                   # the steps did train
+    before = AlbertModel(cfg)
+    before.load_state_dict(sd)
+    with torch.no_grad():
+        h0 = before.to(dev)(ids, attention_mask=(~text_mask).int()).last_hidden_state[~text_mask].cpu().numpy()
+    assert cosine(outs["stock"][1], h0) < 0.99                                         # ... and moved the encoder output
+    assert cosine(outs["fused"][1], outs["stock"][1]) > 0.999                          # the fused encoder followed the optimizer
+    w = "encoder.albert_layer_groups.0.albert_layers.0.ffn.weight"
+    assert cosine(outs["fused"][2][w] - sd[w].numpy(), outs["stock"][2][w] - sd[w].numpy()) > 0.9
+
+
 def test_empty_batch_and_checkpoint_roundtrip(dev, tmp_path):
     import plbert_b200 as P
     from plbert_b200 import train as T
