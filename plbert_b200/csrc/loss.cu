@@ -538,11 +538,15 @@ extern "C" int plb_masked_ce(void* logits, int ld, int M, int V, const int32_t* 
               : per_thread <= 8 ? masked_ce_cluster_kernel<8> : masked_ce_cluster_kernel<16>;
     const int kv = per_thread <= 2 ? 2 : per_thread <= 4 ? 4 : per_thread <= 8 ? 8 : 16;
     const int smem = CE_WARPS * CE_BUFS * kv * 512;
-    static int cached[4] = {0, 0, 0, 0};   // resident clusters per kernel instantiation (a property of the device + binary)
-    int& resident = cached[kv == 2 ? 0 : kv == 4 ? 1 : kv == 8 ? 2 : 3];
+    static int cached[16][4] = {};   // resident clusters per (device, kernel instantiation)
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    PLB_REQUIRE(e == cudaSuccess, PLB_ERR_CUDA, "masked_ce: cudaGetDevice: %s", cudaGetErrorString(e));
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);  // per device, idempotent
+    PLB_REQUIRE(e == cudaSuccess, PLB_ERR_CUDA, "masked_ce: cudaFuncSetAttribute(smem=%d): %s", smem, cudaGetErrorString(e));
+    int uncached = 0;
+    int& resident = (dev >= 0 && dev < 16) ? cached[dev][kv == 2 ? 0 : kv == 4 ? 1 : kv == 8 ? 2 : 3] : uncached;
     if (resident == 0) {
-      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-      PLB_REQUIRE(e == cudaSuccess, PLB_ERR_CUDA, "masked_ce: cudaFuncSetAttribute(smem=%d): %s", smem, cudaGetErrorString(e));
       cudaLaunchConfig_t cfg = {};
       cfg.gridDim = dim3(CE_CLUSTER * sm_count(), 1, 1);
       cfg.blockDim = dim3(CE_THREADS, 1, 1);
