@@ -95,17 +95,20 @@ __global__ void masked_ce_kernel(__nv_bfloat16* __restrict__ logits, int ld, int
 // CE_BUFS shared-memory slots: 1-D bulk copies in (cp.async.bulk + mbarrier, issued by lane 0 one row ahead), three passes
 // over the slot from shared memory (maximum, sum of exponentials, gradient written back in place), one bulk copy out — so
 // the logits cross HBM exactly once each way, nothing is re-read from L2, and the bytes in flight do not depend on
-// registers.  Per row every warp reduces its own (max, sum) with shuffles, lane 0 writes the pair into slot
-// [rank * 4 + warp] of all eight CTAs (st.shared::cluster), ONE cluster barrier publishes the 32 pairs and every warp merges
-// them itself (one pair per lane).  The pair slots alternate between two sets by row parity, so that one barrier per row is
-// enough: a CTA writes set p again only after every peer has passed the barrier of the row in between, i.e. has read set p.
+// registers.  Per row every warp reduces its own (max, sum) with shuffles, lane 0 sends the pair into slot [rank * 4 + warp] of
+// all eight CTAs with st.async (the store completes 8 bytes of the receiver's mbarrier: no cluster barrier per row — with
+// barrier.cluster.arrive.release / wait.acquire around plain st.shared::cluster stores the kernel took 594 us instead of 533),
+// and every warp merges the 32 pairs itself (one pair per lane).  The pair slots and their barriers alternate between two
+// sets by row parity: a CTA can be at most one row ahead of a peer, because it needs the peer's pair of row r + 1, which the
+// peer sends only after it has merged row r.
 // What this replaces: one CTA per row, three passes with one 16-byte load per thread in flight (816 us for the 2.92 GB of
 // the 64 000-wide head = 3.6 TB/s).  Measured on the way (profiles/ce_bench.py, -D variants, same box): a register-resident
 // one-shot cluster per row 580 - 645 us (each generation of CTAs loads, computes and stores in lock-step; made persistent
-// its spills fell out of L1: 1.1 ms); this kernel 594 us = 4.9 TB/s; refilling the ring at the top of the row / before the
-// barrier instead of after it 641 / 690; 256-thread CTAs 641; three slots with 4 resident CTAs 720; 1 / 2 / 3 of 4 gradient
-// exponentials on the FMA pipe 583 / 595 / 627; with NO exponentials at all 530 — the skeleton (bulk copies both ways + one
-// cluster barrier per row), not the MUFU, sets the time.
+// its spills fell out of L1: 1.1 ms).  With the cluster barrier per row: this kernel 594 us; refilling the ring at the top of
+// the row / before the barrier instead of after it 641 / 690; 256-thread CTAs 641; three slots with 4 resident CTAs 720;
+// 1 / 2 / 3 of 4 gradient exponentials on the FMA pipe 583 / 595 / 627; with NO exponentials at all 530 — the skeleton, not
+// the MUFU, set the time.  With the st.async exchange: 533 us = 5.5 TB/s (7 / 5 resident CTAs 541 / 551, three slots 550,
+// 256-thread CTAs 646, 1 / 2 of 4 gradient exponentials on the FMA pipe 520 / 529).
 #ifndef PLB_CE_THREADS
 #define PLB_CE_THREADS 128
 #endif
@@ -113,8 +116,11 @@ constexpr int CE_CLUSTER = 8, CE_THREADS = PLB_CE_THREADS, CE_WARPS = CE_THREADS
 #ifndef PLB_CE_BUFS
 #define PLB_CE_BUFS 2      // ring slots per warp (16 KB per CTA and slot at kVec = 8)
 #endif
+#ifndef PLB_CE_XCHG
+#define PLB_CE_XCHG 1      // 1: pairs travel with st.async + mbarrier complete_tx (no cluster barrier per row), 0: barrier.cluster per row
+#endif
 #ifndef PLB_CE_ISSUE_AT
-#define PLB_CE_ISSUE_AT 2  // where lane 0 refills the ring: 0 = top of the row, 1 = before the cluster barrier, 2 = after it
+#define PLB_CE_ISSUE_AT 2  // where lane 0 refills the ring: 0 = top of the row, 1 / 2 = after the pairs are sent (before / after the cluster barrier when PLB_CE_XCHG == 0)
 #endif
 #ifndef PLB_CE_MINB
 #define PLB_CE_MINB 6      // resident CTAs per SM the register budget is cut for (6 x 33 KB of shared memory fit)
@@ -167,6 +173,7 @@ masked_ce_cluster_kernel(__nv_bfloat16* __restrict__ logits, int ld, int M, int 
   extern __shared__ __align__(128) uint8_t ce_smem[];             // [warp][slot][kVec * 512 bytes]
   __shared__ uint64_t bars[CE_WARPS][CE_BUFS];
   __shared__ float2 s_part[2][CE_CLUSTER * CE_WARPS];
+  __shared__ uint64_t xbar[2];                                    // exchange barriers by row parity (PLB_CE_XCHG)
   constexpr float kLog2e = 1.4426950408889634f;
   constexpr int kPiece = kVec * 32;                               // 16-byte words per warp and row
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -193,10 +200,15 @@ masked_ce_cluster_kernel(__nv_bfloat16* __restrict__ logits, int ld, int M, int 
   };
   if (lane == 0) {
     for (int i = 0; i < CE_BUFS; ++i) mbar_init(&bar[i], 1);
+    if (PLB_CE_XCHG && warp == 0) {
+      mbar_init(&xbar[0], 1);
+      mbar_init(&xbar[1], 1);
+    }
     fence_mbar_init();
     for (int i = 0; i < CE_BUFS - 1; ++i) issue(i);
   }
   __syncwarp();
+  if (PLB_CE_XCHG) cluster_sync_all();   // once: the peers' exchange barriers exist before anybody stores into this CTA
   const f32x2 l2e = f2_splat(kLog2e);
   int it = 0;
   for (int m = first_row; m < M; m += nclusters, ++it) {
@@ -282,14 +294,33 @@ masked_ce_cluster_kernel(__nv_bfloat16* __restrict__ logits, int ld, int M, int 
       f2_unpack(f2_add(acc[0], acc[1]), s0, s1);
       se = warp_sum(s0 + s1);
     }
-    if (lane == 0) {
-      const uint32_t own = smem_u32(&s_part[it & 1][rank * CE_WARPS + warp]);
+    if (PLB_CE_XCHG) {
+      // Every warp sends its pair to all eight CTAs with st.async: the store lands in the peer's s_part and completes 8 bytes
+      // of the peer's exchange barrier; a CTA's barrier of the row completes when its own arrive.expect_tx (thread 0) and all
+      // 32 pairs are in.  No cluster-wide barrier: a CTA can only be one row ahead of a peer (it needs the peer's pair of
+      // row r + 1, which the peer sends after it has merged row r), which is exactly what the two parity sets allow.
+      if (tid == 0) mbar_arrive_expect_tx(&xbar[it & 1], CE_CLUSTER * CE_WARPS * 8);
+      if (lane == 0) {
+        const uint32_t own = smem_u32(&s_part[it & 1][rank * CE_WARPS + warp]), bar_own = smem_u32(&xbar[it & 1]);
 #pragma unroll
-      for (uint32_t r = 0; r < CE_CLUSTER; ++r) st_cluster_f32x2(mapa_u32(own, r), mx, se);
+        for (uint32_t r = 0; r < CE_CLUSTER; ++r)
+          asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.f32 [%0], {%1, %2}, [%3];" ::"r"(
+                           mapa_u32(own, r)),
+                       "f"(mx), "f"(se), "r"(mapa_u32(bar_own, r))
+                       : "memory");
+      }
+      if (PLB_CE_ISSUE_AT != 0) refill();
+      mbar_wait(&xbar[it & 1], static_cast<uint32_t>(it >> 1) & 1);
+    } else {
+      if (lane == 0) {
+        const uint32_t own = smem_u32(&s_part[it & 1][rank * CE_WARPS + warp]);
+#pragma unroll
+        for (uint32_t r = 0; r < CE_CLUSTER; ++r) st_cluster_f32x2(mapa_u32(own, r), mx, se);
+      }
+      if (PLB_CE_ISSUE_AT == 1) refill();
+      cluster_sync_all();   // release / acquire: the 32 pairs of this row are visible everywhere
+      if (PLB_CE_ISSUE_AT == 2) refill();
     }
-    if (PLB_CE_ISSUE_AT == 1) refill();
-    cluster_sync_all();   // release / acquire: the 32 pairs of this row are visible everywhere
-    if (PLB_CE_ISSUE_AT == 2) refill();
     float row_max = -INFINITY, row_se = 0.f;
     {
       float2 part[CE_CLUSTER * CE_WARPS / 32];
