@@ -140,7 +140,7 @@ __global__ void __launch_bounds__(WARPS * 32) ln_fwd_kernel(const __nv_bfloat16*
 // chunks, the math runs on fp32 pairs, and phase two re-derives xhat / g from the raw bf16 words instead of keeping them.
 constexpr int BWD_WARPS = 6;  // per CTA, two CTAs per SM
 constexpr int BWD_DEPTH = 4;  // rows in flight per warp
-template <int MAXC, bool kFull>
+template <int MAXC, bool kFull, bool kStatsRing>
 __global__ void __launch_bounds__(BWD_WARPS * 32, 2)
 ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ z,
               const float* __restrict__ stats, const float* __restrict__ w, int T, int H,
@@ -151,8 +151,12 @@ ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restr
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int nchunk = H >> 3;
   const uint32_t row_bytes = static_cast<uint32_t>(H) * 2;
-  uint8_t* ring = ln_smem + static_cast<size_t>(warp) * BWD_DEPTH * 2 * row_bytes;   // slot = z row | dy row
-  uint8_t* after = ln_smem + static_cast<size_t>(BWD_WARPS) * BWD_DEPTH * 2 * row_bytes;
+  // slot = z row | dy row (| the 16-byte aligned pair of (mean, rstd) entries that holds the row's, kStatsRing: T even, stats
+  // 16-byte aligned).  The statistics used to be a plain 8-byte load per row, requested one ring depth ahead and queued in
+  // registers: its first use carried 15 % of the kernel's stall samples (the request queues behind ~150 KB of bulk copies per SM).
+  const uint32_t slot_bytes = 2 * row_bytes + (kStatsRing ? 16 : 0);
+  uint8_t* ring = ln_smem + static_cast<size_t>(warp) * BWD_DEPTH * slot_bytes;
+  uint8_t* after = ln_smem + static_cast<size_t>(BWD_WARPS) * BWD_DEPTH * slot_bytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(after) + warp * BWD_DEPTH;
   float* s_red = reinterpret_cast<float*>(after + BWD_WARPS * BWD_DEPTH * 8);          // [3][H] column partials of the CTA
   const long first = static_cast<long>(blockIdx.x) * BWD_WARPS + warp, stride = static_cast<long>(gridDim.x) * BWD_WARPS;
@@ -160,10 +164,11 @@ ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restr
     const long row = first + k * stride;
     if (row < T) {
       const int st = static_cast<int>(k % BWD_DEPTH);
-      uint8_t* dst = ring + st * 2 * row_bytes;
-      mbar_arrive_expect_tx(&bars[st], 2 * row_bytes);
+      uint8_t* dst = ring + st * slot_bytes;
+      mbar_arrive_expect_tx(&bars[st], slot_bytes);
       bulk_load_1d(dst, z + row * H, row_bytes, &bars[st]);
       bulk_load_1d(dst + row_bytes, dy + row * H, row_bytes, &bars[st]);
+      if (kStatsRing) bulk_load_1d(dst + 2 * row_bytes, stats + 2 * (row & ~1L), 16, &bars[st]);
     }
   };
   if (lane == 0) {
@@ -192,19 +197,28 @@ ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restr
     if (row < T) asm volatile("ld.global.nc.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(stats + 2 * row));
     return v;
   };
-  float2 sq[BWD_DEPTH];
+  float2 sq[kStatsRing ? 1 : BWD_DEPTH];
+  if (!kStatsRing) {
 #pragma unroll
-  for (int u = 0; u < BWD_DEPTH; ++u) sq[u] = load_stats(first + u * stride);
+    for (int u = 0; u < BWD_DEPTH; ++u) sq[kStatsRing ? 0 : u] = load_stats(first + u * stride);
+  }
 
   for (long k0 = 0; first + k0 * stride < T; k0 += BWD_DEPTH) {
 #pragma unroll
     for (int u = 0; u < BWD_DEPTH; ++u) {
       const long k = k0 + u, row = first + k * stride;
       if (row < T) {
-        const float mean = sq[u].x, rstd = sq[u].y;
-        sq[u] = load_stats(row + BWD_DEPTH * stride);
+        float mean, rstd;
+        if (!kStatsRing) {
+          mean = sq[kStatsRing ? 0 : u].x, rstd = sq[kStatsRing ? 0 : u].y;
+          sq[kStatsRing ? 0 : u] = load_stats(row + BWD_DEPTH * stride);
+        }
         mbar_wait(&bars[u], static_cast<uint32_t>(k0 / BWD_DEPTH) & 1);
-        const uint32_t src = smem_u32(ring + u * 2 * row_bytes);
+        const uint32_t src = smem_u32(ring + u * slot_bytes);
+        if (kStatsRing) {
+          const float2 st2 = lds64_f2(src + 2 * row_bytes + static_cast<uint32_t>(row & 1) * 8);   // broadcast read
+          mean = st2.x, rstd = st2.y;
+        }
         uint4 rz[MAXC], rd[MAXC];
 #pragma unroll
         for (int i = 0; i < MAXC; ++i) {
@@ -497,12 +511,17 @@ extern "C" int plb_ln_bwd(const void* dy, const void* z, const float* stats, con
   PLB_REQUIRE((reinterpret_cast<uintptr_t>(z) & 15) == 0 && (reinterpret_cast<uintptr_t>(dy) & 15) == 0 &&
                   (reinterpret_cast<uintptr_t>(dz) & 15) == 0, PLB_ERR_ARG, "ln_bwd: dy / z / dz must be 16-byte aligned");
   const bool full = H == nc * 256;
-  auto kern = nc == 1 ? (full ? ln_bwd_kernel<1, true> : ln_bwd_kernel<1, false>)
-            : nc == 2 ? (full ? ln_bwd_kernel<2, true> : ln_bwd_kernel<2, false>)
-            : nc == 3 ? (full ? ln_bwd_kernel<3, true> : ln_bwd_kernel<3, false>)
-                      : (full ? ln_bwd_kernel<4, true> : ln_bwd_kernel<4, false>);
-  // per-warp rings of BWD_DEPTH (z row | dy row) slots + their mbarriers + the CTA's [3][H] column partials
-  const int smem = BWD_WARPS * BWD_DEPTH * (2 * H * 2 + 8) + 3 * H * static_cast<int>(sizeof(float));
+#ifndef PLB_LN_STATS_RING
+#define PLB_LN_STATS_RING 1
+#endif
+  // the statistics ride in the ring when the 16-byte pair around every row's entry exists and is aligned
+  const bool sring = PLB_LN_STATS_RING && full && (T % 2 == 0) && (reinterpret_cast<uintptr_t>(stats) & 15) == 0;
+  auto kern = nc == 1 ? (full ? (sring ? ln_bwd_kernel<1, true, true> : ln_bwd_kernel<1, true, false>) : ln_bwd_kernel<1, false, false>)
+            : nc == 2 ? (full ? (sring ? ln_bwd_kernel<2, true, true> : ln_bwd_kernel<2, true, false>) : ln_bwd_kernel<2, false, false>)
+            : nc == 3 ? (full ? (sring ? ln_bwd_kernel<3, true, true> : ln_bwd_kernel<3, true, false>) : ln_bwd_kernel<3, false, false>)
+                      : (full ? (sring ? ln_bwd_kernel<4, true, true> : ln_bwd_kernel<4, true, false>) : ln_bwd_kernel<4, false, false>);
+  // per-warp rings of BWD_DEPTH (z row | dy row [| statistics pair]) slots + their mbarriers + the CTA's [3][H] column partials
+  const int smem = BWD_WARPS * BWD_DEPTH * (2 * H * 2 + (sring ? 16 : 0) + 8) + 3 * H * static_cast<int>(sizeof(float));
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);  // idempotent
   PLB_REQUIRE(e == cudaSuccess, PLB_ERR_CUDA, "ln_bwd: cudaFuncSetAttribute(smem=%d): %s", smem, cudaGetErrorString(e));
   int per_sm = 1;   // resident CTAs per SM: the grid is persistent

@@ -208,7 +208,7 @@ def test_gemm_rejects_bad_arguments(dev):
 
 
 # ------------------------------------------------------------------------------------------ LayerNorm
-@pytest.mark.parametrize("T,H", [(1000, 768), (513, 128), (64, 1024), (7, 8)])
+@pytest.mark.parametrize("T,H", [(1000, 768), (999, 768), (513, 128), (64, 1024), (2, 256), (7, 8)])
 def test_layernorm_fwd_bwd(dev, T, H):
     z = (torch.randn(T, H, device=dev) * 2 + 0.3).to(BF)
     w = torch.randn(H, device=dev)
