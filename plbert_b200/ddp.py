@@ -44,6 +44,20 @@ def all_reduce_buckets(flat: torch.Tensor, bounds: Sequence[Tuple[int, int]], gr
     return works
 
 
+def head_bounds_without(layout, fused_names: Sequence[str]) -> List[Tuple[int, int]]:
+    """[begin, end) ranges of the head region [0, head_end) that remain for the NCCL bucket once the gradients of
+    ``fused_names`` are reduced inside their WGRAD kernels."""
+    bounds, lo = [], 0
+    for n in sorted(fused_names, key=lambda k: layout.offsets[k]):
+        o = layout.offsets[n]
+        if o > lo:
+            bounds.append((lo, o))
+        lo = o + layout.numel(n)
+    if layout.head_end > lo:
+        bounds.append((lo, layout.head_end))
+    return bounds
+
+
 def broadcast_params(flat: torch.Tensor, src: int = 0, group=None) -> None:
     """DDP's initial parameter broadcast: every rank starts from rank ``src``'s weights."""
     dist.broadcast(flat, src=src, group=group)
@@ -118,16 +132,7 @@ class GradientSynchronizer:
         self.fused_heads = names
         eng.grad_multicast = {n: base + 4 * lay.offsets[n] for n in names}
         eng._before_head_backward = self._head_barrier
-        # the NCCL head bucket keeps what is left of [0, head_end)
-        bounds, lo = [], 0
-        for n in sorted(names, key=lambda k: lay.offsets[k]):
-            o = lay.offsets[n]
-            if o > lo:
-                bounds.append((lo, o))
-            lo = o + lay.numel(n)
-        if lay.head_end > lo:
-            bounds.append((lo, lay.head_end))
-        self.head_bounds = bounds
+        self.head_bounds = head_bounds_without(lay, names)   # the NCCL head bucket keeps what is left of [0, head_end)
 
     def _head_barrier(self) -> None:
         self.symm.barrier(channel=0)

@@ -93,6 +93,28 @@ def test_bucket_bounds():
     assert ddp.bucket_bounds(64, 200, 50) == [(0, 50), (50, 64), (64, 114), (114, 164), (164, 200)]
 
 
+def test_head_bounds_without_fused_weights():
+    """Opt-in fused WGRAD + all-reduce (ddp.GradientSynchronizer(fuse_head_allreduce=True)): the NCCL head bucket must cover
+    exactly the head region minus the fused weights, in order, without gaps inside the remaining parameters."""
+    layout = ParamLayout(EngineConfig(188, 16, 32, 2, 64, 2, 64, 2, 1e-12, 0, 188, 50))
+    names = ["token_predictor.weight"]
+    b = ddp.head_bounds_without(layout, names)
+    o, n = layout.offsets["token_predictor.weight"], layout.numel("token_predictor.weight")
+    assert o == 0 and b == [(n, layout.head_end)]
+    covered = torch.zeros(layout.head_end, dtype=torch.int32)
+    for lo, hi in b:
+        covered[lo:hi] += 1
+    covered[o:o + n] += 1
+    assert (covered == 1).all()
+    for name in ("token_predictor.bias", "phoneme_predictor.weight", "phoneme_predictor.bias"):
+        lo = layout.offsets[name]
+        assert any(a <= lo and lo + layout.numel(name) <= e for a, e in b), name
+    assert ddp.head_bounds_without(layout, []) == [(0, layout.head_end)]
+    both = ddp.head_bounds_without(layout, ["phoneme_predictor.weight", "token_predictor.weight"])
+    assert all(a < e for a, e in both) and both[-1][1] == layout.head_end
+    assert sum(e - a for a, e in both) == layout.head_end - n - layout.numel("phoneme_predictor.weight")
+
+
 def _sync_worker(rank, world, port, out):
     """The real ``GradientSynchronizer`` hooks + ``Engine._empty_step`` on CPU tensors: rank 1's shard has no masked rows."""
     import types
