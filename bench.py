@@ -12,7 +12,8 @@ mask / replace / keep, random 512-crop.
 ``value`` counts valid phoneme tokens per second over all ranks with the batch already resident in HBM; ``e2e`` is the same
 step through the public API from HOST data: dataset rows -> masking + collate in background worker processes
 (``CollateWorkerLoader``) -> ``BatchFeeder.step`` (flatten, pinned buffer, H2D, fused step) -> ``FusedAdamW.step`` ->
-``loss.item()`` every step.
+``loss.item()`` every step.  Both loops time exactly K steps after W warm-up steps in the same process, the end-to-end loop first
+(the board drifts ~0.1 ms per 10 steps on its power cap, profiles/e2e_gap.py; ``e2e.order`` records it).
 At N = 1 the line also carries: ``sub_records`` (phoneme-only step, C4 variable-length batches in the packed layout, C5
 encoder-only forward), ``library_baseline`` (the reference model through stock PyTorch libraries on the SAME GPU: HF
 AlbertModel under bf16 autocast + SDPA + torch AdamW, run in a subprocess) with a check of this path's first-step loss
