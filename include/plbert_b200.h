@@ -41,6 +41,10 @@ int plb_abi_version(void);
 const char* plb_last_error_string(void);
 /* Number of SMs of the current device (148 on B200); <0 on error. */
 int plb_device_sm_count(void);
+/* dst[0 .. bytes) = 0 on the stream (any alignment).  The step's own zero fills (the row-gradient buffer the masked rows are
+ * scattered into, the attention delta accumulator, the loss scalar) — torch.Tensor.zero_() in the reference's autograd —
+ * so that a training step launches no library kernel at all and its launches chain with programmatic dependent launch. */
+int plb_fill_zero(void* dst, unsigned long long bytes, plb_stream_t stream);
 /* Programmatic dependent launch for the kernels of one stream (default: enabled).  The reference's step is a chain of
  * ~1000 stream-ordered library kernels (R/train.py:353-357); here the ~260 kernels of a step are launched so that the
  * next kernel's CTAs take over an SM the moment the previous kernel's CTA leaves it (their prologue runs before

@@ -31,6 +31,7 @@ SIGNATURES = {
     "plb_last_error_string": [],
     "plb_device_sm_count": [],
     "plb_set_launch_overlap": [c_int],
+    "plb_fill_zero": [P, ctypes.c_ulonglong, P],
     "plb_length_to_mask": [P, c_int, c_int, P, P],
     "plb_gemm_bf16": _GEMM_ARGS,
     "plb_gemm_bf16_check": _GEMM_ARGS,

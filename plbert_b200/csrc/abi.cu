@@ -172,6 +172,35 @@ using namespace plb;
 
 extern "C" int plb_abi_version(void) { return PLB_ABI_VERSION; }
 extern "C" const char* plb_last_error_string(void) { return g_error; }
+namespace plb {
+namespace {
+// p[0 .. bytes) = 0: 16-byte stores over the aligned middle, byte stores at the ragged ends
+__global__ void __launch_bounds__(256) fill_zero_kernel(uint8_t* __restrict__ p, size_t bytes) {
+  pdl_grid_sync();
+  const size_t head = (16 - (reinterpret_cast<uintptr_t>(p) & 15)) & 15;
+  const size_t h = head < bytes ? head : bytes;
+  const size_t nvec = (bytes - h) >> 4;
+  uint4* v = reinterpret_cast<uint4*>(p + h);
+  const size_t tid = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x, nthr = static_cast<size_t>(gridDim.x) * blockDim.x;
+  for (size_t i = tid; i < nvec; i += nthr) v[i] = make_uint4(0, 0, 0, 0);
+  const size_t tail0 = h + (nvec << 4);
+  if (tid < h) p[tid] = 0;
+  if (tid < bytes - tail0) p[tail0 + tid] = 0;
+}
+}  // namespace
+}  // namespace plb
+
+extern "C" int plb_fill_zero(void* dst, unsigned long long bytes, plb_stream_t stream) {
+  PLB_REQUIRE(dst != nullptr || bytes == 0, PLB_ERR_ARG, "fill_zero: null pointer");
+  if (bytes == 0) return PLB_OK;
+  const unsigned long long want = (bytes / 16 + 255) / 256 + 1;
+  const int grid = static_cast<int>(want < plb::sm_count() * 8ull ? want : plb::sm_count() * 8ull);
+  cudaError_t e = plb::launch_kernel(plb::fill_zero_kernel, dim3(grid), dim3(256), 0, static_cast<cudaStream_t>(stream),
+                                     static_cast<uint8_t*>(dst), static_cast<size_t>(bytes));
+  PLB_REQUIRE(e == cudaSuccess, PLB_ERR_CUDA, "plb_fill_zero: launch failed: %s", cudaGetErrorString(e));
+  return plb::check_launch("plb_fill_zero");
+}
+
 extern "C" int plb_set_launch_overlap(int enable) {
   plb::set_launch_overlap(enable);
   return PLB_OK;

@@ -15,6 +15,7 @@ namespace {
 // dst[i, :] = src[rows[i], :]   (bf16, H % 8 == 0)
 __global__ void gather_rows_kernel(const __nv_bfloat16* __restrict__ src, int ld_src, const int32_t* __restrict__ rows,
                                    int M, int H, __nv_bfloat16* __restrict__ dst, int ld_dst) {
+  pdl_grid_sync();
   const int chunks = H >> 3;
   const long total = static_cast<long>(M) * chunks;
   for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < total; i += static_cast<long>(gridDim.x) * blockDim.x) {
@@ -28,6 +29,7 @@ __global__ void gather_rows_kernel(const __nv_bfloat16* __restrict__ src, int ld
 __global__ void scatter_add_rows_kernel(const __nv_bfloat16* __restrict__ src, int ld_src,
                                         const int32_t* __restrict__ rows, int M, int H, __nv_bfloat16* __restrict__ dst,
                                         int ld_dst) {
+  pdl_grid_sync();
   const int pairs = H >> 1;
   const long total = static_cast<long>(M) * pairs;
   for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < total; i += static_cast<long>(gridDim.x) * blockDim.x) {
@@ -42,6 +44,7 @@ template <int kThreads>
 __global__ void masked_ce_kernel(__nv_bfloat16* __restrict__ logits, int ld, int M, int V,
                                  const int32_t* __restrict__ labels, const float* __restrict__ weights,
                                  float* __restrict__ row_loss) {
+  pdl_grid_sync();
   constexpr int kGroups = 256 / kThreads;
   __shared__ float s_red[kGroups][kThreads / 32 + 1];
   const int group = threadIdx.x / kThreads, tid = threadIdx.x % kThreads;
@@ -170,6 +173,7 @@ template <int kVec>   // 16-byte words per lane and row
 __global__ void __cluster_dims__(CE_CLUSTER, 1, 1) __launch_bounds__(CE_THREADS, kVec * CE_WARPS <= 32 ? PLB_CE_MINB : 3)
 masked_ce_cluster_kernel(__nv_bfloat16* __restrict__ logits, int ld, int M, int V, const int32_t* __restrict__ labels,
                          const float* __restrict__ weights, float* __restrict__ row_loss) {
+  pdl_grid_sync();
   extern __shared__ __align__(128) uint8_t ce_smem[];             // [warp][slot][kVec * 512 bytes]
   __shared__ uint64_t bars[CE_WARPS][CE_BUFS];
   __shared__ float2 s_part[2][CE_CLUSTER * CE_WARPS];
@@ -387,6 +391,7 @@ masked_ce_cluster_kernel(__nv_bfloat16* __restrict__ logits, int ld, int M, int 
 __global__ void __launch_bounds__(256)
 masked_ce_wide_kernel(__nv_bfloat16* __restrict__ logits, int ld, int M, int V, const int32_t* __restrict__ labels,
                       const float* __restrict__ weights, float* __restrict__ row_loss) {
+  pdl_grid_sync();
   __shared__ float s_red[8];
   const int m = blockIdx.x, tid = threadIdx.x;
   __nv_bfloat16* z = logits + static_cast<size_t>(m) * ld;
@@ -458,6 +463,7 @@ masked_ce_wide_kernel(__nv_bfloat16* __restrict__ logits, int ld, int M, int V, 
 
 // deterministic sum of row_loss -> out[0] (+= when accumulate)
 __global__ void sum_rows_kernel(const float* __restrict__ v, int n, float* __restrict__ out, int accumulate) {
+  pdl_grid_sync();
   __shared__ float s[32];
   float acc = 0.f;
   for (int i = threadIdx.x; i < n; i += blockDim.x) acc += v[i];
@@ -531,8 +537,9 @@ extern "C" int plb_gather_rows(const void* src, int ld_src, const int32_t* rows,
   if (M == 0) return PLB_OK;
   const long total = static_cast<long>(M) * (H / 8);
   const int grid = static_cast<int>(total / 256 + 1 < sm_count() * 8L ? total / 256 + 1 : sm_count() * 8L);
-  gather_rows_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const __nv_bfloat16*>(src), ld_src, rows, M,
-                                                                         H, static_cast<__nv_bfloat16*>(dst), ld_dst);
+  cudaError_t e = launch_kernel(gather_rows_kernel, dim3(grid), dim3(256), 0, static_cast<cudaStream_t>(stream),
+                                static_cast<const __nv_bfloat16*>(src), ld_src, rows, M, H, static_cast<__nv_bfloat16*>(dst), ld_dst);
+  PLB_REQUIRE(e == cudaSuccess, PLB_ERR_CUDA, "plb_gather_rows: launch failed: %s", cudaGetErrorString(e));
   return check_launch("plb_gather_rows");
 }
 
@@ -543,8 +550,9 @@ extern "C" int plb_scatter_add_rows(const void* src, int ld_src, const int32_t* 
   if (M == 0) return PLB_OK;
   const long total = static_cast<long>(M) * (H / 2);
   const int grid = static_cast<int>(total / 256 + 1 < sm_count() * 8L ? total / 256 + 1 : sm_count() * 8L);
-  scatter_add_rows_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const __nv_bfloat16*>(src), ld_src,
-                                                                              rows, M, H, static_cast<__nv_bfloat16*>(dst), ld_dst);
+  cudaError_t e = launch_kernel(scatter_add_rows_kernel, dim3(grid), dim3(256), 0, static_cast<cudaStream_t>(stream),
+                                static_cast<const __nv_bfloat16*>(src), ld_src, rows, M, H, static_cast<__nv_bfloat16*>(dst), ld_dst);
+  PLB_REQUIRE(e == cudaSuccess, PLB_ERR_CUDA, "plb_scatter_add_rows: launch failed: %s", cudaGetErrorString(e));
   return check_launch("plb_scatter_add_rows");
 }
 
@@ -561,8 +569,9 @@ extern "C" int plb_masked_ce(void* logits, int ld, int M, int V, const int32_t* 
     return PLB_OK;
   }
   __nv_bfloat16* z = static_cast<__nv_bfloat16*>(logits);
+  cudaError_t le = cudaSuccess;
   if (V <= 2048)
-    masked_ce_kernel<32><<<(M + 7) / 8, 256, 0, stream>>>(z, ld, M, V, labels, weights, row_loss);
+    le = launch_kernel(masked_ce_kernel<32>, dim3((M + 7) / 8), dim3(256), 0, stream, z, ld, M, V, labels, weights, row_loss);
   else if (ld > 8192 && ld <= 16 * 8192 && ld % 8 == 0 && (reinterpret_cast<uintptr_t>(z) & 15) == 0) {
     const int per_thread = (ld / 8 + CE_CLUSTER * CE_THREADS - 1) / (CE_CLUSTER * CE_THREADS);   // 16-byte words per thread
     auto kern = per_thread <= 2 ? masked_ce_cluster_kernel<2> : per_thread <= 4 ? masked_ce_cluster_kernel<4>
@@ -595,12 +604,14 @@ extern "C" int plb_masked_ce(void* logits, int ld, int M, int V, const int32_t* 
     }
     int nclusters = resident;
     if (nclusters > M) nclusters = M;
-    kern<<<nclusters * CE_CLUSTER, CE_THREADS, smem, stream>>>(z, ld, M, V, labels, weights, row_loss);
+    le = launch_kernel(kern, dim3(nclusters * CE_CLUSTER), dim3(CE_THREADS), smem, stream, z, ld, M, V, labels, weights, row_loss);
   } else
-    masked_ce_wide_kernel<<<M, 256, 0, stream>>>(z, ld, M, V, labels, weights, row_loss);
+    le = launch_kernel(masked_ce_wide_kernel, dim3(M), dim3(256), 0, stream, z, ld, M, V, labels, weights, row_loss);
+  PLB_REQUIRE(le == cudaSuccess, PLB_ERR_CUDA, "plb_masked_ce: launch failed: %s", cudaGetErrorString(le));
   int rc = check_launch("plb_masked_ce");
   if (rc) return rc;
-  sum_rows_kernel<<<1, 1024, 0, stream>>>(row_loss, M, loss_out, accumulate);
+  le = launch_kernel(sum_rows_kernel, dim3(1), dim3(1024), 0, stream, static_cast<const float*>(row_loss), M, loss_out, accumulate);
+  PLB_REQUIRE(le == cudaSuccess, PLB_ERR_CUDA, "plb_masked_ce(sum): launch failed: %s", cudaGetErrorString(le));
   return check_launch("plb_masked_ce(sum)");
 }
 

@@ -16,6 +16,7 @@ adamw_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m
              __nv_bfloat16* __restrict__ shadow, long n, float beta1, float beta2, float one_minus_beta1,
              float one_minus_beta2, float eps, float decay, float step_size, float inv_bc2_sqrt, float grad_scale,
              int zero_grad) {
+  pdl_grid_sync();
   const long n4 = n >> 2;
   const long stride = static_cast<long>(gridDim.x) * blockDim.x;
   for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < n4; i += stride) {
@@ -88,10 +89,11 @@ extern "C" int plb_adamw_step(float* params, float* grads, float* exp_avg, float
   const float step_size = static_cast<float>(lr / bc1);
   const float inv_bc2_sqrt = static_cast<float>(1.0 / sqrt(bc2));
   const float decay = static_cast<float>(1.0 - lr * weight_decay);
-  adamw_kernel<<<flat_grid(n / 4), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      params, grads, exp_avg, exp_avg_sq, static_cast<__nv_bfloat16*>(bf16_shadow), n, static_cast<float>(beta1),
-      static_cast<float>(beta2), static_cast<float>(1.0 - beta1), static_cast<float>(1.0 - beta2), static_cast<float>(eps),
-      decay, step_size, inv_bc2_sqrt, static_cast<float>(grad_scale), zero_grad);
+  cudaError_t e = launch_kernel(adamw_kernel, dim3(flat_grid(n / 4)), dim3(256), 0, static_cast<cudaStream_t>(stream), params, grads,
+                                exp_avg, exp_avg_sq, static_cast<__nv_bfloat16*>(bf16_shadow), n, static_cast<float>(beta1),
+                                static_cast<float>(beta2), static_cast<float>(1.0 - beta1), static_cast<float>(1.0 - beta2),
+                                static_cast<float>(eps), decay, step_size, inv_bc2_sqrt, static_cast<float>(grad_scale), zero_grad);
+  PLB_REQUIRE(e == cudaSuccess, PLB_ERR_CUDA, "plb_adamw_step: launch failed: %s", cudaGetErrorString(e));
   return check_launch("plb_adamw_step");
 }
 

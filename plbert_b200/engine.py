@@ -287,6 +287,11 @@ class Engine:
              ptr(aux_out), ld_out, _stream())
         self.launches += 1
 
+    def _zero(self, t: torch.Tensor) -> None:
+        """t[...] = 0 with the library's own fill kernel (t contiguous): the step launches no ATen kernel."""
+        call("plb_fill_zero", t.data_ptr(), t.numel() * t.element_size(), _stream())
+        self.launches += 1
+
     def _head_wgrad(self, head: str, V: int, H: int, m: int, logits, ldv: int) -> None:
         """dW_head += dz^T h_rows — into this rank's arena, or (data parallel on NVSwitch) into every rank's at once."""
         mc = self.grad_multicast.get(head + ".weight")
@@ -422,7 +427,7 @@ class Engine:
         self.grads_clean = False
         self.have_grads = True
         dy = self.d_y
-        dy[:T].zero_()
+        self._zero(dy[:T])
         loss_started = False
 
         self._before_head_backward()
@@ -450,7 +455,7 @@ class Engine:
             call("plb_scatter_add_rows", ptr(self.dh_rows), H, ptr(b.rows), M, H, ptr(dy), H, s)
             self.launches += 1
         elif masked_heads:
-            self.loss_buf.zero_()   # masked heads contribute 0 (every sample's mask set is empty)
+            self._zero(self.loss_buf)   # masked heads contribute 0 (every sample's mask set is empty)
             loss_started = True
         # ---- heads over every valid position (upstream word loss), chunked ---------------------------------------------
         if n_all:
@@ -466,7 +471,7 @@ class Engine:
         inside the bucket all-reduces and will run AdamW on the averaged gradient, so this rank joins both collectives
         with its all-zero contribution and steps like everybody else (DDP semantics, R/train.py:160,218-221) — returning
         early would hang the other ranks and let the replicas drift apart."""
-        self.loss_buf.zero_()
+        self._zero(self.loss_buf)
         if not self.always_reduce:
             self.have_grads = False
             return
@@ -506,7 +511,7 @@ class Engine:
     def begin_backward(self) -> None:
         """Gradients accumulate in place (12 applications of the shared layer), so the arena must start at zero."""
         if not self.grads_clean:
-            self.grads[:self.layout.trainable_end].zero_()
+            self._zero(self.grads[:self.layout.trainable_end])
             self.grads_clean = True
 
     def encoder_backward(self, b: DeviceBatch) -> None:
@@ -561,7 +566,7 @@ class Engine:
                      self.gp[att + "dense.bias"], s)
             self._gemm(GEMM_WGRAD, EPI_NONE, H, H, T, d_proj, H, A["ctx"], H, self.gp[att + "dense.weight"], H)
             # dO = dz Wo, and in the same epilogue attention's delta[h, row] = sum_d dO o O over each head's 64 columns
-            delta_flat[:nh * T].zero_()
+            self._zero(delta_flat[:nh * T])
             self._gemm(GEMM_DGRAD, EPI_ROWDOT, T, H, H, d_proj, H, self.wp[att + "dense.weight"], H, self.d_ctx, H,
                        aux_in=A["ctx"], ld_in=H, aux_out=self.delta, ld_out=T)
             # one kernel: S^T / dP^T and the exponentials are computed once for dQ, dK and dV (attn_bwd_fused.cu).  ctx = NULL:

@@ -597,6 +597,16 @@ def test_colsum(dev, T, N):
     assert rel(out - 1, x[:, :N].float().sum(0)) < 1e-4
 
 
+@pytest.mark.parametrize("nbytes,offset", [(1, 0), (15, 1), (16, 0), (4, 4), (1000, 3), (4096, 0), (1 << 20, 8), ((1 << 22) + 5, 7)])
+def test_fill_zero(dev, nbytes, offset):
+    """plb_fill_zero: exactly [dst, dst + bytes) is zeroed, any alignment (guard bytes on both sides stay untouched)."""
+    buf = torch.full((nbytes + offset + 64,), 0xAB, dtype=torch.uint8, device=dev)
+    call("plb_fill_zero", buf.data_ptr() + offset, nbytes, S())
+    assert not buf[offset:offset + nbytes].any()
+    assert (buf[:offset] == 0xAB).all() and (buf[offset + nbytes:] == 0xAB).all()
+    call("plb_fill_zero", buf.data_ptr(), 0, S())   # nothing to do
+
+
 # ------------------------------------------------------------------------------------------ AdamW
 def test_adamw_matches_torch(dev):
     n = 4096 * 3 + 64
