@@ -471,7 +471,7 @@ class Engine:
         inside the bucket all-reduces and will run AdamW on the averaged gradient, so this rank joins both collectives
         with its all-zero contribution and steps like everybody else (DDP semantics, R/train.py:160,218-221) — returning
         early would hang the other ranks and let the replicas drift apart."""
-        self._zero(self.loss_buf)
+        self.loss_buf.zero_()   # (a torch fill: this path also runs on the CPU stand-ins of tests/test_ddp_gloo.py)
         if not self.always_reduce:
             self.have_grads = False
             return
