@@ -369,7 +369,7 @@ embed_ln_fwd_kernel(const int32_t* __restrict__ ids, const int32_t* __restrict__
 // CTA and flushed once, because a handful of rows (mask, separator) receive ~30 % of all tokens and would otherwise
 // serialise in the L2 atomic units.
 template <bool kSmemWord>
-__global__ void __launch_bounds__(WARPS * 32)
+__global__ void __launch_bounds__(WARPS * 32, 2)   // two CTAs per SM: the kernel waits on dependent gathers (ids -> table rows)
 embed_ln_bwd_kernel(const __nv_bfloat16* __restrict__ de, const int32_t* __restrict__ ids,
                     const int32_t* __restrict__ pos, int T, int E, const float* __restrict__ word,
                     const float* __restrict__ posemb, const float* __restrict__ type0, const float* __restrict__ w,
@@ -565,7 +565,10 @@ extern "C" int plb_embed_ln_bwd(const void* de, const int32_t* ids, const int32_
       configured = true;
     }
     const int need = (T + WARPS - 1) / WARPS;
-    embed_ln_bwd_kernel<true><<<need < sm_count() ? need : sm_count(), WARPS * 32, big, st>>>(
+    // one private copy of the word-table gradient per CTA; two CTAs per SM when two copies fit (the 188 x 128 table: 2 x 98 KB)
+    const int per_sm = 2 * (big + 1024) <= 227 * 1024 ? 2 : 1;
+    const int cap = sm_count() * per_sm;
+    embed_ln_bwd_kernel<true><<<need < cap ? need : cap, WARPS * 32, big, st>>>(
         static_cast<const __nv_bfloat16*>(de), ids, pos, T, E, word, posemb, type0, ln_w, stats, pad_id, V, dword, dpos,
         dtype0, dln_w, dln_b);
   } else {
