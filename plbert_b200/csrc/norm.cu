@@ -318,9 +318,17 @@ embed_ln_fwd_kernel(const int32_t* __restrict__ ids, const int32_t* __restrict__
                     float* __restrict__ stats) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int nchunk = E >> 2;
-  for (int row = blockIdx.x * WARPS + warp; row < T; row += gridDim.x * WARPS) {
-    const float4* wr = reinterpret_cast<const float4*>(word + static_cast<size_t>(ids[row]) * E);
-    const float4* pr = reinterpret_cast<const float4*>(posemb + static_cast<size_t>(pos[row]) * E);
+  // the table rows are gathers that depend on ids[row] / pos[row]: the indices of the warp's NEXT row are requested one row ahead
+  const int row0 = blockIdx.x * WARPS + warp, rstride = gridDim.x * WARPS;
+  int id_nxt = row0 < T ? __ldg(ids + row0) : 0, ps_nxt = row0 < T ? __ldg(pos + row0) : 0;
+  for (int row = row0; row < T; row += rstride) {
+    const int id_cur = id_nxt, ps_cur = ps_nxt;
+    if (row + rstride < T) {
+      id_nxt = __ldg(ids + row + rstride);
+      ps_nxt = __ldg(pos + row + rstride);
+    }
+    const float4* wr = reinterpret_cast<const float4*>(word + static_cast<size_t>(id_cur) * E);
+    const float4* pr = reinterpret_cast<const float4*>(posemb + static_cast<size_t>(ps_cur) * E);
     const float4* tr = reinterpret_cast<const float4*>(type0);
     float x[EMAXC][4];
     float sum = 0.f;
@@ -393,12 +401,25 @@ embed_ln_bwd_kernel(const __nv_bfloat16* __restrict__ de, const int32_t* __restr
     }
   }
   const float invE = 1.f / E;
-  for (int row = blockIdx.x * WARPS + warp; row < T; row += gridDim.x * WARPS) {
-    const int id = ids[row], ps = pos[row];
+  // indices and statistics of the warp's NEXT row are requested one row ahead (the table rows are dependent gathers)
+  const int row0 = blockIdx.x * WARPS + warp, rstride = gridDim.x * WARPS;
+  int id_nxt = 0, ps_nxt = 0;
+  float mean_nxt = 0.f, rstd_nxt = 0.f;
+  if (row0 < T) {
+    id_nxt = __ldg(ids + row0); ps_nxt = __ldg(pos + row0);
+    mean_nxt = __ldg(stats + 2 * row0); rstd_nxt = __ldg(stats + 2 * row0 + 1);
+  }
+  for (int row = row0; row < T; row += rstride) {
+    const int id = id_nxt, ps = ps_nxt;
+    const float mean = mean_nxt, rstd = rstd_nxt;
+    if (row + rstride < T) {
+      const int nr = row + rstride;
+      id_nxt = __ldg(ids + nr); ps_nxt = __ldg(pos + nr);
+      mean_nxt = __ldg(stats + 2 * nr); rstd_nxt = __ldg(stats + 2 * nr + 1);
+    }
     const float4* wr = reinterpret_cast<const float4*>(word + static_cast<size_t>(id) * E);
     const float4* pr = reinterpret_cast<const float4*>(posemb + static_cast<size_t>(ps) * E);
     const float4* tr = reinterpret_cast<const float4*>(type0);
-    const float mean = stats[2 * row], rstd = stats[2 * row + 1];
     float xh[EMAXC][4], g[EMAXC][4];
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
